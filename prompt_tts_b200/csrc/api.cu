@@ -1,0 +1,27 @@
+// Error reporting, version and device check for the prompt_tts_b200 C ABI.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void pt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int pt_version(void) { return 1; }
+extern "C" const char* pt_last_error(void) { return g_err; }
+
+extern "C" int pt_check_device(int dev) {
+  cudaDeviceProp prop;
+  PT_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    pt_set_error("device %d is sm_%d%d; this library only contains sm_100a code", dev, prop.major, prop.minor);
+    return PT_EARCH;
+  }
+  return PT_OK;
+}

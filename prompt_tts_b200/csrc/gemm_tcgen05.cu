@@ -1,0 +1,493 @@
+// tcgen05 / TMEM / TMA GEMM family for sm_100a.
+//
+//   out[z, m, n] = alpha * sum_seg sum_k A_seg[m + shift, k] * B_seg[n, k]  (+ bias, + per-batch bias, + residual)
+//
+// One CTA per 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor.4d into a ring of SWIZZLE_128B stages
+//   warp 1   MMA issuer:   one thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32 in TMEM)
+//   warp 2-5 epilogue:     tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+// Operands may be K-major or MN-major (UMMA descriptors handle the transposed case), so the same kernel
+// serves forward (K-major x K-major), data-gradient (K-major x MN-major) and weight-gradient
+// (MN-major x MN-major, contraction over rows and batch) GEMMs, k=3 convolutions as three shifted
+// segments (TMA out-of-bounds zero fill = conv padding), and the batched attention contractions.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct alignas(64) KParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[2];
+  pt_segment_t seg[8];
+  int nseg;
+  int a_kmajor, b_kmajor;
+  int a_batched[2], b_batched[2];
+  int M, N, nz2, nz3, splitk;
+  int total_iters, iters_per_split;
+  void* out;
+  int out_dtype;
+  long long osm, osz2, osz3;
+  float alpha;
+  const float* bias;
+  const float* bias_z2;
+  const bf16* res;
+  long long rsm, rsz2, rsz3;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 22)) __trap();  // a dead pipeline becomes a launch error, not a hang
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version (sm_100)
+  d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int BN_S = (BN + 63) / 64 * 64;       // smem rows reserved for B (MN-major needs whole 64-blocks)
+  static constexpr int B_STAGE_BYTES = BN_S * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BN <= 64 ? 4 : (BN <= 128 ? 3 : 4);
+  static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  // barriers: full[S], empty[S], tmem_full ; then tmem ptr slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  int z = blockIdx.z;
+  const int zs = z % p.splitk;
+  z /= p.splitk;
+  const int z2 = z % p.nz2;
+  const int z3 = z / p.nz2;
+
+  const int it_begin = zs * p.iters_per_split;
+  const int it_end = min(p.total_iters, it_begin + p.iters_per_split);
+  const int n_iters = it_end - it_begin;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0 && n_iters > 0) {
+      // locate (seg, rep, kb) of it_begin
+      int seg = 0, rep = 0, kb = 0, skip = it_begin;
+      while (true) {
+        const int nkb = (p.seg[seg].nk + BK - 1) / BK;
+        const int cnt = nkb * p.seg[seg].nrep;
+        if (skip < cnt) {
+          rep = skip / nkb;
+          kb = skip % nkb;
+          break;
+        }
+        skip -= cnt;
+        ++seg;
+      }
+      const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_kmajor ? BN * BK * 2 : C::B_STAGE_BYTES);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % C::STAGES;
+        const uint32_t ph = (it / C::STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), tx_bytes);
+        const pt_segment_t& sg = p.seg[seg];
+        const uint32_t sa = smem_base + s * C::STAGE_BYTES;
+        const uint32_t sb = sa + A_STAGE_BYTES;
+        const CUtensorMap* ta = &p.tmA[sg.a_idx];
+        const CUtensorMap* tb = &p.tmB[sg.b_idx];
+        const int bz2 = sg.rep_is_batch ? (sg.rep_c2_0 + rep) : z2;
+        const int a2 = p.a_batched[sg.a_idx] ? bz2 : 0, a3 = p.a_batched[sg.a_idx] ? z3 : 0;
+        const int b2 = p.b_batched[sg.b_idx] ? bz2 : 0, b3 = p.b_batched[sg.b_idx] ? z3 : 0;
+        const int ka = sg.a_k0 + kb * BK, kbb = sg.b_k0 + kb * BK;
+        if (p.a_kmajor) {
+          tma_load_4d(sa, ta, full_bar(s), ka, m0 + sg.a_mn_shift, a2, a3);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_4d(sa + j * (BK * 128), ta, full_bar(s), m0 + sg.a_mn_shift + j * 64, ka, a2, a3);
+        }
+        if (p.b_kmajor) {
+          tma_load_4d(sb, tb, full_bar(s), kbb, n0 + sg.b_mn_shift, b2, b3);
+        } else {
+#pragma unroll
+          for (int j = 0; j < C::BN_S / 64; ++j) tma_load_4d(sb + j * (BK * 128), tb, full_bar(s), n0 + sg.b_mn_shift + j * 64, kbb, b2, b3);
+        }
+        // advance (seg, rep, kb)
+        const int nkb = (sg.nk + BK - 1) / BK;
+        if (++kb == nkb) {
+          kb = 0;
+          if (++rep == sg.nrep) {
+            rep = 0;
+            ++seg;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0 && n_iters > 0) {
+      // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.a_kmajor ? 0u : 1u) << 15) | ((p.b_kmajor ? 0u : 1u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_lbo = p.a_kmajor ? 0u : (uint32_t)(BK * 128), b_lbo = p.b_kmajor ? 0u : (uint32_t)(BK * 128);
+      const uint32_t a_kstep = p.a_kmajor ? 32u : 2048u, b_kstep = p.b_kmajor ? 32u : 2048u;  // bytes per UMMA_K=16
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % C::STAGES;
+        const uint32_t ph = (it / C::STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_base + s * C::STAGE_BYTES;
+        const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t ad = umma_desc(sa + k * a_kstep, a_lbo, 1024);
+          const uint64_t bd = umma_desc(sb + k * b_kstep, b_lbo, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (n_iters > 0) {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + q * 32 + lane;
+    const bool m_ok = m < p.M;
+    const long long out_off = (long long)z2 * p.osz2 + (long long)z3 * p.osz3 + (long long)m * p.osm;
+    const long long res_off = (long long)z2 * p.rsz2 + (long long)z3 * p.rsz3 + (long long)m * p.rsm;
+    const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.N : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= p.N) break;  // warp-uniform
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
+      }
+      if (bz) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.N) f[j] += __ldg(bz + nb + j);
+      }
+      if (m_ok) {
+      if (p.res) {
+        const bf16* r = p.res + res_off + nb;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (nb + g * 8 < p.N) {
+            float t[8];
+            load8(r + g * 8, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[g * 8 + j] += t[j];
+          }
+        }
+      }
+      if (p.out_dtype == PT_OUT_BF16) {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + out_off + nb;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (nb + g * 8 < p.N) store8(o + g * 8, f + g * 8);
+      } else if (p.out_dtype == PT_OUT_F32) {
+        float* o = reinterpret_cast<float*>(p.out) + out_off + nb;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+        {
+          if (nb + g * 4 + 4 <= p.N) {
+            *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (nb + g * 4 + j < p.N) o[g * 4 + j] = f[g * 4 + j];
+          }
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + out_off + nb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.N) atomicAdd(o + j, f[j]);
+      }
+      }  // m_ok
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+int encode_operand(CUtensorMap* tm, const pt_operand_t& op, int box_rows_kmajor, const char* name) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    pt_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return PT_ECUDA;
+  }
+  PT_REQUIRE(op.ptr != nullptr, "gemm operand %s: null pointer", name);
+  PT_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "gemm operand %s: base not 16-byte aligned", name);
+  PT_REQUIRE(op.stride[0] == 1, "gemm operand %s: dim[0] must be contiguous", name);
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4] = {64, 1, 1, 1}, estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    PT_REQUIRE(op.dim[i] >= 1 && op.dim[i] < (1ll << 31), "gemm operand %s: dim[%d]=%lld out of range", name, i, (long long)op.dim[i]);
+    dims[i] = (cuuint64_t)op.dim[i];
+  }
+  for (int i = 1; i < 4; ++i) {
+    long long st = op.stride[i];
+    if (op.dim[i] == 1 && (st <= 0 || (st % 8) != 0)) st = 8;  // irrelevant axis, keep the encoder happy
+    PT_REQUIRE(st > 0 && st % 8 == 0, "gemm operand %s: stride[%d]=%lld must be a positive multiple of 8 elements", name, i, st);
+    strides[i - 1] = (cuuint64_t)st * 2;
+  }
+  box[1] = op.kmajor ? (cuuint32_t)box_rows_kmajor : 64u;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pt_set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d (dims %lld,%lld,%lld,%lld strides %lld,%lld,%lld box %u,%u)", name, (int)r,
+                 (long long)dims[0], (long long)dims[1], (long long)dims[2], (long long)dims[3], (long long)strides[0],
+                 (long long)strides[1], (long long)strides[2], box[0], box[1]);
+    return PT_ECUDA;
+  }
+  return PT_OK;
+}
+
+template <int BN>
+int launch(const KParams& kp, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_kernel<BN><<<grid, 192, Cfg<BN>::SMEM_BYTES, st>>>(kp);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+
+}  // namespace
+
+extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
+  PT_REQUIRE(g != nullptr, "pt_gemm: null descriptor");
+  PT_REQUIRE(g->nseg >= 1 && g->nseg <= 8, "pt_gemm: nseg=%d", g->nseg);
+  PT_REQUIRE(g->M >= 1 && g->N >= 1, "pt_gemm: M=%d N=%d", g->M, g->N);
+  PT_REQUIRE(g->nz2 >= 1 && g->nz3 >= 1 && g->splitk >= 1, "pt_gemm: bad batch/split");
+  PT_REQUIRE(g->out != nullptr, "pt_gemm: null output");
+  PT_REQUIRE(g->splitk == 1 || g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: split-K needs PT_OUT_F32_ATOMIC_ADD");
+  PT_REQUIRE(g->splitk == 1 || (g->bias == nullptr && g->bias_z2 == nullptr && g->residual == nullptr), "pt_gemm: split-K with bias/residual");
+  if (g->out_dtype == PT_OUT_BF16) {
+    PT_REQUIRE(g->N % 8 == 0 && g->out_stride_m % 8 == 0 && g->out_stride_z2 % 8 == 0 && g->out_stride_z3 % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(g->out) & 15) == 0,
+               "pt_gemm: bf16 output needs N, strides multiples of 8 and a 16-byte aligned base (N=%d)", g->N);
+  } else if (g->out_dtype == PT_OUT_F32) {
+    PT_REQUIRE(g->out_stride_m % 4 == 0 && g->out_stride_z2 % 4 == 0 && g->out_stride_z3 % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(g->out) & 15) == 0,
+               "pt_gemm: f32 output needs N, strides multiples of 4 (N=%d)", g->N);
+  } else {
+    PT_REQUIRE(g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: out_dtype=%d", g->out_dtype);
+  }
+  if (g->residual) {
+    PT_REQUIRE(g->N % 8 == 0 && g->res_stride_m % 8 == 0 && g->res_stride_z2 % 8 == 0 && g->res_stride_z3 % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0,
+               "pt_gemm: residual alignment");
+  }
+
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  bool a_used[2] = {false, false}, b_used[2] = {false, false};
+  long long total = 0;
+  for (int i = 0; i < g->nseg; ++i) {
+    const pt_segment_t& s = g->seg[i];
+    PT_REQUIRE(s.a_idx >= 0 && s.a_idx < 2 && s.b_idx >= 0 && s.b_idx < 2, "pt_gemm: segment %d operand index", i);
+    PT_REQUIRE(s.nk >= 1 && s.nrep >= 1, "pt_gemm: segment %d nk=%d nrep=%d", i, s.nk, s.nrep);
+    a_used[s.a_idx] = true;
+    b_used[s.b_idx] = true;
+    kp.seg[i] = s;
+    total += (long long)((s.nk + BK - 1) / BK) * s.nrep;
+  }
+  PT_REQUIRE(total < (1ll << 30), "pt_gemm: too many k iterations");
+  const int a0 = a_used[0] ? 0 : 1, b0 = b_used[0] ? 0 : 1;
+  kp.a_kmajor = g->a[a0].kmajor;
+  kp.b_kmajor = g->b[b0].kmajor;
+  for (int i = 0; i < 2; ++i) {
+    if (a_used[i]) PT_REQUIRE(g->a[i].kmajor == kp.a_kmajor, "pt_gemm: A operands must share one majorness");
+    if (b_used[i]) PT_REQUIRE(g->b[i].kmajor == kp.b_kmajor, "pt_gemm: B operands must share one majorness");
+  }
+
+  // tile width
+  int bn = g->block_n;
+  const long long mt = (g->M + BM - 1) / BM;
+  const long long zz = (long long)g->nz2 * g->nz3 * g->splitk;
+  if (bn == 0) {
+    const int sms = pt_num_sms();
+    if (g->N % 256 == 0 && mt * (g->N / 256) * zz >= sms) bn = 256;
+    else if (kp.b_kmajor && g->N % 160 == 0 && g->N % 128 != 0 && mt * (g->N / 160) * zz >= sms / 2) bn = 160;
+    else if (g->N > 64 && (g->N % 128 == 0 || g->N % 128 > 64 || g->N > 512)) bn = 128;
+    else bn = 64;
+  }
+  PT_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "pt_gemm: block_n=%d", bn);
+
+  for (int i = 0; i < 2; ++i) {
+    if (a_used[i]) {
+      int r = encode_operand(&kp.tmA[i], g->a[i], BM, i ? "A1" : "A0");
+      if (r) return r;
+      kp.a_batched[i] = g->a[i].batched;
+    }
+    if (b_used[i]) {
+      int r = encode_operand(&kp.tmB[i], g->b[i], bn, i ? "B1" : "B0");
+      if (r) return r;
+      kp.b_batched[i] = g->b[i].batched;
+    }
+  }
+  kp.nseg = g->nseg;
+  kp.M = g->M;
+  kp.N = g->N;
+  kp.nz2 = g->nz2;
+  kp.nz3 = g->nz3;
+  kp.total_iters = (int)total;
+  kp.iters_per_split = (int)((total + g->splitk - 1) / g->splitk);
+  kp.splitk = (int)((total + kp.iters_per_split - 1) / kp.iters_per_split);
+  kp.out = g->out;
+  kp.out_dtype = g->out_dtype;
+  kp.osm = g->out_stride_m;
+  kp.osz2 = g->out_stride_z2;
+  kp.osz3 = g->out_stride_z3;
+  kp.alpha = g->alpha;
+  kp.bias = g->bias;
+  kp.bias_z2 = g->bias_z2;
+  kp.res = reinterpret_cast<const bf16*>(g->residual);
+  kp.rsm = g->res_stride_m;
+  kp.rsz2 = g->res_stride_z2;
+  kp.rsz3 = g->res_stride_z3;
+
+  const long long gz = (long long)g->nz2 * g->nz3 * kp.splitk;
+  PT_REQUIRE(gz <= 65535, "pt_gemm: grid.z=%lld too large", gz);
+  const long long gy = (g->N + bn - 1) / bn;
+  PT_REQUIRE(gy <= 65535, "pt_gemm: grid.y too large");
+  dim3 grid((unsigned)mt, (unsigned)gy, (unsigned)gz);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 64: return launch<64>(kp, grid, st);
+    case 128: return launch<128>(kp, grid, st);
+    case 160: return launch<160>(kp, grid, st);
+    default: return launch<256>(kp, grid, st);
+  }
+}
