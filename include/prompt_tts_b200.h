@@ -97,9 +97,10 @@ typedef struct {
   int64_t out_stride_m, out_stride_z2, out_stride_z3; /* elements */
   float alpha;
   const float* bias;       /* [N] fp32 or NULL */
-  const float* bias_z2;    /* [nz2, N] fp32 or NULL (time-embedding shift) */
+  const float* bias_z2;    /* [nz2, >=N] fp32 rows of stride bias_z2_stride, or NULL (time-embedding shift) */
   const void* residual;    /* bf16, same indexing as out with its own strides, or NULL */
   int64_t res_stride_m, res_stride_z2, res_stride_z3;
+  int64_t bias_z2_stride;  /* elements; 0 means N */
 } pt_gemm_t;
 
 int pt_gemm(const pt_gemm_t* g, void* stream);
@@ -154,8 +155,8 @@ int pt_pack_conv_weight(const float* w, void* wp, int Co, int Ci, int k, void* s
 int pt_unpack_conv_wgrad(const float* gp, float* g, int Co, int Ci, int k, int accumulate, void* stream);
 /* column sums of a bf16 matrix: out[c] += sum_r x[r, c]  (bias gradients) */
 int pt_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int cols, void* stream);
-/* per-(batch, channel) sum over L of dy[B, L, C] (time-shift gradient): out[b, c] fp32 (overwritten) */
-int pt_batch_colsum_bf16(const void* x, float* out, int B, int L, int C, void* stream);
+/* per-(batch, channel) sum over L of dy[B, L, C] (time-shift gradient): out[b * out_stride + c] fp32 (overwritten) */
+int pt_batch_colsum_bf16(const void* x, float* out, int64_t out_stride, int B, int L, int C, void* stream);
 
 /* conv_in: x[B, L, Cin<=16] fp32 channels-last... k=3 pad 1 -> y[B, L, Co] bf16 (tts/ldm/unet_1d_condition.py:193,654) */
 int pt_conv_in_fwd(const float* x_ncl, const float* w, const float* bias, void* y, int B, int Cin, int L, int Co, void* stream);
@@ -184,6 +185,9 @@ int pt_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* d
  * Distances are evaluated exactly as the reference does: -(|r|^2 - 2 r.e + |e|^2) in fp32, the dot
  * product accumulated in ascending d order with fused multiply-add. */
 int pt_rvq_encode(const float* latents, const float* codebooks, int64_t* codes, int B, int D, int T, int Q, int K, void* stream);
+/* allocation-free variant: cb_sq is caller scratch [Q, K] fp32 (pt_rvq_encode keeps one library-owned table instead) */
+int pt_rvq_encode_ws(const float* latents, const float* codebooks, float* cb_sq, int64_t* codes, int B, int D, int T, int Q, int K, void* stream);
+int pt_rvq_cb_sq(const float* codebooks, float* out, int Q, int K, int D, void* stream);
 /* latents[b, :, t] = sum_q E[q, codes[b,q,t], :]  (q ascending, fp32) */
 int pt_rvq_decode(const int64_t* codes, const float* codebooks, float* latents, int B, int D, int T, int Q, int K, void* stream);
 /* x0 = (codes / 1023 - 0.5) / 0.5  as fp32, and its inverse  codes = clamp(round((x + 1) * 511.5), 0, 1023) */

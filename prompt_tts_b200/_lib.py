@@ -29,7 +29,8 @@ class Gemm(C.Structure):
                 ("out", C.c_void_p), ("out_dtype", C.c_int32),
                 ("out_stride_m", C.c_int64), ("out_stride_z2", C.c_int64), ("out_stride_z3", C.c_int64),
                 ("alpha", C.c_float), ("bias", C.c_void_p), ("bias_z2", C.c_void_p), ("residual", C.c_void_p),
-                ("res_stride_m", C.c_int64), ("res_stride_z2", C.c_int64), ("res_stride_z3", C.c_int64)]
+                ("res_stride_m", C.c_int64), ("res_stride_z2", C.c_int64), ("res_stride_z3", C.c_int64),
+                ("bias_z2_stride", C.c_int64)]
 
 
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC_ADD = 0, 1, 2
@@ -63,3 +64,73 @@ def call(name: str, *args) -> None:
     """Call `pt_<name>` with ctypes-converted args and raise on a non-zero return."""
     fn = getattr(lib(), "pt_" + name)
     check(fn(*args), "pt_" + name)
+
+
+# ---------------------------------------------------------------------------------------------
+# argtypes for every entry point of include/prompt_tts_b200.h  (p = pointer, i = int, l = int64, f = float)
+# ---------------------------------------------------------------------------------------------
+_SIGS = {
+    "check_device": "i",
+    "gemm": "pp",
+    "groupnorm_stats": "ppiiiifp",
+    "groupnorm_apply": "pppppiiiiip",
+    "groupnorm_bwd": "pppppppppiiiiip",
+    "layernorm_fwd": "ppppplifp",
+    "layernorm_bwd": "pppppppplip",
+    "softmax_fwd": "pplillp",
+    "softmax_bwd": "ppplillfp",
+    "geglu_fwd": "pplip",
+    "geglu_bwd": "ppplip",
+    "add_bf16": "ppplp",
+    "silu_f32_to_bf16": "pplp",
+    "silu_bwd_f32": "ppplp",
+    "copy2d_bf16": "plpllip",
+    "upsample2_fwd": "ppiiip",
+    "upsample2_bwd": "ppiiip",
+    "ncl_f32_to_nlc_bf16": "ppiiip",
+    "nlc_bf16_to_ncl_f32": "ppiiip",
+    "cast_f32_to_bf16": "pplp",
+    "cast_bf16_to_f32": "pplp",
+    "pack_conv_weight": "ppiiip",
+    "unpack_conv_wgrad": "ppiiiip",
+    "colsum_bf16": "plplip",
+    "batch_colsum_bf16": "ppliiip",
+    "conv_in_fwd": "ppppiiiip",
+    "conv_in_bwd": "ppppiiiip",
+    "conv_out_fwd": "ppppiiiip",
+    "conv_out_bwd": "ppppppiiiip",
+    "time_sinusoid": "ppiip",
+    "text_embed_fwd": "ppppiiiip",
+    "text_embed_bwd": "pppiiiip",
+    "add_noise": "ppppppilp",
+    "mse_fwd_bwd": "pppplfp",
+    "rvq_encode": "pppiiiiip",
+    "rvq_encode_ws": "ppppiiiiip",
+    "rvq_cb_sq": "ppiiip",
+    "rvq_decode": "pppiiiiip",
+    "codes_affine": "pplp",
+    "codes_affine_inv": "pplp",
+    "sumsq_f32": "plpp",
+    "adamw_step": "pppplfffffipffp",
+}
+_CT = {"p": C.c_void_p, "i": C.c_int, "l": C.c_int64, "f": C.c_float}
+EXPORTS = ["pt_version", "pt_last_error"] + ["pt_" + k for k in _SIGS]
+
+
+def _bind(l):
+    for name, sig in _SIGS.items():
+        fn = getattr(l, "pt_" + name)
+        fn.argtypes = [_CT[c] for c in sig]
+        fn.restype = C.c_int
+
+
+_orig_lib = lib
+
+
+def lib():  # noqa: F811  (wraps the loader above with argtype binding)
+    global _lib
+    first = _lib is None
+    l = _orig_lib()
+    if first:
+        _bind(l)
+    return l

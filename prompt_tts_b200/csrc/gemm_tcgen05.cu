@@ -39,6 +39,7 @@ struct alignas(64) KParams {
   const float* bias_z2;
   const bf16* res;
   long long rsm, rsz2, rsz3;
+  long long bz2_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
     const bool m_ok = m < p.M;
     const long long out_off = (long long)z2 * p.osz2 + (long long)z3 * p.osz3 + (long long)m * p.osm;
     const long long res_off = (long long)z2 * p.rsz2 + (long long)z3 * p.rsz3 + (long long)m * p.rsm;
-    const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.N : nullptr;
+    const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.bz2_stride : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int nb = n0 + c * 32;
@@ -477,6 +478,7 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   kp.rsm = g->res_stride_m;
   kp.rsz2 = g->res_stride_z2;
   kp.rsz3 = g->res_stride_z3;
+  kp.bz2_stride = g->bias_z2_stride ? g->bias_z2_stride : g->N;
 
   const long long gz = (long long)g->nz2 * g->nz3 * kp.splitk;
   PT_REQUIRE(gz <= 65535, "pt_gemm: grid.z=%lld too large", gz);

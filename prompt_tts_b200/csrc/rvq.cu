@@ -1,0 +1,280 @@
+// Residual vector quantisation (EnCodec RVQ, 8 x 1024 x 128 at 6 kbps): nearest-codebook encode and
+// code -> latent embedding sum.
+//
+// Encode restates encodec's EuclideanCodebook.quantize: dist_j = -(|r|^2 - 2 r.e_j + |e_j|^2), argmax over j,
+// residual r -= e[idx], 8 stages.  The decisive comparison is done in exact fp32 (no TF32 / bf16): the dot
+// product is accumulated with fmaf in ascending d order and |r|^2, |e|^2 likewise, which is the order the
+// C oracle (oracle/rvq_oracle.c) uses, so codes are bit-identical to the oracle; the first index wins ties.
+// A tile of 128 frames stays in shared memory across all stages; codebooks (4 MB) stream from L2.
+//
+// Decode is a gather-sum: HBM-bound, 64 B of codes in and 512 B of fp32 latent out per frame.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TF = 128;   // frames per CTA
+constexpr int TC = 128;   // codes per inner tile
+constexpr int RD = 128;   // latent dimension (fixed by the tiling)
+
+__global__ void __launch_bounds__(256, 1) rvq_encode_kernel(const float* __restrict__ lat, const float* __restrict__ cb, const float* __restrict__ cb_sq,
+                                                            int64_t* __restrict__ codes, long long nframes, int T, int Q, int K) {
+  extern __shared__ float sh[];
+  float* sx = sh;                 // [RD][TF]   residual, d-major
+  float* se = sh + RD * TF;       // [RD][TC]   codebook tile, d-major
+  float* sxx = se + RD * TC;      // [TF]
+  float* sbv = sxx + TF;          // [16][TF] best value per code-column group
+  int* sbi = reinterpret_cast<int*>(sbv + 16 * TF);  // [16][TF]
+  int* sidx = sbi + 16 * TF;      // [TF] winning index of the stage
+
+  const int tid = threadIdx.x;
+  const long long f0 = (long long)blockIdx.x * TF;
+
+  // load the frame tile: lat[b, d, t] with frame f = b*T + t
+  for (int i = tid; i < RD * TF; i += 256) {
+    const int d = i / TF, fi = i % TF;
+    const long long f = f0 + fi;
+    float v = 0.f;
+    if (f < nframes) {
+      const long long b = f / T, t = f % T;
+      v = lat[(b * RD + d) * T + t];
+    }
+    sx[i] = v;
+  }
+  __syncthreads();
+
+  const int tf = tid % 16;   // frame group: frames tf*8 .. tf*8+7
+  const int tc = tid / 16;   // code group:  codes  tc*8 .. tc*8+7 of the tile
+
+  for (int q = 0; q < Q; ++q) {
+    // |r|^2 per frame, ascending d with fmaf (one thread per frame)
+    if (tid < TF) {
+      float s = 0.f;
+      for (int d = 0; d < RD; ++d) s = fmaf(sx[d * TF + tid], sx[d * TF + tid], s);
+      sxx[tid] = s;
+    }
+    float best[8];
+    int bidx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      best[i] = -INFINITY;
+      bidx[i] = 0;
+    }
+    const float* cbq = cb + (long long)q * K * RD;
+    for (int c0 = 0; c0 < K; c0 += TC) {
+      __syncthreads();  // previous tile fully consumed (also orders sxx / sx updates)
+      // codebook tile -> d-major shared
+      for (int i = tid; i < TC * (RD / 4); i += 256) {
+        const int c = i % TC, d4 = i / TC;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c < K) v = *reinterpret_cast<const float4*>(cbq + (long long)(c0 + c) * RD + d4 * 4);
+        se[(d4 * 4 + 0) * TC + c] = v.x;
+        se[(d4 * 4 + 1) * TC + c] = v.y;
+        se[(d4 * 4 + 2) * TC + c] = v.z;
+        se[(d4 * 4 + 3) * TC + c] = v.w;
+      }
+      __syncthreads();
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+      for (int d = 0; d < RD; ++d) {
+        const float4 xa = *reinterpret_cast<const float4*>(sx + d * TF + tf * 8);
+        const float4 xb = *reinterpret_cast<const float4*>(sx + d * TF + tf * 8 + 4);
+        const float4 ea = *reinterpret_cast<const float4*>(se + d * TC + tc * 8);
+        const float4 eb = *reinterpret_cast<const float4*>(se + d * TC + tc * 8 + 4);
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float ev[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv[i], ev[j], acc[i][j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int code = c0 + tc * 8 + j;
+        if (code < K) {
+          const float ee = __ldg(cb_sq + (long long)q * K + code);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // dist = -((xx - 2*dot) + ee), the reference's evaluation order, each step rounded to fp32
+            const float dist = -__fadd_rn(__fsub_rn(sxx[tf * 8 + i], __fmul_rn(2.f, acc[i][j])), ee);
+            if (dist > best[i]) {  // ascending code order within the thread: strict > keeps the first maximum
+              best[i] = dist;
+              bidx[i] = code;
+            }
+          }
+        }
+      }
+    }
+    // reduce over the 16 code groups: larger value wins, equal values -> smaller index
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sbv[tc * TF + tf * 8 + i] = best[i];
+      sbi[tc * TF + tf * 8 + i] = bidx[i];
+    }
+    __syncthreads();
+    if (tid < TF) {
+      float bv = sbv[tid];
+      int bi = sbi[tid];
+      for (int g = 1; g < 16; ++g) {
+        const float v = sbv[g * TF + tid];
+        const int ix = sbi[g * TF + tid];
+        if (v > bv || (v == bv && ix < bi)) {
+          bv = v;
+          bi = ix;
+        }
+      }
+      sidx[tid] = bi;
+      const long long f = f0 + tid;
+      if (f < nframes) {
+        const long long b = f / T, t = f % T;
+        codes[(b * Q + q) * T + t] = bi;
+      }
+    }
+    __syncthreads();
+    // residual update r -= e[idx]
+    for (int i = tid; i < RD * TF; i += 256) {
+      const int d = i / TF, fi = i % TF;
+      sx[i] = __fsub_rn(sx[i], __ldg(cbq + (long long)sidx[fi] * RD + d));
+    }
+    __syncthreads();
+  }
+}
+
+// |e|^2 per codebook entry, ascending d with fmaf
+__global__ void rvq_cb_sq_kernel(const float* __restrict__ cb, float* __restrict__ out, long long n, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s = fmaf(cb[i * D + d], cb[i * D + d], s);
+  out[i] = s;
+}
+
+// decode: one warp gathers the Q rows of a frame (float4 per lane), the CTA transposes 32 frames through
+// shared memory so that the [B, D, T] output is written in 128-byte runs along T.
+__global__ void rvq_decode_kernel(const int64_t* __restrict__ codes, const float* __restrict__ cb, float* __restrict__ lat, long long nframes,
+                                  int T, int Q, int K) {
+  __shared__ float tile[RD][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps
+  const long long ntiles = (nframes + 31) / 32;
+  for (long long tb = blockIdx.x; tb < ntiles; tb += gridDim.x) {
+    const long long f0 = tb * 32;
+    for (int fi = warp; fi < 32; fi += 8) {
+      const long long f = f0 + fi;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < nframes) {
+        const long long b = f / T, t = f % T;
+        for (int q = 0; q < Q; ++q) {
+          const long long c = codes[(b * Q + q) * T + t];
+          const float4 e = *reinterpret_cast<const float4*>(cb + ((long long)q * K + c) * RD + lane * 4);
+          acc.x += e.x;
+          acc.y += e.y;
+          acc.z += e.z;
+          acc.w += e.w;
+        }
+      }
+      tile[lane * 4 + 0][fi] = acc.x;
+      tile[lane * 4 + 1][fi] = acc.y;
+      tile[lane * 4 + 2][fi] = acc.z;
+      tile[lane * 4 + 3][fi] = acc.w;
+    }
+    __syncthreads();
+    const long long f = f0 + lane;
+    if (f < nframes) {
+      const long long b = f / T, t = f % T;
+      for (int d = warp; d < RD; d += 8) lat[(b * RD + d) * T + t] = tile[d][lane];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void codes_affine_kernel(const int64_t* __restrict__ codes, float* __restrict__ x0, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // dataloader.py:64,77,168-170: Normalize(0.5, 0.5)(codes / 1023) = (c/1023 - 0.5) / 0.5, each step rounded to fp32
+    const float u = __fdiv_rn((float)codes[i], 1023.f);
+    x0[i] = __fdiv_rn(__fsub_rn(u, 0.5f), 0.5f);
+  }
+}
+__global__ void codes_affine_inv_kernel(const float* __restrict__ x, int64_t* __restrict__ codes, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float c = rintf((x[i] + 1.f) * 511.5f);
+    codes[i] = (int64_t)fminf(fmaxf(c, 0.f), 1023.f);
+  }
+}
+
+float* g_cbsq = nullptr;
+size_t g_cbsq_cap = 0;
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" int pt_rvq_cb_sq(const float* codebooks, float* out, int Q, int K, int D, void* stream) {
+  PT_REQUIRE(Q > 0 && K > 0 && D > 0, "rvq_cb_sq: Q=%d K=%d D=%d", Q, K, D);
+  const long long n = (long long)Q * K;
+  rvq_cb_sq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST>>>(codebooks, out, n, D);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+
+// cb_sq: caller-provided [Q, K] fp32 scratch (filled here)
+extern "C" int pt_rvq_encode_ws(const float* latents, const float* codebooks, float* cb_sq, int64_t* codes, int B, int D, int T, int Q, int K,
+                                void* stream) {
+  PT_REQUIRE(B > 0 && T > 0 && Q > 0 && K > 0, "rvq_encode: B=%d T=%d Q=%d K=%d", B, T, Q, K);
+  PT_REQUIRE(D == RD, "rvq_encode: latent dimension must be %d (EnCodec), got %d", RD, D);
+  if (int r = pt_rvq_cb_sq(codebooks, cb_sq, Q, K, D, stream)) return r;
+  const size_t smem = sizeof(float) * (RD * TF + RD * TC + TF + 16 * TF) + sizeof(int) * (16 * TF + TF);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PT_CUDA_OK(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long long nframes = (long long)B * T;
+  rvq_encode_kernel<<<(unsigned)((nframes + TF - 1) / TF), 256, smem, ST>>>(latents, codebooks, cb_sq, codes, nframes, T, Q, K);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+
+extern "C" int pt_rvq_encode(const float* latents, const float* codebooks, int64_t* codes, int B, int D, int T, int Q, int K, void* stream) {
+  // the |e|^2 table lives in a library-owned scratch buffer (grown on demand, outside stream capture)
+  const size_t need = sizeof(float) * (size_t)Q * K;
+  if (need > g_cbsq_cap) {
+    if (g_cbsq) cudaFree(g_cbsq);
+    PT_CUDA_OK(cudaMalloc(&g_cbsq, need));
+    g_cbsq_cap = need;
+  }
+  return pt_rvq_encode_ws(latents, codebooks, g_cbsq, codes, B, D, T, Q, K, stream);
+}
+
+extern "C" int pt_rvq_decode(const int64_t* codes, const float* codebooks, float* latents, int B, int D, int T, int Q, int K, void* stream) {
+  PT_REQUIRE(B > 0 && T > 0 && Q > 0 && K > 0, "rvq_decode: B=%d T=%d Q=%d K=%d", B, T, Q, K);
+  PT_REQUIRE(D == RD, "rvq_decode: latent dimension must be %d (EnCodec), got %d", RD, D);
+  const long long nframes = (long long)B * T;
+  long long blocks = (nframes + 31) / 32;
+  const long long cap = 16ll * pt_num_sms();
+  if (blocks > cap) blocks = cap;
+  rvq_decode_kernel<<<(unsigned)blocks, 256, 0, ST>>>(codes, codebooks, latents, nframes, T, Q, K);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+
+extern "C" int pt_codes_affine(const int64_t* codes, float* x0, int64_t n, void* stream) {
+  PT_REQUIRE(n > 0, "codes_affine: n=%lld", (long long)n);
+  long long b = (n + 255) / 256;
+  const long long cap = 8ll * pt_num_sms();
+  if (b > cap) b = cap;
+  codes_affine_kernel<<<(unsigned)b, 256, 0, ST>>>(codes, x0, n);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+extern "C" int pt_codes_affine_inv(const float* x, int64_t* codes, int64_t n, void* stream) {
+  PT_REQUIRE(n > 0, "codes_affine_inv: n=%lld", (long long)n);
+  long long b = (n + 255) / 256;
+  const long long cap = 8ll * pt_num_sms();
+  if (b > cap) b = cap;
+  codes_affine_inv_kernel<<<(unsigned)b, 256, 0, ST>>>(x, codes, n);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}

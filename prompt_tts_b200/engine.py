@@ -1,0 +1,504 @@
+"""Tape engine: forward primitives over channels-last bf16 activations, each recording its own backward.
+
+Why a tape and not one torch.autograd.Function per op: the whole denoiser forward+backward is ~2.5k kernel
+launches; a hand-rolled tape keeps the host cost per launch at one ctypes call, lets backward kernels fuse
+gradient accumulation into GEMM epilogues, and is capturable in a CUDA graph.  The tape is bridged to
+torch.autograd once per public `forward` (see `TapeFunction`), so `loss.backward()`, optimisers and
+DDP-style hooks see ordinary `.grad` tensors.
+
+Every tensor here is a torch CUDA tensor used as a memory handle; all arithmetic is in libpt_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .ops import BF16, F32, OUT_BF16, OUT_F32, OUT_F32_ATOMIC_ADD
+
+_NUM_SMS = 148
+
+
+class Var:
+    """An activation on the tape: `data` (bf16 [.., C] unless noted) and its gradient slot."""
+    __slots__ = ("data", "grad", "owned", "needs_grad")
+
+    def __init__(self, data: torch.Tensor, needs_grad: bool = True):
+        self.data = data
+        self.grad: Optional[torch.Tensor] = None
+        self.owned = False
+        self.needs_grad = needs_grad
+
+
+class PackCache:
+    """bf16 GEMM-layout copies of fp32 parameters, refreshed when a parameter's version counter moves."""
+
+    def __init__(self):
+        self._d: Dict[tuple, Tuple[tuple, torch.Tensor]] = {}
+
+    def get(self, params: Sequence[torch.Tensor], kind: str) -> torch.Tensor:
+        key = (kind,) + tuple(id(p) for p in params)
+        ver = tuple((p._version, p.data_ptr()) for p in params)
+        hit = self._d.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        if kind == "conv":      # [Co, Ci, k] -> [Co, k*Ci]
+            (w,) = params
+            out = ops.pack_conv_weight(w.detach())
+        elif kind == "bias":    # fp32 concatenation of 1-D parameters (a single one is used in place)
+            out = params[0].detach() if len(params) == 1 else torch.cat([p.detach() for p in params])
+        else:                   # "lin": rows of all params stacked, cast to bf16 ([N, K]; 1x1 convs are [N, K, 1])
+            rows = sum(p.shape[0] for p in params)
+            K = params[0].numel() // params[0].shape[0]
+            out = torch.empty(rows, K, dtype=BF16, device=params[0].device)
+            r = 0
+            for p in params:
+                ops.cast_bf16(p.detach().reshape(p.shape[0], K), out[r:r + p.shape[0]])
+                r += p.shape[0]
+        self._d[key] = (ver, out)
+        return out
+
+
+class Tape:
+    def __init__(self, cache: PackCache, recording: bool = True):
+        self.cache = cache
+        self.recording = recording
+        self.bwd: List[Callable[[], None]] = []
+        self.pgrads: Dict[int, torch.Tensor] = {}
+        self.params: Dict[int, torch.Tensor] = {}
+        self.post: List[Callable[[], None]] = []   # run after the reverse sweep (e.g. un-packing conv weight grads)
+
+    def record(self, fn: Callable[[], None]) -> None:
+        if self.recording:
+            self.bwd.append(fn)
+
+    def pgrad(self, p: torch.Tensor) -> torch.Tensor:
+        g = self.pgrads.get(id(p))
+        if g is None:
+            g = torch.zeros(p.shape, dtype=F32, device=p.device)
+            self.pgrads[id(p)] = g
+            self.params[id(p)] = p
+        return g
+
+    def pgrad_cat(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
+        """One fp32 buffer [sum rows, K] whose row slices are the gradients of `params` (fused QKV / KV weights)."""
+        if id(params[0]) in self.pgrads:
+            g0 = self.pgrads[id(params[0])]
+            return g0._pt_cat  # type: ignore[attr-defined]
+        rows = sum(p.shape[0] for p in params)
+        K = params[0].numel() // params[0].shape[0]
+        buf = torch.zeros(rows, K, dtype=F32, device=params[0].device)
+        r = 0
+        for p in params:
+            v = buf[r:r + p.shape[0]].view(p.shape)
+            v._pt_cat = buf  # type: ignore[attr-defined]
+            self.pgrads[id(p)] = v
+            self.params[id(p)] = p
+            r += p.shape[0]
+        return buf
+
+    def backward(self) -> None:
+        for fn in reversed(self.bwd):
+            fn()
+        self.bwd = []
+        for fn in self.post:
+            fn()
+        self.post = []
+
+
+def accum(v: Var, g: torch.Tensor, owned: bool = True) -> None:
+    """Accumulate gradient `g` into `v` (g must be contiguous, same shape as v.data)."""
+    if not v.needs_grad:
+        return
+    if v.grad is None:
+        v.grad, v.owned = g, owned
+    elif v.owned:
+        ops.add_(v.grad, g, out=v.grad)
+    else:
+        v.grad = ops.add_(v.grad, g)
+        v.owned = True
+
+
+def _splitk(tiles: int, iters: int) -> int:
+    """Split the contraction so that the launch fills ~2 waves, keeping >= 8 k-iterations per split."""
+    want = max(1, (2 * _NUM_SMS) // max(1, tiles))
+    return max(1, min(want, iters // 8 if iters >= 16 else 1))
+
+
+def _wgrad_gemm(dy2d_op, x2d_op, seg, N: int, K: int, out: torch.Tensor, out_stride_m: int, iters: int) -> None:
+    tiles = ((N + 127) // 128) * ((K + 127) // 128)
+    ops.gemm([dy2d_op], [x2d_op], [seg], N, K, out, out_strides=(out_stride_m, 0, 0), out_mode=OUT_F32_ATOMIC_ADD,
+             splitk=_splitk(tiles, iters))
+
+
+# ------------------------------------------------------------------------------------------------ linear / 1x1 conv
+def linear(tape: Tape, x: Var, wparams: Sequence[torch.Tensor], bias: Optional[Sequence[torch.Tensor]] = None,
+           residual: Optional[Var] = None, out_f32: bool = False) -> Var:
+    """y[M, N] = x[M, K] @ W^T (+ bias) (+ residual).  `wparams`: one or more fp32 parameters whose rows are stacked
+    (nn.Linear [N, K] or 1x1 nn.Conv1d [N, K, 1])."""
+    xd = x.data
+    K = xd.shape[-1]
+    x2 = xd.reshape(-1, K)
+    M = x2.shape[0]
+    wp = tape.cache.get(wparams, "lin")
+    N = wp.shape[0]
+    out = torch.empty(xd.shape[:-1] + (N,), dtype=F32 if out_f32 else BF16, device=xd.device)
+    res = residual.data.reshape(M, N) if residual is not None else None
+    ops.gemm([ops.operand(x2, True)], [ops.operand(wp, True)], [ops.segment(K)], M, N, out,
+             out_mode=OUT_F32 if out_f32 else OUT_BF16, bias=tape.cache.get(bias, "bias") if bias is not None else None, residual=res)
+    y = Var(out)
+
+    def bwd():
+        dy = y.grad
+        if dy is None:
+            return
+        if out_f32:
+            dy = ops.cast_bf16(dy)
+        dy2 = dy.reshape(M, N)
+        if bias is not None:
+            ops.colsum(dy2, tape.pgrad_cat(bias) if len(bias) > 1 else tape.pgrad(bias[0]))
+        gw = tape.pgrad_cat(wparams) if len(wparams) > 1 else tape.pgrad(wparams[0]).view(N, K)
+        _wgrad_gemm(ops.operand(dy2, False), ops.operand(x2, False), ops.segment(M), N, K, gw, K, (M + 63) // 64)
+        if x.needs_grad:
+            dx = torch.empty_like(x2) if (x.grad is None or not x.owned) else x.grad.reshape(M, K)
+            prev = x.grad.reshape(M, K) if x.grad is not None else None
+            ops.gemm([ops.operand(dy2, True)], [ops.operand(wp, False)], [ops.segment(N)], M, K, dx, residual=prev)
+            x.grad, x.owned = dx.view(xd.shape), True
+        if residual is not None:
+            accum(residual, dy.view(residual.data.shape) if not out_f32 else dy.view(residual.data.shape), owned=False)
+
+    tape.record(bwd)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ conv k=3
+class TimeShift:
+    """Per-(batch, channel) additive shift for conv1 of a resnet: a column slice of the batched time projection
+    `proj` fp32 [B, total]; `dproj` collects its gradient."""
+
+    def __init__(self, proj: torch.Tensor, dproj: Optional[torch.Tensor], offset: int):
+        self.proj, self.dproj, self.offset = proj, dproj, offset
+
+
+def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: int = 1,
+          tshift: Optional[TimeShift] = None, residual: Optional[Var] = None) -> Var:
+    """Conv1d(k=3, padding=1, stride 1|2) on channels-last x[B, L, Ci] as an implicit GEMM: three K segments whose
+    A tile is the input shifted by -1/0/+1 rows (TMA zero fill = padding).  Optional fused time shift and residual."""
+    xd = x.data
+    B, L, Ci = xd.shape
+    wp = tape.cache.get([wparam], "conv")      # [Co, 3*Ci]
+    Co = wp.shape[0]
+    Lo = L if stride == 1 else (L - 1) // 2 + 1
+    out = torch.empty(B, Lo, Co, dtype=BF16, device=xd.device)
+    if stride == 1:
+        a_ops = [ops.operand(xd, True, batched=True)]
+        taps = [(0, t - 1) for t in range(3)]                 # (A map, row shift)
+    else:
+        a_ops = [ops.operand(xd[:, 0::2], True, batched=True), ops.operand(xd[:, 1::2], True, batched=True)]
+        taps = [(1, -1), (0, 0), (1, 0)]                      # in row 2l-1 = odd[l-1], 2l = even[l], 2l+1 = odd[l]
+    segs = [ops.segment(Ci, a_idx=ai, a_shift=sh, b_k0=t * Ci) for t, (ai, sh) in enumerate(taps)]
+    bz2 = tshift.proj[:, tshift.offset:] if tshift is not None else None
+    ops.gemm(a_ops, [ops.operand(wp, True)], segs, Lo, Co, out, out_strides=(Co, Lo * Co, 0), nz2=B,
+             bias=bias.detach(), bias_z2=bz2, bias_z2_stride=tshift.proj.stride(0) if tshift is not None else 0,
+             residual=residual.data if residual is not None else None, res_strides=(Co, Lo * Co, 0))
+    y = Var(out)
+
+    def bwd():
+        dy = y.grad
+        if dy is None:
+            return
+        ops.colsum(dy.view(B * Lo, Co), tape.pgrad(bias))
+        if tshift is not None and tshift.dproj is not None:
+            ops.batch_colsum(dy, tshift.dproj[:, tshift.offset:], tshift.dproj.stride(0))
+        # weight gradient, packed layout [Co, 3*Ci], then un-packed into the [Co, Ci, 3] parameter gradient
+        gp = torch.zeros(Co, 3 * Ci, dtype=F32, device=xd.device)
+        dy_op = ops.operand(dy, False, batched=True)
+        for t, (ai, sh) in enumerate(taps):
+            xs = xd if stride == 1 else (xd[:, 0::2] if ai == 0 else xd[:, 1::2])
+            seg = ops.segment(Lo, b_k0=sh, nrep=B, rep_is_batch=True)
+            tiles = ((Co + 127) // 128) * ((Ci + 127) // 128)
+            ops.gemm([dy_op], [ops.operand(xs, False, batched=True)], [seg], Co, Ci, gp[:, t * Ci:],
+                     out_strides=(3 * Ci, 0, 0), out_mode=OUT_F32_ATOMIC_ADD, splitk=_splitk(tiles, B * ((Lo + 63) // 64)))
+        g = tape.pgrad(wparam)
+        ops.unpack_conv_wgrad(gp, g, accumulate=True)
+        if x.needs_grad:
+            dy_k = ops.operand(dy, True, batched=True)
+            wp_mn = ops.operand(wp, False)
+            if stride == 1:
+                own = x.grad is not None and x.owned
+                dx = x.grad if own else torch.empty_like(xd)
+                segs_dx = [ops.segment(Co, a_shift=1 - t, b_shift=t * Ci) for t in range(3)]
+                ops.gemm([dy_k], [wp_mn], segs_dx, L, Ci, dx, out_strides=(Ci, L * Ci, 0), nz2=B,
+                         residual=x.grad, res_strides=(Ci, L * Ci, 0))
+                x.grad, x.owned = dx, True
+            else:
+                dx = torch.empty_like(xd)
+                ev, od = dx[:, 0::2], dx[:, 1::2]
+                # even input rows 2l' feed tap 1 of output l'; odd rows 2l'+1 feed tap 0 of output l'+1 and tap 2 of output l'
+                ops.gemm([dy_k], [wp_mn], [ops.segment(Co, b_shift=Ci)], ev.shape[1], Ci, ev, out_strides=(2 * Ci, L * Ci, 0), nz2=B)
+                if od.shape[1] > 0:
+                    ops.gemm([dy_k], [wp_mn], [ops.segment(Co, a_shift=1, b_shift=0), ops.segment(Co, a_shift=0, b_shift=2 * Ci)],
+                             od.shape[1], Ci, od, out_strides=(2 * Ci, L * Ci, 0), nz2=B)
+                accum(x, dx, owned=True)
+        if residual is not None:
+            accum(residual, dy, owned=False)
+
+    tape.record(bwd)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ norms
+def groupnorm(tape: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor, eps: float, act: bool, groups: int = 32) -> Var:
+    stats = ops.groupnorm_stats(x.data, groups, eps)
+    y = Var(ops.groupnorm_apply(x.data, stats, gamma.detach(), beta.detach(), groups, act))
+
+    def bwd():
+        if y.grad is None:
+            return
+        dx = ops.groupnorm_bwd(y.grad, x.data, stats, gamma.detach(), beta.detach(), tape.pgrad(gamma), tape.pgrad(beta), groups, act)
+        accum(x, dx, owned=True)
+
+    tape.record(bwd)
+    return y
+
+
+def layernorm(tape: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> Var:
+    xd = x.data
+    Cc = xd.shape[-1]
+    x2 = xd.reshape(-1, Cc)
+    yd, rs = ops.layernorm_fwd(x2, gamma.detach(), beta.detach(), eps)
+    y = Var(yd.view(xd.shape))
+
+    def bwd():
+        if y.grad is None:
+            return
+        prev = x.grad.reshape(-1, Cc) if x.grad is not None else None
+        dx = ops.layernorm_bwd(y.grad.reshape(-1, Cc), x2, rs, gamma.detach(), tape.pgrad(gamma), tape.pgrad(beta), dx_add=prev)
+        if x.needs_grad:
+            x.grad, x.owned = dx.view(xd.shape), True
+
+    tape.record(bwd)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ attention core
+def attention_core(tape: Tape, q_src: Var, q_off: int, kv_src: Var, k_off: int, v_off: int, heads: int, C: int) -> Var:
+    """softmax(Q K^T / sqrt(d)) V with Q = q_src[..., q_off:q_off+C], K/V column slices of kv_src (no mask, no dropout:
+    diffusers AttnProcessor2_0 as the reference uses it).  q_src [B, Lq, Wq], kv_src [B, Lk, Wkv]."""
+    qd, kvd = q_src.data, kv_src.data
+    B, Lq, Wq = qd.shape
+    Lk, Wkv = kvd.shape[1], kvd.shape[2]
+    d = C // heads
+    scale = d ** -0.5
+    Lkp = (Lk + 7) // 8 * 8
+
+    def heads_view(t, off):       # [B, L, W] -> [B, H, L, d] strided view
+        return t[:, :, off:off + C].unflatten(2, (heads, d)).permute(0, 2, 1, 3)
+
+    qv, kv_, vv = heads_view(qd, q_off), heads_view(kvd, k_off), heads_view(kvd, v_off)
+    S = torch.empty(B, heads, Lq, Lkp, dtype=F32, device=qd.device)
+    ops.gemm([ops.operand(qv, True, batched=True)], [ops.operand(kv_, True, batched=True)], [ops.segment(d)], Lq, Lk, S,
+             out_strides=(Lkp, Lq * Lkp, heads * Lq * Lkp), out_mode=OUT_F32, nz2=heads, nz3=B, alpha=scale)
+    P = torch.empty(B, heads, Lq, Lkp, dtype=BF16, device=qd.device)
+    ops.softmax_fwd(S, P, B * heads * Lq, Lk, Lkp)
+    del S
+    o = torch.empty(B, Lq, C, dtype=BF16, device=qd.device)
+    Pv = P[..., :Lk]
+    ops.gemm([ops.operand(Pv, True, batched=True)], [ops.operand(vv, False, batched=True)], [ops.segment(Lk)], Lq, d, o,
+             out_strides=(C, d, Lq * C), nz2=heads, nz3=B)
+    y = Var(o)
+
+    def bwd():
+        do = y.grad
+        if do is None:
+            return
+        dov = do.unflatten(2, (heads, d)).permute(0, 2, 1, 3)            # [B, H, Lq, d]
+        same = q_src is kv_src
+        dq_buf = torch.empty_like(qd)
+        dkv_buf = dq_buf if same else torch.empty_like(kvd)
+        dqv, dkv, dvv = heads_view(dq_buf, q_off), heads_view(dkv_buf, k_off), heads_view(dkv_buf, v_off)
+        # dV = P^T dO
+        ops.gemm([ops.operand(Pv, False, batched=True)], [ops.operand(dov, False, batched=True)], [ops.segment(Lq)], Lk, d, dvv,
+                 out_strides=(Wkv, d, Lk * Wkv), nz2=heads, nz3=B)
+        # dP = dO V^T  (fp32)
+        dP = torch.empty(B, heads, Lq, Lkp, dtype=F32, device=qd.device)
+        ops.gemm([ops.operand(dov, True, batched=True)], [ops.operand(vv, True, batched=True)], [ops.segment(d)], Lq, Lk, dP,
+                 out_strides=(Lkp, Lq * Lkp, heads * Lq * Lkp), out_mode=OUT_F32, nz2=heads, nz3=B)
+        dS = torch.empty(B, heads, Lq, Lkp, dtype=BF16, device=qd.device)
+        ops.softmax_bwd(dP, P, dS, B * heads * Lq, Lk, Lkp, scale)
+        del dP
+        dSv = dS[..., :Lk]
+        # dQ = dS K ; dK = dS^T Q
+        ops.gemm([ops.operand(dSv, True, batched=True)], [ops.operand(kv_, False, batched=True)], [ops.segment(Lk)], Lq, d, dqv,
+                 out_strides=(Wq, d, Lq * Wq), nz2=heads, nz3=B)
+        ops.gemm([ops.operand(dSv, False, batched=True)], [ops.operand(qv, False, batched=True)], [ops.segment(Lq)], Lk, d, dkv,
+                 out_strides=(Wkv, d, Lk * Wkv), nz2=heads, nz3=B)
+        accum(q_src, dq_buf, owned=True)
+        if not same:
+            accum(kv_src, dkv_buf, owned=True)
+
+    tape.record(bwd)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ small ops
+def geglu(tape: Tape, u: Var) -> Var:
+    ud = u.data
+    u2 = ud.reshape(-1, ud.shape[-1])
+    y = Var(ops.geglu_fwd(u2).view(ud.shape[:-1] + (ud.shape[-1] // 2,)))
+
+    def bwd():
+        if y.grad is None:
+            return
+        accum(u, ops.geglu_bwd(y.grad.reshape(-1, ud.shape[-1] // 2), u2).view(ud.shape), owned=True)
+
+    tape.record(bwd)
+    return y
+
+
+def add(tape: Tape, a: Var, b: Var) -> Var:
+    y = Var(ops.add_(a.data, b.data))
+
+    def bwd():
+        if y.grad is None:
+            return
+        accum(a, y.grad, owned=False)
+        accum(b, y.grad, owned=False)
+
+    tape.record(bwd)
+    return y
+
+
+def concat_channels(tape: Tape, a: Var, b: Var) -> Var:
+    """torch.cat([a, b], dim=channel) on channels-last tensors (unet_blocks.py:184,497)."""
+    B, L, Ca = a.data.shape
+    Cb = b.data.shape[2]
+    out = torch.empty(B, L, Ca + Cb, dtype=BF16, device=a.data.device)
+    ops.copy2d(a.data, Ca, out, Ca + Cb, B * L, Ca)
+    ops.copy2d(b.data, Cb, out[:, :, Ca:], Ca + Cb, B * L, Cb)
+    y = Var(out)
+
+    def bwd():
+        if y.grad is None:
+            return
+        g = y.grad
+        ga = torch.empty_like(a.data)
+        gb = torch.empty_like(b.data)
+        ops.copy2d(g, Ca + Cb, ga, Ca, B * L, Ca)
+        ops.copy2d(g[:, :, Ca:], Ca + Cb, gb, Cb, B * L, Cb)
+        accum(a, ga, owned=True)
+        accum(b, gb, owned=True)
+
+    tape.record(bwd)
+    return y
+
+
+def upsample2(tape: Tape, x: Var) -> Var:
+    y = Var(ops.upsample2_fwd(x.data))
+
+    def bwd():
+        if y.grad is None:
+            return
+        accum(x, ops.upsample2_bwd(y.grad), owned=True)
+
+    tape.record(bwd)
+    return y
+
+
+def silu_f32(tape: Tape, x: Var) -> Var:
+    """bf16(silu(x)) of a small fp32 tensor (time embedding path: resnet.py:255-257, TimestepEmbedding.act)."""
+    y = Var(ops.silu_to_bf16(x.data))
+
+    def bwd():
+        if y.grad is None or not x.needs_grad:
+            return
+        g = ops.silu_bwd(x.data, ops.cast_f32(y.grad))
+        if x.grad is None:
+            x.grad, x.owned = g, True
+        else:
+            x.grad = x.grad + g   # fp32 [B, temb]: never hit on the reference path (single consumer)
+
+    tape.record(bwd)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------ autograd bridge
+class TapeFunction(torch.autograd.Function):
+    """Runs `runner(tape, *tensor_inputs)` -> (outputs, finish) once; `finish(tape, grad_outputs)` seeds the output
+    gradients, after which the tape is swept in reverse and parameter / input gradients are handed to autograd."""
+
+    @staticmethod
+    def forward(ctx, runner, cache, n_in, *args):
+        ins, params = args[:n_in], args[n_in:]
+        need = any(ctx.needs_input_grad[3:])
+        tape = Tape(cache, recording=need)
+        outs, seed, in_grads = runner(tape, *ins)
+        ctx.tape, ctx.seed, ctx.in_grads, ctx.n_in, ctx.params = tape, seed, in_grads, n_in, params
+        ctx.mark_non_differentiable(*[o for o in outs if not o.is_floating_point()])
+        return outs if len(outs) > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        tape = ctx.tape
+        ctx.seed([g.contiguous() if g is not None else None for g in gouts])
+        tape.backward()
+        gin = ctx.in_grads()
+        gparams = tuple(tape.pgrads.get(id(p)) if ctx.needs_input_grad[3 + ctx.n_in + i] else None for i, p in enumerate(ctx.params))
+        ctx.tape = None
+        return (None, None, None) + tuple(gin) + gparams
+
+
+def get_cache(module) -> PackCache:
+    c = module.__dict__.get("_pt_pack_cache")
+    if c is None:
+        c = PackCache()
+        module.__dict__["_pt_pack_cache"] = c
+    return c
+
+
+def run_module(module, body, inputs, kinds, out_kind="ncl"):
+    """Public-forward helper: convert reference-layout inputs to tape Vars, run `body(tape, *vars)`, convert the
+    result back and bridge to autograd.  kinds: 'ncl' fp32 [B, C, L] activation, 'blc' float [B, L, C] activation,
+    'f32' small fp32 tensor kept as is (differentiable), 'raw' passed through (no gradient)."""
+    params = [p for p in module.parameters()]
+    cache = get_cache(module)
+    for t in inputs:
+        if not t.is_cuda:
+            raise ops._lib.PtError(f"{type(module).__name__}: inputs must be CUDA tensors; there is no CPU fallback")
+
+    def runner(tape, *ins):
+        vs = []
+        for t, k in zip(ins, kinds):
+            if k == "ncl":
+                vs.append(Var(ops.ncl_to_nlc(t.detach().float().contiguous())))
+            elif k == "blc":
+                vs.append(Var(ops.cast_bf16(t.detach().float().contiguous())))
+            elif k == "f32":
+                vs.append(Var(t.detach().float().contiguous()))
+            else:
+                vs.append(t.detach())
+        yv = body(tape, *vs)
+        out = ops.nlc_to_ncl(yv.data) if out_kind == "ncl" else ops.cast_f32(yv.data)
+
+        def seed(gouts):
+            g = gouts[0]
+            yv.grad = ops.ncl_to_nlc(g.float().contiguous()) if out_kind == "ncl" else ops.cast_bf16(g.float().contiguous())
+            yv.owned = True
+
+        def in_grads():
+            r = []
+            for v, k in zip(vs, kinds):
+                if k == "raw" or v.grad is None:
+                    r.append(None)
+                elif k == "ncl":
+                    r.append(ops.nlc_to_ncl(v.grad))
+                elif k == "blc":
+                    r.append(ops.cast_f32(v.grad))
+                else:
+                    r.append(v.grad)
+            return r
+
+        return (out,), seed, in_grads
+
+    return TapeFunction.apply(runner, cache, len(inputs), *inputs, *params)

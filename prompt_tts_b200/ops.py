@@ -60,7 +60,8 @@ def segment(nk, a_idx=0, b_idx=0, a_k0=0, b_k0=0, a_shift=0, b_shift=0, nrep=1, 
 def gemm(a: Sequence[Operand], b: Sequence[Operand], segs: Sequence[Segment], M: int, N: int, out: torch.Tensor,
          out_strides=(None, 0, 0), out_mode: int = OUT_BF16, nz2: int = 1, nz3: int = 1, splitk: int = 1,
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, bias_z2: Optional[torch.Tensor] = None,
-         residual: Optional[torch.Tensor] = None, res_strides=(None, 0, 0), block_n: int = 0) -> None:
+         residual: Optional[torch.Tensor] = None, res_strides=(None, 0, 0), block_n: int = 0,
+         bias_z2_stride: int = 0) -> None:
     """out[z2, z3, m, n] (element strides out_strides = (m, z2, z3)) = epilogue(sum over segments)."""
     g = Gemm()
     for i, o in enumerate(a):
@@ -86,9 +87,207 @@ def gemm(a: Sequence[Operand], b: Sequence[Operand], segs: Sequence[Segment], M:
     if bias_z2 is not None:
         _need(bias_z2, F32, "gemm bias_z2")
         g.bias_z2 = bias_z2.data_ptr()
+        g.bias_z2_stride = bias_z2_stride
     if residual is not None:
         _need(residual, BF16, "gemm residual")
         g.residual = residual.data_ptr()
         g.res_stride_m = res_strides[0] if res_strides[0] is not None else N
         g.res_stride_z2, g.res_stride_z3 = res_strides[1], res_strides[2]
     call("gemm", C.byref(g), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ thin wrappers
+def empty(shape, dtype=BF16, like: Optional[torch.Tensor] = None, device=None):
+    return torch.empty(shape, dtype=dtype, device=(like.device if like is not None else device))
+
+
+def groupnorm_stats(x: torch.Tensor, G: int, eps: float) -> torch.Tensor:
+    B, L, Cc = x.shape
+    stats = torch.empty(B, G, 2, dtype=F32, device=x.device)
+    call("groupnorm_stats", _p(x), _p(stats), B, L, Cc, G, eps, _stream())
+    return stats
+
+
+def groupnorm_apply(x, stats, gamma, beta, G: int, act: bool) -> torch.Tensor:
+    B, L, Cc = x.shape
+    y = torch.empty_like(x)
+    call("groupnorm_apply", _p(x), _p(stats), _p(gamma), _p(beta), _p(y), B, L, Cc, G, 1 if act else 0, _stream())
+    return y
+
+
+def groupnorm_bwd(dy, x, stats, gamma, beta, dgamma, dbeta, G: int, act: bool) -> torch.Tensor:
+    B, L, Cc = x.shape
+    dx = torch.empty_like(x)
+    scratch = torch.empty(B, G, 2, dtype=F32, device=x.device)
+    call("groupnorm_bwd", _p(dy), _p(x), _p(stats), _p(gamma), _p(beta), _p(dx), _p(dgamma), _p(dbeta), _p(scratch),
+         B, L, Cc, G, 1 if act else 0, _stream())
+    return dx
+
+
+def layernorm_fwd(x2d, gamma, beta, eps=1e-5):
+    M, Cc = x2d.shape
+    y = torch.empty_like(x2d)
+    rs = torch.empty(M, 2, dtype=F32, device=x2d.device)
+    call("layernorm_fwd", _p(x2d), _p(gamma), _p(beta), _p(y), _p(rs), M, Cc, eps, _stream())
+    return y, rs
+
+
+def layernorm_bwd(dy, x2d, rs, gamma, dgamma, dbeta, dx_add=None):
+    M, Cc = x2d.shape
+    dx = torch.empty_like(x2d)
+    call("layernorm_bwd", _p(dy), _p(x2d), _p(rs), _p(gamma), _p(dx_add), _p(dx), _p(dgamma), _p(dbeta), M, Cc, _stream())
+    return dx
+
+
+def softmax_fwd(S, P, rows, n, ld):
+    call("softmax_fwd", _p(S), _p(P), rows, n, ld, ld, _stream())
+
+
+def softmax_bwd(dP, P, dS, rows, n, ld, scale):
+    call("softmax_bwd", _p(dP), _p(P), _p(dS), rows, n, ld, ld, scale, _stream())
+
+
+def geglu_fwd(u2d):
+    M, F2 = u2d.shape
+    y = torch.empty(M, F2 // 2, dtype=BF16, device=u2d.device)
+    call("geglu_fwd", _p(u2d), _p(y), M, F2 // 2, _stream())
+    return y
+
+
+def geglu_bwd(dy, u2d):
+    M, F2 = u2d.shape
+    du = torch.empty_like(u2d)
+    call("geglu_bwd", _p(dy), _p(u2d), _p(du), M, F2 // 2, _stream())
+    return du
+
+
+def add_(a, b, out=None):
+    """out = a + b (bf16, same shape, contiguous); out may alias a or b."""
+    out = torch.empty_like(a) if out is None else out
+    call("add_bf16", _p(a), _p(b), _p(out), a.numel(), _stream())
+    return out
+
+
+def copy2d(src, ld_src, dst, ld_dst, rows, cols):
+    call("copy2d_bf16", _p(src), ld_src, _p(dst), ld_dst, rows, cols, _stream())
+
+
+def upsample2_fwd(x):
+    B, L, Cc = x.shape
+    y = torch.empty(B, 2 * L, Cc, dtype=BF16, device=x.device)
+    call("upsample2_fwd", _p(x), _p(y), B, L, Cc, _stream())
+    return y
+
+
+def upsample2_bwd(dy):
+    B, L2, Cc = dy.shape
+    dx = torch.empty(B, L2 // 2, Cc, dtype=BF16, device=dy.device)
+    call("upsample2_bwd", _p(dy), _p(dx), B, L2 // 2, Cc, _stream())
+    return dx
+
+
+def ncl_to_nlc(x_ncl):
+    B, Cc, L = x_ncl.shape
+    y = torch.empty(B, L, Cc, dtype=BF16, device=x_ncl.device)
+    call("ncl_f32_to_nlc_bf16", _p(x_ncl), _p(y), B, Cc, L, _stream())
+    return y
+
+
+def nlc_to_ncl(x_nlc):
+    B, L, Cc = x_nlc.shape
+    y = torch.empty(B, Cc, L, dtype=F32, device=x_nlc.device)
+    call("nlc_bf16_to_ncl_f32", _p(x_nlc), _p(y), B, Cc, L, _stream())
+    return y
+
+
+def cast_bf16(x_f32, out=None):
+    out = torch.empty(x_f32.shape, dtype=BF16, device=x_f32.device) if out is None else out
+    call("cast_f32_to_bf16", _p(x_f32), _p(out), x_f32.numel(), _stream())
+    return out
+
+
+def cast_f32(x_bf16):
+    out = torch.empty(x_bf16.shape, dtype=F32, device=x_bf16.device)
+    call("cast_bf16_to_f32", _p(x_bf16), _p(out), x_bf16.numel(), _stream())
+    return out
+
+
+def pack_conv_weight(w_f32, out=None):
+    Co, Ci, k = w_f32.shape
+    out = torch.empty(Co, k * Ci, dtype=BF16, device=w_f32.device) if out is None else out
+    call("pack_conv_weight", _p(w_f32), _p(out), Co, Ci, k, _stream())
+    return out
+
+
+def unpack_conv_wgrad(gp, g, accumulate=True):
+    Co, Ci, k = g.shape
+    call("unpack_conv_wgrad", _p(gp), _p(g), Co, Ci, k, 1 if accumulate else 0, _stream())
+
+
+def colsum(x2d, out_f32, ld=None):
+    rows, cols = x2d.shape
+    call("colsum_bf16", _p(x2d), ld if ld is not None else x2d.stride(0), _p(out_f32), rows, cols, _stream())
+
+
+def batch_colsum(x_blc, out_f32, out_stride):
+    B, L, Cc = x_blc.shape
+    call("batch_colsum_bf16", _p(x_blc), _p(out_f32), out_stride, B, L, Cc, _stream())
+
+
+def silu_to_bf16(x_f32):
+    y = torch.empty(x_f32.shape, dtype=BF16, device=x_f32.device)
+    call("silu_f32_to_bf16", _p(x_f32), _p(y), x_f32.numel(), _stream())
+    return y
+
+
+def silu_bwd(x_f32, dy_f32):
+    dx = torch.empty_like(x_f32)
+    call("silu_bwd_f32", _p(x_f32), _p(dy_f32), _p(dx), x_f32.numel(), _stream())
+    return dx
+
+
+def time_sinusoid(t_i64, dim):
+    out = torch.empty(t_i64.shape[0], dim, dtype=F32, device=t_i64.device)
+    call("time_sinusoid", _p(t_i64), _p(out), t_i64.shape[0], dim, _stream())
+    return out
+
+
+def rvq_encode(latents, codebooks):
+    """latents [B, 128, T] fp32, codebooks [Q, K, 128] fp32 -> codes [B, Q, T] int64."""
+    _need(latents, F32, "rvq_encode latents"); _need(codebooks, F32, "rvq_encode codebooks")
+    latents, codebooks = latents.contiguous(), codebooks.contiguous()
+    B, D, T = latents.shape
+    Q, K, D2 = codebooks.shape
+    assert D == D2
+    codes = torch.empty(B, Q, T, dtype=torch.int64, device=latents.device)
+    cb_sq = torch.empty(Q, K, dtype=F32, device=latents.device)
+    call("rvq_encode_ws", _p(latents), _p(codebooks), _p(cb_sq), _p(codes), B, D, T, Q, K, _stream())
+    return codes
+
+
+def rvq_decode(codes, codebooks):
+    """codes [B, Q, T] int64 -> latents [B, 128, T] fp32 = sum_q E_q[codes_q]."""
+    _need(codes, torch.int64, "rvq_decode codes"); _need(codebooks, F32, "rvq_decode codebooks")
+    codes, codebooks = codes.contiguous(), codebooks.contiguous()
+    B, Q, T = codes.shape
+    Q2, K, D = codebooks.shape
+    assert Q == Q2
+    lat = torch.empty(B, D, T, dtype=F32, device=codes.device)
+    call("rvq_decode", _p(codes), _p(codebooks), _p(lat), B, D, T, Q, K, _stream())
+    return lat
+
+
+def codes_affine(codes):
+    _need(codes, torch.int64, "codes_affine")
+    codes = codes.contiguous()
+    x0 = torch.empty(codes.shape, dtype=F32, device=codes.device)
+    call("codes_affine", _p(codes), _p(x0), codes.numel(), _stream())
+    return x0
+
+
+def codes_affine_inv(x):
+    _need(x, F32, "codes_affine_inv")
+    x = x.contiguous()
+    c = torch.empty(x.shape, dtype=torch.int64, device=x.device)
+    call("codes_affine_inv", _p(x), _p(c), x.numel(), _stream())
+    return c
