@@ -263,11 +263,14 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ gp, float* __
   }
 }
 
-// out[c] += sum_r x[r, c]: thread (rl, v) as in the GroupNorm statistics kernel
+// out[c] += sum_r x[r, c].  grid = (row chunks, column chunks of 2048, batch); thread (rl, v) owns one 8-column
+// vector and walks rows rl, rl + rpp, ... so partial sums stay in registers; one atomicAdd per (CTA, column).
 __global__ void colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int cols, int rows_per_cta,
-                              int rpp, long long batch_stride, long long out_stride) {
-  x += (long long)blockIdx.y * batch_stride;
-  const int nvec = cols >> 3;
+                              long long batch_stride, long long out_stride) {
+  x += (long long)blockIdx.z * batch_stride;
+  const int c0 = blockIdx.y * 2048;
+  const int nvec = min(2048, cols - c0) >> 3;
+  const int rpp = 256 / nvec;
   const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
   if (rl >= rpp) return;
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
@@ -277,12 +280,12 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, long long ld, float* _
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
   for (long long r = r0 + rl; r < r1; r += rpp) {
     float f[8];
-    load8(x + r * ld + v * 8, f);
+    load8(x + r * ld + c0 + v * 8, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] += f[j];
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&out[(long long)blockIdx.y * out_stride + v * 8 + j], s[j]);
+  for (int j = 0; j < 8; ++j) atomicAdd(&out[(long long)blockIdx.z * out_stride + c0 + v * 8 + j], s[j]);
 }
 
 __global__ void time_sinusoid_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int B, int dim) {
@@ -494,16 +497,14 @@ extern "C" int pt_unpack_conv_wgrad(const float* gp, float* g, int Co, int Ci, i
 
 static int colsum_launch(const bf16* x, long long ld, float* out, long long rows, int cols, int nbatch, long long batch_stride,
                          long long out_stride, cudaStream_t st) {
-  const int nvec = cols / 8;
-  PT_REQUIRE(cols % 8 == 0 && nvec <= 1024 && ld % 8 == 0 && nbatch >= 1 && nbatch <= 65535, "colsum: cols=%d", cols);
-  const int rpp = nvec >= 256 ? 1 : 256 / nvec;
-  const int threads = (nvec * rpp + 31) / 32 * 32;
-  long long want = (4ll * pt_num_sms() + nbatch - 1) / nbatch;
+  PT_REQUIRE(cols % 8 == 0 && ld % 8 == 0 && nbatch >= 1 && nbatch <= 65535, "colsum: cols=%d", cols);
+  const int cchunks = (cols + 2047) / 2048;
+  long long want = (4ll * pt_num_sms() + (long long)nbatch * cchunks - 1) / ((long long)nbatch * cchunks);
+  if (want < 1) want = 1;
   long long rpc = (rows + want - 1) / want;
-  rpc = (rpc + rpp - 1) / rpp * rpp;
-  if (rpc < 4 * rpp) rpc = 4 * rpp;
+  if (rpc < 32) rpc = 32;
   const unsigned blocks = (unsigned)((rows + rpc - 1) / rpc);
-  colsum_kernel<<<dim3(blocks, nbatch), threads, 0, st>>>(x, ld, out, rows, cols, (int)rpc, rpp, batch_stride, out_stride);
+  colsum_kernel<<<dim3(blocks, cchunks, nbatch), 256, 0, st>>>(x, ld, out, rows, cols, (int)rpc, batch_stride, out_stride);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }

@@ -162,12 +162,13 @@ class Unet1DConditionModel(nn.Module):
         w, bia = self.conv_in.weight, self.conv_in.bias
         h0 = torch.empty(B, L, C0, dtype=E.BF16, device=sample_ncl.device)
         ops.call("conv_in_fwd", ops._p(sample_ncl), ops._p(w.detach()), ops._p(bia.detach()), ops._p(h0), B, Cin, L, C0, ops._stream())
-        h = E.Var(h0)
+        h_in = E.Var(h0)      # NB: a distinct name -- the closure below must not see later rebinding of `h`
 
         def conv_in_bwd():
-            if h.grad is not None:
-                ops.call("conv_in_bwd", ops._p(h.grad), ops._p(sample_ncl), ops._p(tape.pgrad(w)), ops._p(tape.pgrad(bia)), B, Cin, L, C0, ops._stream())
+            if h_in.grad is not None:
+                ops.call("conv_in_bwd", ops._p(h_in.grad), ops._p(sample_ncl), ops._p(tape.pgrad(w)), ops._p(tape.pgrad(bia)), B, Cin, L, C0, ops._stream())
         tape.record(conv_in_bwd)
+        h = h_in
 
         skips = [h]
         for blk in self.down_blocks:

@@ -76,12 +76,13 @@ class TextEncoder(nn.Module):
         pe = self.pos_embedding.table(L, D, ids_i32.device)
         x = torch.empty(B, L, D, dtype=E.BF16, device=ids_i32.device)
         ops.call("text_embed_fwd", ops._p(ids_i32), ops._p(Wt.detach()), ops._p(pe), ops._p(x), B, L, D, V, ops._stream())
-        h = E.Var(x)
+        h_emb = E.Var(x)      # distinct name: the closure must not see the rebinding of `h` in the block loop
 
         def bwd():
-            if h.grad is not None:
-                ops.call("text_embed_bwd", ops._p(ids_i32), ops._p(h.grad), ops._p(tape.pgrad(Wt)), B, L, D, V, ops._stream())
+            if h_emb.grad is not None:
+                ops.call("text_embed_bwd", ops._p(ids_i32), ops._p(h_emb.grad), ops._p(tape.pgrad(Wt)), B, L, D, V, ops._stream())
         tape.record(bwd)
+        h = h_emb
         for blk in self.transformer_blocks:
             h = blk._fwd(tape, h, None)      # the mask lands in the unused encoder_hidden_states slot
         return h
