@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- denoiser train codec-frames/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle restatement) on the host cores
+
+Workload (BASELINE.json configs[1]): reconstructed run_code/1d_config denoiser (536.8 M params), bf16 compute,
+one step = add_noise -> forward -> MSE -> backward over a synthetic batch of 32 x 752 codec frames with 550 text tokens per
+GPU (weak scaling; at N > 1 the step also all-reduces the gradients over NCCL, overlapped with the backward sweep).
+`value` = frames/s with the batch resident in HBM; `e2e` = the same step through the public API with the batch in pinned
+host memory (H2D copies and the loss read-back inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = "1d_config"
+BATCH, T_FRAMES = 32, 752
+FLOP_PER_FRAME = 1.051e9          # fwd+bwd algorithmic FLOPs per codec frame (SURVEY 8d / BASELINE.md section 3)
+METRIC = "denoiser_train_codec_frames_per_sec"
+
+
+def load_cfg(name):
+    return json.load(open(os.path.join(ROOT, "configs", name + ".json")))
+
+
+def synth(cfg, B, T, seed, device):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    codes = torch.randint(0, 1024, (B, cfg["in_channels"], T), generator=g)
+    x0 = (codes.float() / 1023 - 0.5) / 0.5
+    noise = torch.randn(B, cfg["in_channels"], T, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    Lt = cfg["cmu_seq_len"]
+    ids = torch.randint(1, cfg["cmu_vocab_len"], (B, Lt), generator=g).to(torch.int32)
+    lens = torch.randint(100, Lt + 1, (B,), generator=g)
+    mask = (torch.arange(Lt)[None, :] < lens[:, None]).to(torch.int32)
+    ids = ids * mask
+    return {k: v.to(device) for k, v in dict(x0=x0, noise=noise, t=t, ids=ids, mask=mask).items()}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        busy = sorted(sm)[len(sm) // 2:] if sm else []     # upper half = samples taken under load
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_step_time(steps, warmup, threads=None):
+    """The reference's training step (train.py:100-120: forward, MSE, backward, clip-grad 1.0, AdamW) in fp32 on the host
+    cores, on BASELINE.json configs[0] (batch 2 x 752 frames) -- a bounded sample of the GPU workload's batch of 32.
+    Runs the oracle restatement (oracle/ref_model.py); /root/reference does not exist on the GPU box."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_model
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = load_cfg(CFG)
+    Bc = 2
+    sd = ref_model.random_state_dict(cfg, seed=0)
+    params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "inv_freq" not in k}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-5, betas=(0.95, 0.999), weight_decay=1e-6, eps=1e-8)
+    inp = synth(cfg, Bc, T_FRAMES, 0, "cpu")
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _ = ref_model.train_step_loss(sd, cfg, inp["x0"], inp["noise"], inp["t"], inp["ids"], inp["mask"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": Bc * T_FRAMES / sec, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{len(times)} full fp32 train steps (fwd+bwd+clip+AdamW) of the same model at batch {Bc} x {T_FRAMES} frames, "
+                      f"{warmup} warm-up; oracle/ref_model.py restatement of the reference modules on torch CPU kernels"}, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 4)     # ~5 s per step on 8 host threads: keep the arm within a few minutes
+    warm = min(args.warmup, 1)
+    cb, sec = cpu_reference_step_time(steps, warm)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"{CFG} denoiser train step on host cores, batch 2 x {T_FRAMES} frames x 550 text tokens"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from prompt_tts_b200 import _lib, ops
+    from prompt_tts_b200.models import TTSSingleSpeaker
+    from prompt_tts_b200.train import DenoiserTrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.check(_lib.lib().pt_check_device(local), "pt_check_device")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = load_cfg(CFG)
+    torch.manual_seed(0)
+    model = TTSSingleSpeaker(cfg).to(dev)
+    grad_sync = None
+    if world > 1:
+        from prompt_tts_b200.dp import GradSync
+        grad_sync = GradSync(model, world_size=world)
+    stepper = DenoiserTrainStep(model, grad_sync=grad_sync)
+    inp = synth(cfg, BATCH, T_FRAMES, 1000 + rank, dev)
+    host = {k: v.cpu().pin_memory() for k, v in inp.items()}
+    loss_buf = torch.zeros((), dtype=torch.float32, device=dev)
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step():
+        return stepper(inp["x0"], inp["noise"], inp["t"], inp["ids"], inp["mask"], loss_out=loss_buf)
+
+    # launches per step (eager) + warm-up of caches / packed weights
+    lib = _lib.lib()
+    for _ in range(2):
+        for p in model.parameters():
+            p.grad = None
+        l0 = lib.pt_launch_count()
+        step()
+        launches_per_step = lib.pt_launch_count() - l0
+    torch.cuda.synchronize()
+
+    # per-GEMM event timing over one eager step: the roofline of the dominant kernel family (tcgen05 GEMM)
+    gemm_flops, gemm_ms = gemm_profile(step, model, ops, torch)
+
+    use_graph = not args.no_graph
+    graph = None
+    if use_graph:
+        for p in model.parameters():
+            p.grad = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in model.parameters():
+            p.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            for p in model.parameters():
+                p.grad = None
+            step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    def e2e_step():
+        for k in ("x0", "noise", "t", "ids", "mask"):
+            inp[k].copy_(host[k], non_blocking=True)
+        run_step()
+        loss_host.copy_(loss_buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the user reads the loss every step (train.py:110-111)
+
+    for _ in range(max(args.warmup, 3)):
+        run_step()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms = timed(run_step, args.steps)
+    ms_e2e = timed(e2e_step, args.steps)
+    ck = clocks.stop() if rank == 0 else None
+    loss_val = float(loss_buf.item())
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        frames = BATCH * T_FRAMES * world
+        value = frames / (ms_step / 1e3)
+        e2e_v = frames / (ms_e2e / args.steps / 1e3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        h2d = sum(host[k].numel() * host[k].element_size() for k in ("x0", "noise", "t", "ids", "mask"))
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{CFG} denoiser (536.8M params) fwd+bwd, batch {BATCH} x {T_FRAMES} codec frames x 550 text tokens per GPU"
+                                   + (", NCCL gradient all-reduce overlapped with backward" if world > 1 else ""),
+                       "l2": "working set (1.07 GB bf16 weights + ~30 GB activations per step) >> 126 MB L2; no explicit flush",
+                       "cuda_graph": bool(use_graph), "loss": loss_val},
+            "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches_per_step) * args.steps * 2,   # timed value region + timed e2e region
+            "gpu_launches_per_step": int(launches_per_step),
+            "clocks": ck,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "gemm_kernel<BN> (tcgen05 GEMM family: all conv / linear / attention contractions)",
+                         "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_flops / 1e12, "peak_source": peak_src + " (of measured)",
+                         "step_frac": (FLOP_PER_FRAME * BATCH * T_FRAMES / (ms_step / 1e3) / 1e12) / peak},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference_step_time(2, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gemm_profile(step, model, ops, torch):
+    """One eager step with every pt_gemm bracketed by CUDA events: (algorithmic FLOPs, summed ms) of the GEMM family."""
+    recs = []
+    orig = ops.gemm
+
+    def timed_gemm(a, b, segs, M, N, out, **kw):
+        k_total = sum(s.nk * s.nrep for s in segs)
+        flops = 2.0 * M * N * k_total * kw.get("nz2", 1) * kw.get("nz3", 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(a, b, segs, M, N, out, **kw)
+        e1.record()
+        recs.append((flops, e0, e1))
+
+    import prompt_tts_b200.engine as eng
+    ops.gemm = timed_gemm
+    try:
+        for p in model.parameters():
+            p.grad = None
+        step()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+    fl = sum(r[0] for r in recs)
+    ms = sum(r[1].elapsed_time(r[2]) for r in recs)
+    return fl, ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,8 @@ int pt_version(void);
 const char* pt_last_error(void);
 /* 0 if device `dev` is sm_100 and the TMA driver entry point resolves */
 int pt_check_device(int dev);
+/* cumulative number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long pt_launch_count(void);
 
 /* ------------------------------------------------------------------ tcgen05 GEMM family ------- */
 /* One operand = a bf16 tensor of rank <= 4.  dim[0] is the contiguous axis (stride[0] == 1).

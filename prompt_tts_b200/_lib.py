@@ -52,6 +52,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.pt_last_error.restype = C.c_char_p
         _lib.pt_version.restype = C.c_int
+        _lib.pt_launch_count.restype = C.c_ulonglong
     return _lib
 
 
@@ -114,7 +115,7 @@ _SIGS = {
     "adamw_step": "pppplfffffipffp",
 }
 _CT = {"p": C.c_void_p, "i": C.c_int, "l": C.c_int64, "f": C.c_float}
-EXPORTS = ["pt_version", "pt_last_error"] + ["pt_" + k for k in _SIGS]
+EXPORTS = ["pt_version", "pt_last_error", "pt_launch_count"] + ["pt_" + k for k in _SIGS]
 
 
 def _bind(l):

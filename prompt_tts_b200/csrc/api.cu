@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_pt_launches = 0;
 
 void pt_set_error(const char* fmt, ...) {
   va_list ap;
@@ -25,3 +26,5 @@ extern "C" int pt_check_device(int dev) {
   }
   return PT_OK;
 }
+
+extern "C" unsigned long long pt_launch_count(void) { return g_pt_launches; }

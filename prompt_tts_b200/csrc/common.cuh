@@ -28,7 +28,12 @@ void pt_set_error(const char* fmt, ...);
     }                                                                             \
   } while (0)
 
-#define PT_LAUNCH_CHECK() PT_CUDA_OK(cudaGetLastError())
+extern unsigned long long g_pt_launches;  // kernels launched by this library (api.cu)
+#define PT_LAUNCH_CHECK()            \
+  do {                               \
+    ++g_pt_launches;                 \
+    PT_CUDA_OK(cudaGetLastError());  \
+  } while (0)
 
 static inline int pt_num_sms() {
   static int n = 0;

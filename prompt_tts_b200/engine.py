@@ -67,7 +67,10 @@ class Tape:
         self.bwd: List[Callable[[], None]] = []
         self.pgrads: Dict[int, torch.Tensor] = {}
         self.params: Dict[int, torch.Tensor] = {}
-        self.post: List[Callable[[], None]] = []   # run after the reverse sweep (e.g. un-packing conv weight grads)
+        self.post: List[Callable[[], None]] = []   # run after the reverse sweep
+        self.pgrad_order: List[Tuple[Sequence[torch.Tensor], torch.Tensor]] = []   # (params, buffer) in completion order
+        self.grad_alloc: Optional[Callable[[Sequence[torch.Tensor]], Optional[torch.Tensor]]] = None   # flat-buffer provider (dp.GradSync)
+        self.on_ready: Optional[Callable[[List[Tuple[Sequence[torch.Tensor], torch.Tensor]]], None]] = None
 
     def record(self, fn: Callable[[], None]) -> None:
         if self.recording:
@@ -76,9 +79,11 @@ class Tape:
     def pgrad(self, p: torch.Tensor) -> torch.Tensor:
         g = self.pgrads.get(id(p))
         if g is None:
-            g = torch.zeros(p.shape, dtype=F32, device=p.device)
+            buf = self.grad_alloc([p]) if self.grad_alloc is not None else None
+            g = buf.view(p.shape) if buf is not None else torch.zeros(p.shape, dtype=F32, device=p.device)
             self.pgrads[id(p)] = g
             self.params[id(p)] = p
+            self.pgrad_order.append(([p], g))
         return g
 
     def pgrad_cat(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -88,7 +93,9 @@ class Tape:
             return g0._pt_cat  # type: ignore[attr-defined]
         rows = sum(p.shape[0] for p in params)
         K = params[0].numel() // params[0].shape[0]
-        buf = torch.zeros(rows, K, dtype=F32, device=params[0].device)
+        buf = self.grad_alloc(params) if self.grad_alloc is not None else None
+        buf = buf.view(rows, K) if buf is not None else torch.zeros(rows, K, dtype=F32, device=params[0].device)
+        self.pgrad_order.append((list(params), buf))
         r = 0
         for p in params:
             v = buf[r:r + p.shape[0]].view(p.shape)
@@ -99,8 +106,13 @@ class Tape:
         return buf
 
     def backward(self) -> None:
+        done = 0
         for fn in reversed(self.bwd):
             fn()
+            if self.on_ready is not None and len(self.pgrad_order) > done:
+                # every parameter feeds exactly one op, so its gradient is final when that op's backward returns
+                self.on_ready(self.pgrad_order[done:])
+                done = len(self.pgrad_order)
         self.bwd = []
         for fn in self.post:
             fn()

@@ -1,0 +1,236 @@
+"""GPU: each bandwidth-bound kernel against a plain torch fp32 statement of the same formula, and the RVQ kernels
+bit-exactly against the C oracle and the committed golden vectors (through the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import ROOT, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def gen(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@pytest.mark.parametrize("B,L,C,act", [(2, 50, 64, True), (3, 94, 320, True), (2, 188, 1920, False), (2, 33, 2560, True)])
+def test_groupnorm_fwd_bwd(cuda, B, L, C, act):
+    from prompt_tts_b200 import ops
+    g = gen(1)
+    x = bf(torch.randn(B, L, C, device=cuda, generator=g) * 2 + 0.5)
+    gamma = torch.randn(C, device=cuda, generator=g)
+    beta = torch.randn(C, device=cuda, generator=g)
+    dy = bf(torch.randn(B, L, C, device=cuda, generator=g))
+    stats = ops.groupnorm_stats(x, 32, 1e-5)
+    y = ops.groupnorm_apply(x, stats, gamma, beta, 32, act)
+    xr = x.float().transpose(1, 2).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.group_norm(xr, 32, gr, br, 1e-5)
+    yr = F.silu(yr) if act else yr
+    yr.backward(dy.float().transpose(1, 2))
+    assert rel(y.float().transpose(1, 2), yr) < 6e-3
+    dgam, dbet = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+    dx = ops.groupnorm_bwd(dy, x, stats, gamma, beta, dgam, dbet, 32, act)
+    assert rel(dx.float().transpose(1, 2), xr.grad) < 8e-3
+    assert rel(dgam, gr.grad) < 2e-3 and rel(dbet, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("M,C", [(100, 64), (4099, 320), (777, 768), (513, 1280)])
+def test_layernorm_fwd_bwd(cuda, M, C):
+    from prompt_tts_b200 import ops
+    g = gen(2)
+    x = bf(torch.randn(M, C, device=cuda, generator=g) * 1.5 + 0.3)
+    gamma, beta = torch.randn(C, device=cuda, generator=g), torch.randn(C, device=cuda, generator=g)
+    dy, add = bf(torch.randn(M, C, device=cuda, generator=g)), bf(torch.randn(M, C, device=cuda, generator=g))
+    y, rs = ops.layernorm_fwd(x, gamma, beta)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (C,), gr, br, 1e-5)
+    yr.backward(dy.float())
+    assert rel(y, yr) < 6e-3
+    dgam, dbet = torch.zeros(C, device=cuda), torch.zeros(C, device=cuda)
+    dx = ops.layernorm_bwd(dy, x, rs, gamma, dgam, dbet, dx_add=add)
+    assert rel(dx, xr.grad + add.float()) < 8e-3
+    assert rel(dgam, gr.grad) < 2e-3 and rel(dbet, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("rows,n", [(37, 94), (1000, 550), (64, 752), (5, 1504), (9, 20)])
+def test_softmax_fwd_bwd(cuda, rows, n):
+    from prompt_tts_b200 import ops
+    g = gen(3)
+    ld = (n + 7) // 8 * 8
+    S = torch.full((rows, ld), float("nan"), device=cuda)
+    S[:, :n] = torch.randn(rows, n, device=cuda, generator=g) * 3
+    P = torch.empty(rows, ld, device=cuda, dtype=torch.bfloat16)
+    ops.softmax_fwd(S, P, rows, n, ld)
+    ref = torch.softmax(S[:, :n], -1)
+    assert rel(P[:, :n], ref) < 5e-3
+    assert (P[:, n:].float() == 0).all()
+    dP = torch.full((rows, ld), float("nan"), device=cuda)
+    dP[:, :n] = torch.randn(rows, n, device=cuda, generator=g)
+    dS = torch.empty(rows, ld, device=cuda, dtype=torch.bfloat16)
+    ops.softmax_bwd(dP, P, dS, rows, n, ld, 0.25)
+    Pf = P[:, :n].float()
+    refd = 0.25 * Pf * (dP[:, :n] - (dP[:, :n] * Pf).sum(-1, keepdim=True))
+    assert rel(dS[:, :n], refd) < 6e-3
+
+
+def test_geglu_add_upsample_copy(cuda):
+    from prompt_tts_b200 import ops
+    g = gen(4)
+    u = bf(torch.randn(300, 512, device=cuda, generator=g))
+    dy = bf(torch.randn(300, 256, device=cuda, generator=g))
+    y = ops.geglu_fwd(u)
+    ur = u.float().requires_grad_(True)
+    a, gt = ur.chunk(2, -1)
+    yr = a * F.gelu(gt)
+    yr.backward(dy.float())
+    assert rel(y, yr) < 5e-3 and rel(ops.geglu_bwd(dy, u), ur.grad) < 6e-3
+    a2, b2 = bf(torch.randn(64, 320, device=cuda, generator=g)), bf(torch.randn(64, 320, device=cuda, generator=g))
+    assert rel(ops.add_(a2, b2), a2.float() + b2.float()) < 5e-3
+    x = bf(torch.randn(2, 47, 64, device=cuda, generator=g))
+    up = ops.upsample2_fwd(x)
+    assert torch.equal(up, x.repeat_interleave(2, dim=1))
+    d = bf(torch.randn(2, 94, 64, device=cuda, generator=g))
+    assert rel(ops.upsample2_bwd(d), d.float().view(2, 47, 2, 64).sum(2)) < 5e-3
+    ncl = torch.randn(3, 70, 45, device=cuda, generator=g)
+    nlc = ops.ncl_to_nlc(ncl)
+    assert torch.equal(nlc, bf(ncl.transpose(1, 2)))
+    assert torch.equal(ops.nlc_to_ncl(nlc), nlc.float().transpose(1, 2))
+    w = torch.randn(96, 40, 3, device=cuda, generator=g)
+    assert torch.equal(ops.pack_conv_weight(w), bf(w.permute(0, 2, 1).reshape(96, 120)))
+    gp = torch.randn(96, 120, device=cuda, generator=g)
+    gacc = torch.ones(96, 40, 3, device=cuda)
+    ops.unpack_conv_wgrad(gp, gacc, accumulate=True)
+    assert torch.allclose(gacc, 1 + gp.view(96, 3, 40).permute(0, 2, 1))
+    xs = bf(torch.randn(5000, 10240, device=cuda, generator=g))
+    cs = torch.zeros(10240, device=cuda)
+    ops.colsum(xs, cs)
+    assert rel(cs, xs.float().sum(0)) < 1e-4
+    xb = bf(torch.randn(4, 300, 320, device=cuda, generator=g))
+    bc = torch.full((4, 1000), 7.0, device=cuda)
+    ops.batch_colsum(xb, bc[:, 100:], 1000)
+    assert rel(bc[:, 100:420], xb.float().sum(1)) < 1e-4 and (bc[:, :100] == 7).all() and (bc[:, 420:] == 7).all()
+
+
+def test_conv_in_out(cuda):
+    from prompt_tts_b200 import ops
+    from prompt_tts_b200.ops import _p, _stream, call
+    g = gen(5)
+    B, Cin, L, C = 3, 8, 75, 320
+    x = torch.randn(B, Cin, L, device=cuda, generator=g)
+    w = (torch.randn(C, Cin, 3, device=cuda, generator=g) * 0.2).requires_grad_(True)
+    b = torch.randn(C, device=cuda, generator=g).requires_grad_(True)
+    y = torch.empty(B, L, C, device=cuda, dtype=torch.bfloat16)
+    call("conv_in_fwd", _p(x), _p(w.detach()), _p(b.detach()), _p(y), B, Cin, L, C, _stream())
+    yr = F.conv1d(x, w, b, padding=1)
+    assert rel(y.float().transpose(1, 2), yr) < 5e-3
+    dy = bf(torch.randn(B, L, C, device=cuda, generator=g))
+    yr.backward(dy.float().transpose(1, 2))
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    call("conv_in_bwd", _p(dy), _p(x), _p(dw), _p(db), B, Cin, L, C, _stream())
+    assert rel(dw, w.grad) < 1e-4 and rel(db, b.grad) < 1e-4
+    # conv_out
+    h = bf(torch.randn(B, L, C, device=cuda, generator=g))
+    wo = (torch.randn(8, C, 3, device=cuda, generator=g) * 0.1).requires_grad_(True)
+    bo = torch.randn(8, device=cuda, generator=g).requires_grad_(True)
+    yo = torch.empty(B, 8, L, device=cuda)
+    call("conv_out_fwd", _p(h), _p(wo.detach()), _p(bo.detach()), _p(yo), B, C, L, 8, _stream())
+    hr = h.float().transpose(1, 2).requires_grad_(True)
+    yor = F.conv1d(hr, wo, bo, padding=1)
+    assert rel(yo, yor) < 1e-5
+    dyo = torch.randn(B, 8, L, device=cuda, generator=g)
+    yor.backward(dyo)
+    dh = torch.empty_like(h)
+    dwo, dbo = torch.zeros_like(wo), torch.zeros_like(bo)
+    call("conv_out_bwd", _p(dyo), _p(h), _p(wo.detach()), _p(dh), _p(dwo), _p(dbo), B, C, L, 8, _stream())
+    assert rel(dh.float().transpose(1, 2), hr.grad) < 5e-3
+    assert rel(dwo, wo.grad) < 1e-4 and rel(dbo, bo.grad) < 1e-4
+
+
+def test_time_text_noise_mse(cuda):
+    import ref_model
+    from prompt_tts_b200 import ops
+    from prompt_tts_b200.ops import _p, _stream, call
+    from prompt_tts_b200.train import ddpm_tables
+    t = torch.tensor([0, 1, 17, 500, 999], device=cuda)
+    assert rel(ops.time_sinusoid(t, 320), ref_model.timestep_sinusoid(t, 320)) < 2e-5
+    g = gen(6)
+    x0, nz = torch.randn(5, 8, 40, device=cuda, generator=g), torch.randn(5, 8, 40, device=cuda, generator=g)
+    sa, sb = ddpm_tables(device=cuda)
+    xt = torch.empty_like(x0)
+    call("add_noise", _p(x0), _p(nz), _p(t), _p(sa), _p(sb), _p(xt), 5, 320, _stream())
+    assert rel(xt, ref_model.add_noise(x0, nz, t)) < 1e-6
+    loss, dp = torch.zeros((), device=cuda), torch.empty_like(x0)
+    call("mse_fwd_bwd", _p(xt), _p(nz), _p(loss), _p(dp), xt.numel(), 1.0, _stream())
+    assert abs(loss.item() - F.mse_loss(xt, nz).item()) < 1e-5 and rel(dp, 2 * (xt - nz) / xt.numel()) < 1e-6
+    ids = torch.randint(0, 150, (3, 24), device=cuda, generator=g).to(torch.int32)
+    E_ = torch.randn(150, 64, device=cuda, generator=g)
+    pe = ref_model.text_positional_encoding(24, 64, 24, cuda)
+    y = torch.empty(3, 24, 64, device=cuda, dtype=torch.bfloat16)
+    call("text_embed_fwd", _p(ids), _p(E_), _p(pe), _p(y), 3, 24, 64, 150, _stream())
+    assert rel(y, F.embedding(ids.long(), E_) + pe[None]) < 4e-3
+
+
+def _golden_rvq(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "oracle", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"rvq_{name}.npz"))
+    seed, B, T, grid = int(g["seed"]), int(g["B"]), int(g["T"]), bool(g["grid"])
+    return g, mg.rvq_codebooks(seed, grid), mg.rvq_latents(seed, B, T, grid)
+
+
+@pytest.mark.parametrize("name", ["grid", "gauss"])
+def test_rvq_matches_golden_and_oracle_bit_exact(cuda, name):
+    import rvq_oracle
+    from prompt_tts_b200 import ops
+    g, cb, lat = _golden_rvq(name)
+    codes = ops.rvq_encode(torch.from_numpy(lat).to(cuda), torch.from_numpy(cb).to(cuda)).cpu().numpy()
+    assert np.array_equal(codes, rvq_oracle.encode(lat, cb))                  # bit-exact against the oracle
+    if name == "grid":
+        assert np.array_equal(codes, g["codes"].astype(np.int64))             # and against the encodec golden vectors
+    else:
+        assert (codes != g["codes"]).mean() < 1e-3
+    dec = ops.rvq_decode(torch.from_numpy(g["codes"].astype(np.int64)).to(cuda), torch.from_numpy(cb).to(cuda)).cpu().numpy()
+    assert np.array_equal(dec[:, :, : g["dec_slice"].shape[2]], g["dec_slice"])
+    assert np.array_equal(dec, rvq_oracle.decode(g["codes"].astype(np.int64), cb))
+
+
+def test_rvq_ragged_and_properties(cuda):
+    """LJSpeech-like batch (32 x 900 frames, reference layout generate_code.py:29-34): bit-exact against the oracle on a
+    sample, plus size-independent properties: decode(encode(x)) reduces the residual at every stage; encode of an exact
+    code vector sum returns codes whose decode reproduces the input."""
+    import rvq_oracle
+    from prompt_tts_b200 import ops
+    rs = np.random.RandomState(3)
+    cb = rs.standard_normal((8, 1024, 128)).astype(np.float32)
+    lat = rs.standard_normal((32, 128, 900)).astype(np.float32)
+    lat[:, :, 700:] = 0.0                                    # zero padding tail as in the reference's padded clips
+    cbd, latd = torch.from_numpy(cb).to(cuda), torch.from_numpy(lat).to(cuda)
+    codes = ops.rvq_encode(latd, cbd)
+    assert codes.shape == (32, 8, 900) and codes.dtype == torch.int64 and int(codes.min()) >= 0 and int(codes.max()) < 1024
+    sub = slice(0, 2)
+    assert np.array_equal(codes[sub].cpu().numpy(), rvq_oracle.encode(lat[sub], cb))
+    prev = latd.norm()
+    for q in range(1, 9):
+        r = (latd - ops.rvq_decode(codes[:, :q].contiguous(), cbd[:q].contiguous())).norm()
+        assert r < prev
+        prev = r
+    for T in (1, 31, 129):                                   # ragged lengths / partial tiles
+        c = torch.randint(0, 1024, (3, 8, T), device=cuda)
+        d = ops.rvq_decode(c, cbd)
+        assert np.array_equal(d.cpu().numpy(), rvq_oracle.decode(c.cpu().numpy(), cb))
+        c2 = ops.rvq_encode(d, cbd)
+        assert np.array_equal(c2.cpu().numpy(), rvq_oracle.encode(d.cpu().numpy(), cb))
+    x = torch.randint(0, 1024, (4, 8, 100), device=cuda)
+    assert np.array_equal(ops.codes_affine(x).cpu().numpy(), rvq_oracle.codes_affine(x.cpu().numpy()))
+    assert torch.equal(ops.codes_affine_inv(ops.codes_affine(x)), x)
