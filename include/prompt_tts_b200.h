@@ -103,6 +103,7 @@ typedef struct {
   const void* residual;    /* bf16, same indexing as out with its own strides, or NULL */
   int64_t res_stride_m, res_stride_z2, res_stride_z3;
   int64_t bias_z2_stride;  /* elements; 0 means N */
+  int64_t out_stride_n;    /* PT_OUT_F32_ATOMIC_ADD only: element stride between output columns; 0 means 1 */
 } pt_gemm_t;
 
 int pt_gemm(const pt_gemm_t* g, void* stream);

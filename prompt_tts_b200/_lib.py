@@ -30,7 +30,7 @@ class Gemm(C.Structure):
                 ("out_stride_m", C.c_int64), ("out_stride_z2", C.c_int64), ("out_stride_z3", C.c_int64),
                 ("alpha", C.c_float), ("bias", C.c_void_p), ("bias_z2", C.c_void_p), ("residual", C.c_void_p),
                 ("res_stride_m", C.c_int64), ("res_stride_z2", C.c_int64), ("res_stride_z3", C.c_int64),
-                ("bias_z2_stride", C.c_int64)]
+                ("bias_z2_stride", C.c_int64), ("out_stride_n", C.c_int64)]
 
 
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC_ADD = 0, 1, 2

@@ -263,29 +263,49 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ gp, float* __
   }
 }
 
-// out[c] += sum_r x[r, c].  grid = (row chunks, column chunks of 2048, batch); thread (rl, v) owns one 8-column
-// vector and walks rows rl, rl + rpp, ... so partial sums stay in registers; one atomicAdd per (CTA, column).
-__global__ void colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int cols, int rows_per_cta,
-                              long long batch_stride, long long out_stride) {
+// out[c] += sum_r x[r, c].  grid = (column blocks of 256, row chunks, batch).  A warp reads 32 consecutive 16-byte
+// vectors of one row (512 contiguous bytes); the 8 warps of a CTA take rows w, w+8, ... four at a time (four independent
+// loads in flight per thread); partials are combined through shared memory and leave as one atomicAdd per (CTA, column).
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int cols,
+                                                     int rows_per_cta, long long batch_stride, long long out_stride) {
+  __shared__ float sh[8][256];
   x += (long long)blockIdx.z * batch_stride;
-  const int c0 = blockIdx.y * 2048;
-  const int nvec = min(2048, cols - c0) >> 3;
-  const int rpp = 256 / nvec;
-  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
-  if (rl >= rpp) return;
-  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = min(rows, r0 + rows_per_cta);
   float s[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
-  for (long long r = r0 + rl; r < r1; r += rpp) {
-    float f[8];
-    load8(x + r * ld + c0 + v * 8, f);
+  if (c < cols) {
+    const bf16* xc = x + c;
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      float f0[8], f1[8], f2[8], f3[8];
+      load8(xc + r * ld, f0);
+      load8(xc + (r + 8) * ld, f1);
+      load8(xc + (r + 16) * ld, f2);
+      load8(xc + (r + 24) * ld, f3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] += f[j];
+      for (int j = 0; j < 8; ++j) s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; r < r1; r += 8) {
+      float f0[8];
+      load8(xc + r * ld, f0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f0[j];
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&out[(long long)blockIdx.z * out_stride + c0 + v * 8 + j], s[j]);
+  for (int j = 0; j < 8; ++j) sh[warp][lane * 8 + j] = s[j];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+    atomicAdd(&out[(long long)blockIdx.z * out_stride + cc], t);
+  }
 }
 
 __global__ void time_sinusoid_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int B, int dim) {
@@ -498,13 +518,14 @@ extern "C" int pt_unpack_conv_wgrad(const float* gp, float* g, int Co, int Ci, i
 static int colsum_launch(const bf16* x, long long ld, float* out, long long rows, int cols, int nbatch, long long batch_stride,
                          long long out_stride, cudaStream_t st) {
   PT_REQUIRE(cols % 8 == 0 && ld % 8 == 0 && nbatch >= 1 && nbatch <= 65535, "colsum: cols=%d", cols);
-  const int cchunks = (cols + 2047) / 2048;
-  long long want = (4ll * pt_num_sms() + (long long)nbatch * cchunks - 1) / ((long long)nbatch * cchunks);
+  const int cblocks = (cols + 255) / 256;
+  long long want = (8ll * pt_num_sms() + (long long)nbatch * cblocks - 1) / ((long long)nbatch * cblocks);
   if (want < 1) want = 1;
   long long rpc = (rows + want - 1) / want;
-  if (rpc < 32) rpc = 32;
-  const unsigned blocks = (unsigned)((rows + rpc - 1) / rpc);
-  colsum_kernel<<<dim3(blocks, cchunks, nbatch), 256, 0, st>>>(x, ld, out, rows, cols, (int)rpc, batch_stride, out_stride);
+  if (rpc < 64) rpc = 64;
+  const unsigned rchunks = (unsigned)((rows + rpc - 1) / rpc);
+  PT_REQUIRE(rchunks <= 65535, "colsum: too many row chunks");
+  colsum_kernel<<<dim3(cblocks, rchunks, nbatch), 256, 0, st>>>(x, ld, out, rows, cols, (int)rpc, batch_stride, out_stride);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }

@@ -40,6 +40,7 @@ struct alignas(64) KParams {
   const bf16* res;
   long long rsm, rsz2, rsz3;
   long long bz2_stride;
+  long long osn;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,7 +116,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = BN <= 64 ? 4 : (BN <= 128 ? 3 : 4);
   static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_COLS = (BN >= 160 && BN % 64 == 0) ? 64 : 32;   // columns per epilogue pass (BN <= 128 keeps 2 CTAs per SM)
+  static constexpr int EPI_BYTES = 4 * 32 * (EPI_COLS * 2 + 16);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/ + 1024 /*bias*/ + EPI_BYTES;
 };
 
 template <int BN>
@@ -147,6 +150,8 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
   const int n_iters = it_end - it_begin;
 
   if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA[p.seg[0].a_idx])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB[p.seg[0].b_idx])) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -242,75 +247,148 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
       }
       umma_commit(tmem_full_bar);
     }
-  } else if (n_iters > 0) {
+  } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
+    // While the mainloop runs: stage the per-column additive term (bias + per-batch time shift) in shared memory.
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + q * 32 + lane;
-    const bool m_ok = m < p.M;
-    const long long out_off = (long long)z2 * p.osz2 + (long long)z3 * p.osz3 + (long long)m * p.osm;
-    const long long res_off = (long long)z2 * p.rsz2 + (long long)z3 * p.rsz3 + (long long)m * p.rsm;
-    const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.bz2_stride : nullptr;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int nb = n0 + c * 32;
-      if (nb >= p.N) break;  // warp-uniform
-      uint32_t v[32];
-      __syncwarp();
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nb + j < p.N) f[j] += __ldg(p.bias + nb + j);
+    const int et = threadIdx.x - 64;
+    float* sbias = reinterpret_cast<float*>(smem_raw + (bar_base + 128 - smem_u32(smem_raw)));
+    {
+      const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.bz2_stride : nullptr;
+      for (int j = et; j < BN; j += 128) {
+        const int n = n0 + j;
+        float b = 0.f;
+        if (n < p.N) {
+          if (p.bias) b += __ldg(p.bias + n);
+          if (bz) b += __ldg(bz + n);
+        }
+        sbias[j] = b;
       }
-      if (bz) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if (n_iters > 0 && p.out_dtype == PT_OUT_BF16) {
+      // ---- bf16 output (+ optional bf16 residual): every global access is a full 64/128-byte row segment.
+      // Accumulator rows live one per thread; a warp-private padded smem tile transposes between "thread = row"
+      // and "8 (or 4) lanes = one contiguous row segment".
+      constexpr int CH = C::EPI_COLS;            // columns per pass (64 or 32)
+      constexpr int NPASS = BN / CH;
+      constexpr int VPR = CH / 8;                // 16-byte vectors per row segment
+      constexpr int RPI = 32 / VPR;              // rows covered by one warp-wide access
+      constexpr int NIT = 32 / RPI;              // accesses per pass
+      constexpr int PITCH = CH * 2 + 16;         // bytes, padded: conflict-free for both access patterns
+      uint8_t* stg = smem_raw + (bar_base + 128 + 1024 - smem_u32(smem_raw)) + q * (32 * PITCH);
+      const int mw = m0 + q * 32;                // first row of this warp
+      const int crow = lane / VPR, cvec = lane % VPR;
+      const long long zoff_o = (long long)z2 * p.osz2 + (long long)z3 * p.osz3;
+      const long long zoff_r = (long long)z2 * p.rsz2 + (long long)z3 * p.rsz3;
+      bf16* outp = reinterpret_cast<bf16*>(p.out);
+      const bool has_res = p.res != nullptr;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+      uint32_t v[2][CH];
+      bf16x8 rr[2][NIT];
+      auto load_res = [&](int pass, bf16x8* dst) {
+        const int nb = n0 + pass * CH + cvec * 8;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nb + j < p.N) f[j] += __ldg(bz + nb + j);
-      }
-      if (m_ok) {
-      if (p.res) {
-        const bf16* r = p.res + res_off + nb;
+        for (int i = 0; i < NIT; ++i) {
+          const int m = mw + crow + i * RPI;
+          if (m < p.M && nb < p.N) dst[i] = *reinterpret_cast<const bf16x8*>(p.res + zoff_r + (long long)m * p.rsm + nb);
+        }
+      };
+      if (has_res) load_res(0, rr[0]);
+      mbar_wait(tmem_full_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (nb + g * 8 < p.N) {
-            float t[8];
-            load8(r + g * 8, t);
+      for (int h = 0; h < CH / 32; ++h) tmem_ld32(tbase + h * 32, v[0] + h * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[g * 8 + j] += t[j];
+      for (int c = 0; c < NPASS; ++c) {
+        const int nb = n0 + c * CH;
+        if (nb < p.N) {  // warp-uniform
+          __syncwarp();
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c + 1 < NPASS && nb + CH < p.N) {
+#pragma unroll
+            for (int h = 0; h < CH / 32; ++h) tmem_ld32(tbase + (uint32_t)((c + 1) * CH + h * 32), v[(c + 1) & 1] + h * 32);
+            if (has_res) load_res(c + 1, rr[(c + 1) & 1]);
+          }
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) *reinterpret_cast<bf16x8*>(stg + (crow + i * RPI) * PITCH + cvec * 16) = rr[c & 1][i];
+            __syncwarp();
+          }
+#pragma unroll
+          for (int g = 0; g < VPR; ++g) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][g * 8 + j]), p.alpha, sbias[c * CH + g * 8 + j]);
+            bf16x8* cell = reinterpret_cast<bf16x8*>(stg + lane * PITCH + g * 16);   // this thread's row, vector g
+            if (has_res) {
+              const bf16x8 t = *cell;
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const float2 u = __bfloat1622float2(t.v[h]);
+                f[2 * h] += u.x;
+                f[2 * h + 1] += u.y;
+              }
+            }
+            bf16x8 t;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) t.v[h] = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
+            *cell = t;
+          }
+          __syncwarp();
+          const int ncol = nb + cvec * 8;
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int m = mw + crow + i * RPI;
+            if (m < p.M && ncol < p.N)
+              *reinterpret_cast<bf16x8*>(outp + zoff_o + (long long)m * p.osm + ncol) =
+                  *reinterpret_cast<const bf16x8*>(stg + (crow + i * RPI) * PITCH + cvec * 16);
           }
         }
       }
-      if (p.out_dtype == PT_OUT_BF16) {
-        bf16* o = reinterpret_cast<bf16*>(p.out) + out_off + nb;
+    } else if (n_iters > 0) {
+      // ---- fp32 store / fp32 atomic accumulate (logits, tiny MLP outputs, weight gradients): one row per thread
+      const int m = m0 + q * 32 + lane;
+      const bool m_ok = m < p.M;
+      const long long out_off = (long long)z2 * p.osz2 + (long long)z3 * p.osz3 + (long long)m * p.osm;
+      constexpr int NCH = BN / 32;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+      uint32_t v[2][32];
+      mbar_wait(tmem_full_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tmem_ld32(tbase, v[0]);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (nb + g * 8 < p.N) store8(o + g * 8, f + g * 8);
-      } else if (p.out_dtype == PT_OUT_F32) {
-        float* o = reinterpret_cast<float*>(p.out) + out_off + nb;
+      for (int c = 0; c < NCH; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb < p.N) {  // warp-uniform
+          __syncwarp();
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c + 1 < NCH && nb + 32 < p.N) tmem_ld32(tbase + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
+          float f[32];
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-        {
-          if (nb + g * 4 + 4 <= p.N) {
-            *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-          } else {
+          for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][j]), p.alpha, sbias[c * 32 + j]);
+          if (m_ok) {
+            if (p.out_dtype == PT_OUT_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + out_off + nb;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (nb + g * 4 + j < p.N) o[g * 4 + j] = f[g * 4 + j];
+              for (int g = 0; g < 8; ++g) {
+                if (nb + g * 4 + 4 <= p.N) {
+                  *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (nb + g * 4 + j < p.N) o[g * 4 + j] = f[g * 4 + j];
+                }
+              }
+            } else {
+              float* o = reinterpret_cast<float*>(p.out) + out_off + (long long)nb * p.osn;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) atomicAdd(o + j * p.osn, f[j]);
+            }
           }
         }
-      } else {
-        float* o = reinterpret_cast<float*>(p.out) + out_off + nb;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nb + j < p.N) atomicAdd(o + j, f[j]);
       }
-      }  // m_ok
     }
   }
 
@@ -479,6 +557,8 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   kp.rsz2 = g->res_stride_z2;
   kp.rsz3 = g->res_stride_z3;
   kp.bz2_stride = g->bias_z2_stride ? g->bias_z2_stride : g->N;
+  kp.osn = g->out_stride_n ? g->out_stride_n : 1;
+  PT_REQUIRE(kp.osn == 1 || g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: out_stride_n needs PT_OUT_F32_ATOMIC_ADD");
 
   const long long gz = (long long)g->nz2 * g->nz3 * kp.splitk;
   PT_REQUIRE(gz <= 65535, "pt_gemm: grid.z=%lld too large", gz);

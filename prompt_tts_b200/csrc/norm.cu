@@ -5,26 +5,39 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics.  Thread (rl, v) owns 8 consecutive channels (vector v) and walks rows
-// rl, rl + rpp, ... of its chunk, so per-channel partials stay in registers; they are folded into
-// per-group sums through shared memory and then one atomicAdd per (CTA, group) to global.
+// GroupNorm statistics.  grid = (column blocks of 256 channels, row chunks, batch).  A warp reads 32 consecutive
+// 16-byte vectors of a row; the 8 warps take rows w, w+8, ... four at a time, so per-channel partials stay in
+// registers; they are folded into per-group sums through shared memory and one atomicAdd per (CTA, group).
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ sums, int L, int C, int G, int rows_per_cta, int rpp) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ sums, int L, int C, int G,
+                                                       int rows_per_cta) {
   extern __shared__ float sh[];  // [2*G]
-  const int nvec = C >> 3;
-  const int b = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_cta;
+  const int b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(L, r0 + rows_per_cta);
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  const int v = threadIdx.x % nvec;
-  const int rl = threadIdx.x / nvec;
-  if (rl < rpp) {
+  if (c < C) {
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    const bf16* xb = x + ((long long)b * L) * C + v * 8;
-    for (int r = r0 + rl; r < r1; r += rpp) {
+    const bf16* xb = x + ((long long)b * L) * C + c;
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      float f[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(xb + (long long)(r + 8 * u) * C, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += f[u][j];
+          q[j] += f[u][j] * f[u][j];
+        }
+    }
+    for (; r < r1; r += 8) {
       float f[8];
       load8(xb + (long long)r * C, f);
 #pragma unroll
@@ -36,13 +49,15 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ 
     const int cpg = C / G;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (v * 8 + j) / cpg;
+      const int g = (c + j) / cpg;
       atomicAdd(&sh[2 * g], s[j]);
       atomicAdd(&sh[2 * g + 1], q[j]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(long long)b * 2 * G + i], sh[i]);
+  const int cpg = C / G;
+  const int g0 = (blockIdx.x * 256) / cpg, g1 = min(G - 1, (min(C, blockIdx.x * 256 + 256) - 1) / cpg);
+  for (int i = 2 * g0 + threadIdx.x; i <= 2 * g1 + 1; i += blockDim.x) atomicAdd(&sums[(long long)b * 2 * G + i], sh[i]);
 }
 
 __global__ void gn_finalize_kernel(float* __restrict__ stats, int n, float inv_count, float eps) {
@@ -74,51 +89,81 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restr
   const int nvec = C >> 3;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(L, r0 + rows_per_cta);
-  const long long base = ((long long)b * L) * C;
-  const int total = (r1 - r0) * nvec;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int r = r0 + i / nvec, v = i % nvec;
-    float f[8];
-    load8(x + base + (long long)r * C + v * 8, f);
+  const bf16* xb = x + ((long long)b * L + r0) * C;
+  bf16* yb = y + ((long long)b * L + r0) * C;
+  const int total = (r1 - r0) * nvec;   // the chunk is contiguous: vector i covers elements [8i, 8i+8)
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+    float f[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float z = f[j] * sa[v * 8 + j] + sb[v * 8 + j];
-      f[j] = act ? silu_f(z) : z;
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total) load8(xb + (long long)i * 8, f[u]);
     }
-    store8(y + base + (long long)r * C + v * 8, f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total) {
+        const int v = i % nvec;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float z = f[u][j] * sa[v * 8 + j] + sb[v * 8 + j];
+          f[u][j] = act ? silu_f(z) : z;
+        }
+        store8(yb + (long long)i * 8, f[u]);
+      }
+    }
   }
 }
 
 // backward pass 1: per-channel sum(dz), sum(dz*xhat) -> dgamma/dbeta (global atomics) and
-// per-(b,g) s1 = sum(dz*gamma), s2 = sum(dz*gamma*xhat) -> scratch.
-__global__ void gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, float* __restrict__ scratch, int L, int C, int G, int rows_per_cta, int rpp,
-                                     int act) {
-  extern __shared__ float sh[];  // [2*G]
-  const int nvec = C >> 3;
-  const int b = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_cta;
+// per-(b,g) s1 = sum(dz*gamma), s2 = sum(dz*gamma*xhat) -> scratch.  Same tiling as gn_stats_kernel.
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ scratch,
+                                                            int L, int C, int G, int rows_per_cta, int act) {
+  extern __shared__ float sh[];  // [2*G] group sums, then [8][256][2] per-warp channel partials
+  float* chp = sh + 2 * G;
+  const int b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(L, r0 + rows_per_cta);
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  const int v = threadIdx.x % nvec;
-  const int rl = threadIdx.x / nvec;
   const int cpg = C / G;
-  if (rl < rpp) {
-    float sdz[8], sdzx[8], mean[8], rstd[8], gm[8], bt[8];
+  float sdz[8], sdzx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sdz[j] = sdzx[j] = 0.f;
+  if (c < C) {
+    float mean[8], rstd[8], gm[8], bt[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const int g = c / cpg;
+      const int g = (c + j) / cpg;
       mean[j] = stats[((long long)b * G + g) * 2];
       rstd[j] = stats[((long long)b * G + g) * 2 + 1];
-      gm[j] = gamma[c];
-      bt[j] = beta[c];
-      sdz[j] = sdzx[j] = 0.f;
+      gm[j] = gamma[c + j];
+      bt[j] = beta[c + j];
     }
-    const long long base = ((long long)b * L) * C + v * 8;
-    for (int r = r0 + rl; r < r1; r += rpp) {
+    const long long base = ((long long)b * L) * C + c;
+    int r = r0 + warp;
+    for (; r + 8 < r1; r += 16) {
+      float fx[2][8], fd[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        load8(x + base + (long long)(r + 8 * u) * C, fx[u]);
+        load8(dy + base + (long long)(r + 8 * u) * C, fd[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (fx[u][j] - mean[j]) * rstd[j];
+          float dz = fd[u][j];
+          if (act) dz *= silu_grad_f(xh * gm[j] + bt[j]);
+          sdz[j] += dz;
+          sdzx[j] += dz * xh;
+        }
+    }
+    for (; r < r1; r += 8) {
       float fx[8], fd[8];
       load8(x + base + (long long)r * C, fx);
       load8(dy + base + (long long)r * C, fd);
@@ -131,18 +176,31 @@ __global__ void gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __
         sdzx[j] += dz * xh;
       }
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const int g = c / cpg;
-      atomicAdd(&dgamma[c], sdzx[j]);
-      atomicAdd(&dbeta[c], sdz[j]);
-      atomicAdd(&sh[2 * g], sdz[j] * gm[j]);
-      atomicAdd(&sh[2 * g + 1], sdzx[j] * gm[j]);
-    }
+  for (int j = 0; j < 8; ++j) {
+    chp[(warp * 256 + lane * 8 + j) * 2] = sdz[j];
+    chp[(warp * 256 + lane * 8 + j) * 2 + 1] = sdzx[j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&scratch[(long long)b * 2 * G + i], sh[i]);
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < C) {
+    float a = 0.f, bsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += chp[(w * 256 + threadIdx.x) * 2];
+      bsum += chp[(w * 256 + threadIdx.x) * 2 + 1];
+    }
+    atomicAdd(&dbeta[cc], a);
+    atomicAdd(&dgamma[cc], bsum);
+    const int g = cc / cpg;
+    const float gmc = gamma[cc];
+    atomicAdd(&sh[2 * g], a * gmc);
+    atomicAdd(&sh[2 * g + 1], bsum * gmc);
+  }
+  __syncthreads();
+  const int g0 = (blockIdx.x * 256) / cpg, g1 = min(G - 1, (min(C, blockIdx.x * 256 + 256) - 1) / cpg);
+  for (int i = 2 * g0 + threadIdx.x; i <= 2 * g1 + 1; i += blockDim.x) atomicAdd(&scratch[(long long)b * 2 * G + i], sh[i]);
 }
 
 // backward pass 2: dx = rstd * (dz*gamma - s1/n - xhat * s2/n)
@@ -172,27 +230,40 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
   const int nvec = C >> 3;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(L, r0 + rows_per_cta);
-  const long long base = ((long long)b * L) * C;
+  const long long base = ((long long)b * L + r0) * C;
   const int total = (r1 - r0) * nvec;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int r = r0 + i / nvec, v = i % nvec;
-    float fx[8], fd[8];
-    load8(x + base + (long long)r * C + v * 8, fx);
-    load8(dy + base + (long long)r * C + v * 8, fd);
+  for (int i0 = threadIdx.x; i0 < total; i0 += 2 * blockDim.x) {
+    float fx[2][8], fd[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const float xh = (fx[j] - s_mean[c]) * s_rstd[c];
-      float dz = fd[j];
-      if (act) dz *= silu_grad_f(xh * s_g[c] + s_b[c]);
-      fd[j] = s_rstd[c] * (dz * s_g[c] - s_k1[c] - xh * s_k2[c]);
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total) {
+        load8(x + base + (long long)i * 8, fx[u]);
+        load8(dy + base + (long long)i * 8, fd[u]);
+      }
     }
-    store8(dx + base + (long long)r * C + v * 8, fd);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < total) {
+        const int v = i % nvec;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = v * 8 + j;
+          const float xh = (fx[u][j] - s_mean[c]) * s_rstd[c];
+          float dz = fd[u][j];
+          if (act) dz *= silu_grad_f(xh * s_g[c] + s_b[c]);
+          fd[u][j] = s_rstd[c] * (dz * s_g[c] - s_k1[c] - xh * s_k2[c]);
+        }
+        store8(dx + base + (long long)i * 8, fd[u]);
+      }
+    }
   }
 }
 
 struct GnGeom {
-  int rpp, threads, rows_per_cta, chunks;
+  int rpp, threads, rows_per_cta, chunks;   // elementwise passes: grid (chunks, B)
+  int cblocks, red_rows, red_chunks;         // reduction passes: grid (cblocks, red_chunks, B)
 };
 int gn_geom(int B, int L, int C, GnGeom* g) {
   const int nvec = C / 8;
@@ -205,6 +276,12 @@ int gn_geom(int B, int L, int C, GnGeom* g) {
   if (rows < 4 * g->rpp) rows = 4 * g->rpp;
   g->rows_per_cta = rows;
   g->chunks = (L + rows - 1) / rows;
+  g->cblocks = (C + 255) / 256;
+  int rwant = (8 * pt_num_sms() + B * g->cblocks - 1) / (B * g->cblocks);
+  int rr = (L + rwant - 1) / rwant;
+  if (rr < 32) rr = 32;
+  g->red_rows = rr;
+  g->red_chunks = (L + rr - 1) / rr;
   return PT_OK;
 }
 
@@ -346,7 +423,7 @@ extern "C" int pt_groupnorm_stats(const void* x, float* stats, int B, int L, int
   if (int r = gn_geom(B, L, C, &g)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   PT_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * G, st));
-  gn_stats_kernel<<<dim3(g.chunks, B), g.threads, 2 * G * sizeof(float), st>>>((const bf16*)x, stats, L, C, G, g.rows_per_cta, g.rpp);
+  gn_stats_kernel<<<dim3(g.cblocks, g.red_chunks, B), 256, 2 * G * sizeof(float), st>>>((const bf16*)x, stats, L, C, G, g.red_rows);
   PT_LAUNCH_CHECK();
   const int n = B * G;
   gn_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats, n, 1.f / ((float)(C / G) * (float)L), eps);
@@ -372,8 +449,8 @@ extern "C" int pt_groupnorm_bwd(const void* dy, const void* x, const float* stat
   if (int r = gn_geom(B, L, C, &g)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   PT_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * G, st));
-  gn_bwd_reduce_kernel<<<dim3(g.chunks, B), g.threads, 2 * G * sizeof(float), st>>>((const bf16*)dy, (const bf16*)x, stats, gamma, beta, dgamma,
-                                                                                   dbeta, scratch, L, C, G, g.rows_per_cta, g.rpp, act);
+  gn_bwd_reduce_kernel<<<dim3(g.cblocks, g.red_chunks, B), 256, (2 * G + 8 * 256 * 2) * sizeof(float), st>>>(
+      (const bf16*)dy, (const bf16*)x, stats, gamma, beta, dgamma, dbeta, scratch, L, C, G, g.red_rows, act);
   PT_LAUNCH_CHECK();
   PT_REQUIRE(6 * C * sizeof(float) <= 160 * 1024, "groupnorm_bwd: C=%d too large", C);
   static bool attr_set = false;

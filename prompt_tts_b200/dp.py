@@ -22,7 +22,7 @@ import torch.distributed as dist
 class GradSync:
     def __init__(self, model, world_size: Optional[int] = None, bucket_mb: float = 64.0, group=None):
         self.group = group
-        self.world = world_size if world_size is not None else dist.get_world_size(group)
+        self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
         self.layout: Optional[Dict[int, Tuple[int, int]]] = None      # id(first param of a group) -> (offset, numel)
         self.flat: Optional[torch.Tensor] = None
@@ -59,6 +59,9 @@ class GradSync:
             self._launch(self._sent, self._sent + self.bucket_elems)
 
     def _launch(self, lo: int, hi: int) -> None:
+        if self.world == 1:
+            self._sent = hi
+            return
         w = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
         self._works.append(w)
         self._sent = hi
@@ -78,10 +81,11 @@ class GradSync:
             for params, buf in order:
                 o, n = self.layout[id(params[0])]
                 self.flat[o:o + n].copy_(buf.reshape(-1))
-            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
-            for params, buf in order:
-                o, n = self.layout[id(params[0])]
-                buf.reshape(-1).copy_(self.flat[o:o + n])
+            if self.world > 1:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+                for params, buf in order:
+                    o, n = self.layout[id(params[0])]
+                    buf.reshape(-1).copy_(self.flat[o:o + n])
             self.n_buckets_last = 1
             return
         if self._done > self._sent:

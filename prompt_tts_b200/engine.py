@@ -223,17 +223,16 @@ def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: 
         ops.colsum(dy.view(B * Lo, Co), tape.pgrad(bias))
         if tshift is not None and tshift.dproj is not None:
             ops.batch_colsum(dy, tshift.dproj[:, tshift.offset:], tshift.dproj.stride(0))
-        # weight gradient, packed layout [Co, 3*Ci], then un-packed into the [Co, Ci, 3] parameter gradient
-        gp = torch.zeros(Co, 3 * Ci, dtype=F32, device=xd.device)
+        # weight gradient: one MN-major x MN-major GEMM per tap, written straight into the [Co, Ci, 3] parameter gradient
+        # (fp32 atomic accumulate with column stride 3 -- no packed temporary, no un-pack pass)
+        g3 = tape.pgrad(wparam).view(Co, Ci * 3)
         dy_op = ops.operand(dy, False, batched=True)
         for t, (ai, sh) in enumerate(taps):
             xs = xd if stride == 1 else (xd[:, 0::2] if ai == 0 else xd[:, 1::2])
             seg = ops.segment(Lo, b_k0=sh, nrep=B, rep_is_batch=True)
             tiles = ((Co + 127) // 128) * ((Ci + 127) // 128)
-            ops.gemm([dy_op], [ops.operand(xs, False, batched=True)], [seg], Co, Ci, gp[:, t * Ci:],
-                     out_strides=(3 * Ci, 0, 0), out_mode=OUT_F32_ATOMIC_ADD, splitk=_splitk(tiles, B * ((Lo + 63) // 64)))
-        g = tape.pgrad(wparam)
-        ops.unpack_conv_wgrad(gp, g, accumulate=True)
+            ops.gemm([dy_op], [ops.operand(xs, False, batched=True)], [seg], Co, Ci, g3[:, t:],
+                     out_strides=(3 * Ci, 0, 0), out_mode=OUT_F32_ATOMIC_ADD, splitk=_splitk(tiles, B * ((Lo + 63) // 64)), out_stride_n=3)
         if x.needs_grad:
             dy_k = ops.operand(dy, True, batched=True)
             wp_mn = ops.operand(wp, False)

@@ -61,7 +61,7 @@ def gemm(a: Sequence[Operand], b: Sequence[Operand], segs: Sequence[Segment], M:
          out_strides=(None, 0, 0), out_mode: int = OUT_BF16, nz2: int = 1, nz3: int = 1, splitk: int = 1,
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, bias_z2: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, res_strides=(None, 0, 0), block_n: int = 0,
-         bias_z2_stride: int = 0) -> None:
+         bias_z2_stride: int = 0, out_stride_n: int = 0) -> None:
     """out[z2, z3, m, n] (element strides out_strides = (m, z2, z3)) = epilogue(sum over segments)."""
     g = Gemm()
     for i, o in enumerate(a):
@@ -81,6 +81,7 @@ def gemm(a: Sequence[Operand], b: Sequence[Operand], segs: Sequence[Segment], M:
     g.out_stride_m = out_strides[0] if out_strides[0] is not None else N
     g.out_stride_z2, g.out_stride_z3 = out_strides[1], out_strides[2]
     g.alpha = alpha
+    g.out_stride_n = out_stride_n
     if bias is not None:
         _need(bias, F32, "gemm bias")
         g.bias = bias.data_ptr()

@@ -34,6 +34,9 @@ class DenoiserTrainStep:
         self.cache = E.get_cache(model)
         self.sa: Optional[torch.Tensor] = None
         self.sb: Optional[torch.Tensor] = None
+        if grad_sync is None:      # single GPU: still use the flat gradient buffer (one memset per step, no per-tensor zero fills)
+            from .dp import GradSync
+            grad_sync = GradSync(model, world_size=1)
         self.grad_sync = grad_sync
         self.loss = None
 
