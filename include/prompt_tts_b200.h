@@ -18,6 +18,7 @@
  *                                                                  tts/ldm/transformer_1d.py:130,251; unet_1d_condition.py:401,732-733
  *   pt_layernorm_*     LayerNorm in BasicTransformerBlock          (diffusers 0.15, used at transformer_1d.py:258-265)
  *   pt_softmax_*       softmax(QK^T/sqrt d)                        (diffusers AttnProcessor2_0)
+ *   pt_attn_fwd/bwd    fused softmax(QK^T/sqrt d) V                (diffusers AttnProcessor2_0 / F.scaled_dot_product_attention)
  *   pt_geglu_*         h * gelu_erf(g)                             (diffusers GEGLU)
  *   pt_conv_in_*, pt_conv_out_*   8<->C convs                      tts/ldm/unet_1d_condition.py:193,410,654,734
  *   pt_upsample2_*     nearest x2                                  tts/ldm/resnet.py:41-44
@@ -134,6 +135,25 @@ int pt_softmax_fwd(const float* S, void* P, int64_t rows, int n, int64_t ld_s, i
 /* dS[r, :] = scale * P * (dP - sum(dP * P)) ; dP fp32 (stride ld_s), P bf16, dS bf16 (stride ld_p) */
 int pt_softmax_bwd(const float* dP, const void* P, void* dS, int64_t rows, int n, int64_t ld_s, int64_t ld_p,
                    float scale, void* stream);
+/* Fused softmax attention on tcgen05 (no mask, no dropout: diffusers AttnProcessor2_0 as used from
+ * tts/ldm/transformer_1d.py:258-265 and tts/models.py:95-100).  q/k/v/o/d_o/dq/dk/dv point at the head-0 column of
+ * bf16 [B, L, W] tensors (row stride *_rs, batch stride *_bs, in elements; head h occupies columns [h*d, (h+1)*d)),
+ * so fused QKV / KV projections are consumed and their gradients produced in place.  d: multiple of 8, <= 192.
+ * lse [B, H, Lq] fp32 = log-sum-exp of the scaled logits (written by fwd, read by bwd); delta: bwd scratch [B, H, Lq]. */
+typedef struct {
+  const void* q; int64_t q_rs, q_bs;
+  const void* k; const void* v; int64_t kv_rs, kv_bs;
+  void* o; int64_t o_rs, o_bs;
+  float* lse;
+  const void* d_o; int64_t do_rs, do_bs;
+  void* dq; int64_t dq_rs, dq_bs;
+  void* dk; void* dv; int64_t dkv_rs, dkv_bs;
+  float* delta;
+  int32_t B, H, Lq, Lk, d;
+  float scale;
+} pt_attn_t;
+int pt_attn_fwd(const pt_attn_t* a, void* stream);
+int pt_attn_bwd(const pt_attn_t* a, void* stream);
 /* GEGLU: y[m, j] = u[m, j] * gelu_erf(u[m, F + j]), u[M, 2F] bf16 -> y[M, F] bf16 */
 int pt_geglu_fwd(const void* u, void* y, int64_t M, int F, void* stream);
 int pt_geglu_bwd(const void* dy, const void* u, void* du, int64_t M, int F, void* stream);

@@ -33,6 +33,19 @@ class Gemm(C.Structure):
                 ("bias_z2_stride", C.c_int64), ("out_stride_n", C.c_int64)]
 
 
+class Attn(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("q_rs", C.c_int64), ("q_bs", C.c_int64),
+                ("k", C.c_void_p), ("v", C.c_void_p), ("kv_rs", C.c_int64), ("kv_bs", C.c_int64),
+                ("o", C.c_void_p), ("o_rs", C.c_int64), ("o_bs", C.c_int64),
+                ("lse", C.c_void_p),
+                ("d_o", C.c_void_p), ("do_rs", C.c_int64), ("do_bs", C.c_int64),
+                ("dq", C.c_void_p), ("dq_rs", C.c_int64), ("dq_bs", C.c_int64),
+                ("dk", C.c_void_p), ("dv", C.c_void_p), ("dkv_rs", C.c_int64), ("dkv_bs", C.c_int64),
+                ("delta", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32), ("d", C.c_int32),
+                ("scale", C.c_float)]
+
+
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC_ADD = 0, 1, 2
 
 _lib = None
@@ -73,6 +86,8 @@ def call(name: str, *args) -> None:
 _SIGS = {
     "check_device": "i",
     "gemm": "pp",
+    "attn_fwd": "pp",
+    "attn_bwd": "pp",
     "groupnorm_stats": "ppiiiifp",
     "groupnorm_apply": "pppppiiiiip",
     "groupnorm_bwd": "pppppppppiiiiip",

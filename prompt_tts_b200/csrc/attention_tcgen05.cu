@@ -1,0 +1,594 @@
+// Fused softmax attention (forward and backward) on tcgen05 / TMEM / TMA for sm_100a.
+//
+// Replaces diffusers' AttnProcessor2_0 (F.scaled_dot_product_attention, no mask, no dropout) as the reference
+// uses it from tts/ldm/transformer_1d.py:258-265 and tts/models.py:95-100,117-119.  No [Lq, Lk] matrix ever
+// reaches HBM: logits live in TMEM, probabilities go registers -> shared memory -> tensor core.
+//
+// One kernel template, three modes.  A CTA owns 128 "resident" rows and streams 64-row tiles of the other side:
+//
+//   mode  resident (R1,R2)  streamed (S1,S2)  stage 1 (TMEM X)              transform (CUDA cores)       stage 2 (TMEM ACC)
+//   FWD   Q                 K, V              X1 = Q K^T                    P  = exp(X1*s - m)           O  += P V          (/ rowsum)
+//   DQ    Q, dO             K, V              X1 = Q K^T,  X2 = dO V^T      dS = P (X2 - D) s            dQ += dS K
+//   DKV   K, V              Q, dO             X1 = K Q^T,  X2 = V dO^T      P^T, dS^T                    dV += P^T dO ; dK += dS^T Q
+//
+// with P = exp(X1*s - lse) in the backward modes (lse saved by FWD, D = rowsum(dO * O) from a small pre-pass).
+// FWD makes two sweeps over the streamed side: sweep 1 only takes the row maximum of the logits (exact softmax,
+// no accumulator rescaling), sweep 2 does the work.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-5 and 6-9 two
+// transform groups that ping-pong over the streamed tiles (group g owns TMEM buffer X[g] and smem tile T[g]),
+// so the tensor core computes the logits of tile j+1 while the CUDA cores exponentiate tile j.
+// Every streamed tile is used twice from the same shared-memory bytes: K-major as the B operand of stage 1 and
+// MN-major as the B operand of stage 2 (only the UMMA descriptor differs).
+#include <math.h>
+
+#include "tc_common.cuh"
+
+namespace {
+using namespace tc;
+
+enum { MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2 };
+
+constexpr int BM = 128;  // resident rows per CTA
+constexpr int BN = 64;   // streamed rows per tile (= one SWIZZLE_128B row of bf16 in the T tile)
+
+struct alignas(64) AParams {
+  CUtensorMap tmR[2];
+  CUtensorMap tmS[2];
+  int Lr, Ls, H, D;
+  float scale;
+  bf16* out0;
+  bf16* out1;
+  long long o_rs, o_bs;
+  float* lse;          // FWD: written; DQ/DKV: read.  [B, H, Lq]
+  const float* delta;  // DQ/DKV.                      [B, H, Lq]
+};
+
+template <int MODE, int DP>
+struct ACfg {
+  static constexpr int NX = MODE == MODE_FWD ? 1 : 2;       // stage-1 products per tile
+  static constexpr int NACC = MODE == MODE_DKV ? 2 : 1;     // stage-2 accumulators
+  static constexpr int XBUF = (MODE == MODE_DKV && DP > 128) ? 1 : 2;   // TMEM budget: 2*2*64 + 2*192 > 512
+  static constexpr int KB = DP / 64;                         // 64-element blocks along the head dimension
+  static constexpr int R_BYTES = BM * DP * 2;
+  static constexpr int S_BYTES = BN * DP * 2;
+  static constexpr int STAGE_BYTES = 2 * S_BYTES;
+  static constexpr int T_BYTES = BM * BN * 2;
+  static constexpr int FIXED = NX * R_BYTES + XBUF * NACC * T_BYTES;
+  static constexpr int NSTAGE = (FIXED + 2 * STAGE_BYTES <= 200 * 1024) ? 2 : 1;
+  static constexpr int OFF_S = NX * R_BYTES;
+  static constexpr int OFF_T = OFF_S + NSTAGE * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_T + XBUF * NACC * T_BYTES;
+  static constexpr int OFF_STAT = OFF_BAR + 256;
+  static constexpr int STAT_BYTES = 2 * 2 * 2 * BN * 4 + 2 * BM * 4;   // DKV column stats [g][buf][2][BN] + row reduce [2][BM]
+  static constexpr int SMEM_BYTES = 1024 + OFF_STAT + STAT_BYTES;
+  static constexpr int X_COLS = XBUF * NX * BN;
+  static constexpr int ACC_STRIDE = DP;
+  static constexpr int TMEM_USED = X_COLS + NACC * ACC_STRIDE;
+  static constexpr int TMEM_COLS = TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512));
+  static_assert(TMEM_USED <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int MODE, int DP>
+__global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AParams p) {
+  using C = ACfg<MODE, DP>;
+  constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t sR = sbase, sS = sbase + C::OFF_S, sT = sbase + C::OFF_T, bar0 = sbase + C::OFF_BAR;
+  // barriers
+  const uint32_t r_full = bar0;
+  auto s_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto s_empty = [&](int s) { return bar0 + 8u * (3 + s); };
+  auto x_full = [&](int g) { return bar0 + 8u * (5 + g); };
+  auto x_empty = [&](int g) { return bar0 + 8u * (7 + g); };
+  auto t_full = [&](int g) { return bar0 + 8u * (9 + g); };
+  auto t_empty = [&](int g) { return bar0 + 8u * (11 + g); };
+  const uint32_t acc_full = bar0 + 8u * 13;
+  const uint32_t tmem_slot = bar0 + 8u * 14;
+  float* sstat = reinterpret_cast<float*>(sgen + C::OFF_STAT);          // [g][buf][2][BN]
+  float* sred = sstat + 2 * 2 * 2 * BN;                                 // [2][BM]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.Ls + BN - 1) / BN;
+  const int ks1 = (p.D + 15) >> 4;            // stage-1 k-steps (head dim, zero padded to a multiple of 16)
+  const int nd = ks1 << 4;                    // stage-2 N
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < NX; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmR[i])) : "memory");
+    for (int i = 0; i < 2; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmS[i])) : "memory");
+    mbar_init(r_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full(s), 1);
+      mbar_init(s_empty(s), 1);
+      mbar_init(x_full(s), 1);
+      mbar_init(x_empty(s), 128);
+      mbar_init(t_full(s), 128);
+      mbar_init(t_empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 14);
+  auto xcol = [&](int g, int x) { return (uint32_t)((g * NX + x) * BN); };
+  auto acccol = [&](int a) { return (uint32_t)(C::X_COLS + a * C::ACC_STRIDE); };
+  auto tT = [&](int g, int a) { return sT + (uint32_t)((g * NACC + a) * C::T_BYTES); };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(r_full, NX * C::R_BYTES);
+      for (int x = 0; x < NX; ++x)
+        for (int kb = 0; kb < KB; ++kb) tma_load_4d(sR + x * C::R_BYTES + kb * (BM * 128), &p.tmR[x], r_full, kb * 64, r0, h, b);
+      int it = 0;
+      constexpr int NPASS = MODE == MODE_FWD ? 2 : 1;
+      for (int pass = 0; pass < NPASS; ++pass) {
+        const bool first_only = MODE == MODE_FWD && pass == 0;
+        for (int j = 0; j < n_tiles; ++j, ++it) {
+          const int s = it % NSTAGE;
+          mbar_wait(s_empty(s), ((it / NSTAGE) & 1) ^ 1);
+          mbar_expect_tx(s_full(s), first_only ? C::S_BYTES : 2 * C::S_BYTES);
+          const uint32_t dst = sS + s * C::STAGE_BYTES;
+          for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + kb * (BN * 128), &p.tmS[0], s_full(s), kb * 64, j * BN, h, b);
+          if (!first_only)
+            for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + C::S_BYTES + kb * (BN * 128), &p.tmS[1], s_full(s), kb * 64, j * BN, h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = idesc_f16(0, 0, BN, BM);
+      const uint32_t idesc2 = idesc_f16(0, 1, nd, BM);
+      int kx[2] = {0, 0}, kt[2] = {0, 0};
+      mbar_wait(r_full, 0);
+      auto mma1 = [&](int it, int g) {
+        const int s = it % NSTAGE;
+        mbar_wait(s_full(s), (it / NSTAGE) & 1);
+        mbar_wait(x_empty(g), (kx[g] & 1) ^ 1);
+        fence_after();
+        const uint32_t st = sS + s * C::STAGE_BYTES;
+        for (int x = 0; x < NX; ++x)
+          for (int k = 0; k < ks1; ++k) {
+            const uint64_t ad = umma_desc(sR + x * C::R_BYTES + (k >> 2) * (BM * 128) + (k & 3) * 32, 0, 1024);
+            const uint64_t bd = umma_desc(st + x * C::S_BYTES + (k >> 2) * (BN * 128) + (k & 3) * 32, 0, 1024);
+            umma_f16(tmem + xcol(g, x), ad, bd, idesc1, k > 0 ? 1u : 0u);
+          }
+        umma_commit(x_full(g));
+        ++kx[g];
+      };
+      auto mma2 = [&](int it, int g, bool first) {
+        const int s = it % NSTAGE;
+        mbar_wait(t_full(g), kt[g] & 1);
+        fence_after();
+        const uint32_t st = sS + s * C::STAGE_BYTES;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          // B operand of stage 2, MN-major view of a streamed tile: FWD -> V (S2); DQ -> K (S1); DKV: dV <- dO (S2), dK <- Q (S1)
+          const int cs = MODE == MODE_FWD ? 1 : (MODE == MODE_DQ ? 0 : (a == 0 ? 1 : 0));
+#pragma unroll
+          for (int k = 0; k < BN / 16; ++k) {
+            const uint64_t ad = umma_desc(tT(g, a) + k * 32, 0, 1024);
+            const uint64_t bd = umma_desc(st + cs * C::S_BYTES + k * 2048, BN * 128, 1024);
+            umma_f16(tmem + acccol(a), ad, bd, idesc2, (first && k == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(t_empty(g));
+        ++kt[g];
+        umma_commit(s_empty(s));
+      };
+      int it = 0;
+      if (MODE == MODE_FWD) {
+        for (int j = 0; j < n_tiles; ++j, ++it) {
+          mma1(it, XBUF == 2 ? (j & 1) : 0);
+          umma_commit(s_empty(it % NSTAGE));
+        }
+      }
+      constexpr bool LOOKAHEAD = NSTAGE >= 2 && XBUF == 2;
+      mma1(it, 0);
+      for (int j = 0; j < n_tiles; ++j, ++it) {
+        const int g = XBUF == 2 ? (j & 1) : 0;
+        if (LOOKAHEAD && j + 1 < n_tiles) mma1(it + 1, (j + 1) & 1);
+        mma2(it, g, j == 0);
+        if (!LOOKAHEAD && j + 1 < n_tiles) mma1(it + 1, XBUF == 2 ? ((j + 1) & 1) : 0);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ transform groups (warps 2-5, 6-9)
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;                // row of the 128-row tile owned by this thread
+    const int tg = (warp - 2 - g * 4) * 32 + lane;   // 0..127 within the group
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const bool active = XBUF == 2 || g == 0;      // with one X buffer only group 0 transforms (group 1 helps in the epilogue)
+    const int jstep = XBUF == 2 ? 2 : 1;
+    const float c2 = p.scale * 1.4426950408889634f;
+    const uint32_t trow = (uint32_t)(row * 128);
+    const int rsw = row & 7;
+    int kx = 0, kt = 0;
+    uint32_t v1[32], v2[32];
+
+    if (MODE == MODE_FWD) {
+      // ---- sweep 1: exact row maximum of the raw logits
+      float m = -INFINITY;
+      if (active)
+        for (int j = g; j < n_tiles; j += jstep) {
+          mbar_wait(x_full(g), kx & 1);
+          fence_after();
+          const int ncol = min(BN, p.Ls - j * BN);
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
+            tmem_wait_ld();
+            if (ncol >= (c + 1) * 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v1[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < ncol) m = fmaxf(m, __uint_as_float(v1[i]));
+            }
+          }
+          fence_before();
+          mbar_arrive(x_empty(g));
+          ++kx;
+        }
+      sred[g * BM + row] = m;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      m = fmaxf(sred[row], sred[BM + row]);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float mc = m * c2;
+      // ---- sweep 2: P = exp(s - m) -> T[g] (bf16, K-major, SWIZZLE_128B) ; partial row sums
+      float rsum = 0.f;
+      if (active)
+        for (int j = g; j < n_tiles; j += jstep) {
+          mbar_wait(x_full(g), kx & 1);
+          fence_after();
+          mbar_wait(t_empty(g), (kt & 1) ^ 1);
+          const int ncol = min(BN, p.Ls - j * BN);
+          const uint32_t tt = tT(g, 0) + trow;
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
+            tmem_wait_ld();
+            float pv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float e = ex2f(fmaf(__uint_as_float(v1[i]), c2, -mc));
+              if (ncol < BN && c * 32 + i >= ncol) e = 0.f;
+              pv[i] = e;
+              rsum += e;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              sts128(tt + (uint32_t)(((c * 4 + u) ^ rsw) << 4), pack2(pv[u * 8], pv[u * 8 + 1]), pack2(pv[u * 8 + 2], pv[u * 8 + 3]),
+                     pack2(pv[u * 8 + 4], pv[u * 8 + 5]), pack2(pv[u * 8 + 6], pv[u * 8 + 7]));
+          }
+          fence_before();
+          mbar_arrive(x_empty(g));
+          fence_async_smem();
+          mbar_arrive(t_full(g));
+          ++kx;
+          ++kt;
+        }
+      sred[g * BM + row] = rsum;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      rsum = sred[row] + sred[BM + row];
+      // ---- epilogue: O = ACC / rowsum ; lse = m * scale + ln(rowsum)
+      mbar_wait(acc_full, 0);
+      fence_after();
+      const float inv = 1.f / rsum;
+      const int r = r0 + row;
+      bf16* orow = p.out0 + (long long)b * p.o_bs + (long long)r * p.o_rs + (long long)h * p.D;
+      for (int cc = g; cc * 16 < p.D; cc += 2) {
+        tmem_ld16(tl + acccol(0) + cc * 16, v1);
+        tmem_wait_ld();
+        if (r < p.Lr) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (cc * 16 + u * 8 < p.D) {
+              uint4 w;
+              w.x = pack2(__uint_as_float(v1[u * 8]) * inv, __uint_as_float(v1[u * 8 + 1]) * inv);
+              w.y = pack2(__uint_as_float(v1[u * 8 + 2]) * inv, __uint_as_float(v1[u * 8 + 3]) * inv);
+              w.z = pack2(__uint_as_float(v1[u * 8 + 4]) * inv, __uint_as_float(v1[u * 8 + 5]) * inv);
+              w.w = pack2(__uint_as_float(v1[u * 8 + 6]) * inv, __uint_as_float(v1[u * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + cc * 16 + u * 8) = w;
+            }
+        }
+      }
+      if (g == 0 && r < p.Lr) p.lse[((long long)b * p.H + h) * p.Lr + r] = m * p.scale + __logf(rsum);
+    } else {
+      // ---- backward modes
+      float lse2 = INFINITY, dl = 0.f;   // DQ: this thread's row statistics
+      if (MODE == MODE_DQ && r0 + row < p.Lr) {
+        const long long si = ((long long)b * p.H + h) * p.Lr + r0 + row;
+        lse2 = p.lse[si] * 1.4426950408889634f;
+        dl = p.delta[si] * p.scale;
+      }
+      if (active)
+        for (int j = g; j < n_tiles; j += jstep) {
+          const float* cst = nullptr;
+          if (MODE == MODE_DKV) {
+            // column statistics of this tile (columns = query rows): lse * log2(e) (+inf masks the column), delta * scale
+            float* st = sstat + ((g * 2 + (kx & 1)) * 2) * BN;
+            if (tg < BN) {
+              const int qi = j * BN + tg;
+              float a = INFINITY, d = 0.f;
+              if (qi < p.Ls) {
+                const long long si = ((long long)b * p.H + h) * p.Ls + qi;
+                a = p.lse[si] * 1.4426950408889634f;
+                d = p.delta[si] * p.scale;
+              }
+              st[tg] = a;
+              st[BN + tg] = d;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
+            cst = st;
+          }
+          mbar_wait(x_full(g), kx & 1);
+          fence_after();
+          mbar_wait(t_empty(g), (kt & 1) ^ 1);
+          const uint32_t tt0 = tT(g, 0) + trow;
+          const uint32_t tt1 = tT(g, NACC - 1) + trow;
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
+            tmem_ld32(tl + xcol(g, 1) + c * 32, v2);
+            tmem_wait_ld();
+            uint32_t pp[16], dd[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float pe[2], de[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const float l2 = MODE == MODE_DKV ? cst[c * 32 + i + u] : lse2;
+                const float dv = MODE == MODE_DKV ? cst[BN + c * 32 + i + u] : dl;
+                const float e = ex2f(fmaf(__uint_as_float(v1[i + u]), c2, -l2));
+                pe[u] = e;
+                de[u] = e * fmaf(__uint_as_float(v2[i + u]), p.scale, -dv);
+              }
+              pp[i >> 1] = pack2(pe[0], pe[1]);
+              dd[i >> 1] = pack2(de[0], de[1]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t off = (uint32_t)(((c * 4 + u) ^ rsw) << 4);
+              if (MODE == MODE_DKV) sts128(tt0 + off, pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
+              sts128(tt1 + off, dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
+            }
+          }
+          fence_before();
+          mbar_arrive(x_empty(g));
+          fence_async_smem();
+          mbar_arrive(t_full(g));
+          ++kx;
+          ++kt;
+        }
+      // ---- epilogue: accumulators -> bf16 rows
+      mbar_wait(acc_full, 0);
+      fence_after();
+      const int r = r0 + row;
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        bf16* obase = (a == 0 ? p.out0 : p.out1) + (long long)b * p.o_bs + (long long)r * p.o_rs + (long long)h * p.D;
+        // DKV: group a writes accumulator a; DQ: the two groups interleave 16-column chunks
+        const int c_begin = MODE == MODE_DKV ? 0 : g, c_step = MODE == MODE_DKV ? 1 : 2;
+        if (MODE == MODE_DKV && g != a) continue;
+        for (int cc = c_begin; cc * 16 < p.D; cc += c_step) {
+          tmem_ld16(tl + acccol(a) + cc * 16, v1);
+          tmem_wait_ld();
+          if (r < p.Lr) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              if (cc * 16 + u * 8 < p.D) {
+                uint4 w;
+                w.x = pack2(__uint_as_float(v1[u * 8]), __uint_as_float(v1[u * 8 + 1]));
+                w.y = pack2(__uint_as_float(v1[u * 8 + 2]), __uint_as_float(v1[u * 8 + 3]));
+                w.z = pack2(__uint_as_float(v1[u * 8 + 4]), __uint_as_float(v1[u * 8 + 5]));
+                w.w = pack2(__uint_as_float(v1[u * 8 + 6]), __uint_as_float(v1[u * 8 + 7]));
+                *reinterpret_cast<uint4*>(obase + cc * 16 + u * 8) = w;
+              }
+          }
+        }
+      }
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// delta[b, h, q] = sum_j dO[b, q, h*d + j] * O[b, q, h*d + j]   (one thread per (row, head))
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_rs, long long o_bs, const bf16* __restrict__ d_o, long long do_rs,
+                                  long long do_bs, float* __restrict__ delta, int B, int H, int L, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * L * H) return;
+  const int hh = (int)(i % H);
+  const long long bl = i / H;
+  const int l = (int)(bl % L), bb = (int)(bl / L);
+  const bf16* po = o + (long long)bb * o_bs + (long long)l * o_rs + (long long)hh * D;
+  const bf16* pd = d_o + (long long)bb * do_bs + (long long)l * do_rs + (long long)hh * D;
+  float acc = 0.f;
+  for (int j = 0; j < D; j += 8) {
+    float a[8], c[8];
+    load8(po + j, a);
+    load8(pd + j, c);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fmaf(a[u], c[u], acc);
+  }
+  delta[((long long)bb * H + hh) * L + l] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ host
+int encode_heads(CUtensorMap* tm, const void* ptr, int D, int L, int H, int B, long long rs, long long bs, int box_rows, const char* name) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    pt_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return PT_ECUDA;
+  }
+  PT_REQUIRE(ptr != nullptr, "pt_attn: %s is null", name);
+  PT_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && rs % 8 == 0 && bs % 8 == 0, "pt_attn: %s needs a 16-byte aligned base and strides that are multiples of 8", name);
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)rs * 2, (cuuint64_t)D * 2, (cuuint64_t)(B > 1 ? bs : 8) * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1}, estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pt_set_error("pt_attn: cuTensorMapEncodeTiled(%s) failed: CUresult %d (D=%d L=%d H=%d B=%d rs=%lld bs=%lld)", name, (int)r, D, L, H, B, rs, bs);
+    return PT_ECUDA;
+  }
+  return PT_OK;
+}
+
+template <int MODE, int DP>
+int launch_attn(const AParams& ap, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PT_CUDA_OK(cudaFuncSetAttribute(attn_kernel<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<MODE, DP>::SMEM_BYTES));
+    attr_set = true;
+  }
+  attn_kernel<MODE, DP><<<grid, 320, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+
+template <int MODE>
+int launch_mode(const AParams& ap, dim3 grid, cudaStream_t st) {
+  if (ap.D <= 64) return launch_attn<MODE, 64>(ap, grid, st);
+  if (ap.D <= 128) return launch_attn<MODE, 128>(ap, grid, st);
+  return launch_attn<MODE, 192>(ap, grid, st);
+}
+
+int check_common(const pt_attn_t* a) {
+  PT_REQUIRE(a != nullptr, "pt_attn: null descriptor");
+  PT_REQUIRE(a->B >= 1 && a->H >= 1 && a->Lq >= 1 && a->Lk >= 1, "pt_attn: B=%d H=%d Lq=%d Lk=%d", a->B, a->H, a->Lq, a->Lk);
+  PT_REQUIRE(a->d >= 8 && a->d <= 192 && a->d % 8 == 0, "pt_attn: head dim %d must be a multiple of 8 in [8, 192]", a->d);
+  PT_REQUIRE(a->H <= 65535 && a->B <= 65535, "pt_attn: grid too large");
+  PT_REQUIRE(a->lse != nullptr, "pt_attn: lse is null");
+  return PT_OK;
+}
+
+}  // namespace
+
+extern "C" int pt_attn_fwd(const pt_attn_t* a, void* stream) {
+  if (int r = check_common(a)) return r;
+  PT_REQUIRE(a->o != nullptr && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0 && a->o_rs % 8 == 0 && a->o_bs % 8 == 0, "pt_attn_fwd: output alignment");
+  AParams ap;
+  memset(&ap, 0, sizeof(ap));
+  if (int r = encode_heads(&ap.tmR[0], a->q, a->d, a->Lq, a->H, a->B, a->q_rs, a->q_bs, BM, "q")) return r;
+  if (int r = encode_heads(&ap.tmS[0], a->k, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BN, "k")) return r;
+  if (int r = encode_heads(&ap.tmS[1], a->v, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BN, "v")) return r;
+  ap.Lr = a->Lq;
+  ap.Ls = a->Lk;
+  ap.H = a->H;
+  ap.D = a->d;
+  ap.scale = a->scale;
+  ap.out0 = reinterpret_cast<bf16*>(a->o);
+  ap.o_rs = a->o_rs;
+  ap.o_bs = a->o_bs;
+  ap.lse = a->lse;
+  dim3 grid((a->Lq + BM - 1) / BM, a->H, a->B);
+  return launch_mode<MODE_FWD>(ap, grid, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
+  if (int r = check_common(a)) return r;
+  PT_REQUIRE(a->o && a->d_o && a->dq && a->dk && a->dv && a->delta, "pt_attn_bwd: null pointer");
+  PT_REQUIRE((reinterpret_cast<uintptr_t>(a->o) & 15) == 0 && a->o_rs % 8 == 0 && a->o_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(a->dq) & 15) == 0 &&
+                 a->dq_rs % 8 == 0 && a->dq_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(a->dk) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(a->dv) & 15) == 0 && a->dkv_rs % 8 == 0 && a->dkv_bs % 8 == 0,
+             "pt_attn_bwd: alignment");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    const long long n = (long long)a->B * a->Lq * a->H;
+    attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(a->o), a->o_rs, a->o_bs,
+                                                                   reinterpret_cast<const bf16*>(a->d_o), a->do_rs, a->do_bs, a->delta, a->B, a->H,
+                                                                   a->Lq, a->d);
+    PT_LAUNCH_CHECK();
+  }
+  {  // dQ: resident Q, dO ; streamed K, V
+    AParams ap;
+    memset(&ap, 0, sizeof(ap));
+    if (int r = encode_heads(&ap.tmR[0], a->q, a->d, a->Lq, a->H, a->B, a->q_rs, a->q_bs, BM, "q")) return r;
+    if (int r = encode_heads(&ap.tmR[1], a->d_o, a->d, a->Lq, a->H, a->B, a->do_rs, a->do_bs, BM, "do")) return r;
+    if (int r = encode_heads(&ap.tmS[0], a->k, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BN, "k")) return r;
+    if (int r = encode_heads(&ap.tmS[1], a->v, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BN, "v")) return r;
+    ap.Lr = a->Lq;
+    ap.Ls = a->Lk;
+    ap.H = a->H;
+    ap.D = a->d;
+    ap.scale = a->scale;
+    ap.out0 = reinterpret_cast<bf16*>(a->dq);
+    ap.o_rs = a->dq_rs;
+    ap.o_bs = a->dq_bs;
+    ap.lse = a->lse;
+    ap.delta = a->delta;
+    dim3 grid((a->Lq + BM - 1) / BM, a->H, a->B);
+    if (int r = launch_mode<MODE_DQ>(ap, grid, st)) return r;
+  }
+  {  // dK, dV: resident K, V ; streamed Q, dO
+    AParams ap;
+    memset(&ap, 0, sizeof(ap));
+    if (int r = encode_heads(&ap.tmR[0], a->k, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BM, "k")) return r;
+    if (int r = encode_heads(&ap.tmR[1], a->v, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BM, "v")) return r;
+    if (int r = encode_heads(&ap.tmS[0], a->q, a->d, a->Lq, a->H, a->B, a->q_rs, a->q_bs, BN, "q")) return r;
+    if (int r = encode_heads(&ap.tmS[1], a->d_o, a->d, a->Lq, a->H, a->B, a->do_rs, a->do_bs, BN, "do")) return r;
+    ap.Lr = a->Lk;
+    ap.Ls = a->Lq;
+    ap.H = a->H;
+    ap.D = a->d;
+    ap.scale = a->scale;
+    ap.out0 = reinterpret_cast<bf16*>(a->dv);
+    ap.out1 = reinterpret_cast<bf16*>(a->dk);
+    ap.o_rs = a->dkv_rs;
+    ap.o_bs = a->dkv_bs;
+    ap.lse = a->lse;
+    ap.delta = a->delta;
+    dim3 grid((a->Lk + BM - 1) / BM, a->H, a->B);
+    if (int r = launch_mode<MODE_DKV>(ap, grid, st)) return r;
+  }
+  return PT_OK;
+}

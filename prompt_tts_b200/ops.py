@@ -148,6 +148,44 @@ def softmax_bwd(dP, P, dS, rows, n, ld, scale):
     call("softmax_bwd", _p(dP), _p(P), _p(dS), rows, n, ld, ld, scale, _stream())
 
 
+def _attn_desc(q, k, v, o, lse, heads: int, d: int, scale: float) -> "_lib.Attn":
+    """q [B, Lq, >=H*d] / k, v [B, Lk, >=H*d] / o [B, Lq, >=H*d]: bf16 column-slice views (last stride 1)."""
+    a = _lib.Attn()
+    for t, what in ((q, "q"), (k, "k"), (v, "v"), (o, "o")):
+        _need(t, BF16, "attention " + what)
+        assert t.dim() == 3 and t.stride(2) == 1, (what, t.shape, t.stride())
+    assert k.stride() == v.stride() and k.shape == v.shape
+    _need(lse, F32, "attention lse")
+    B, Lq, _ = q.shape
+    a.q, a.q_rs, a.q_bs = q.data_ptr(), q.stride(1), q.stride(0)
+    a.k, a.v, a.kv_rs, a.kv_bs = k.data_ptr(), v.data_ptr(), k.stride(1), k.stride(0)
+    a.o, a.o_rs, a.o_bs = o.data_ptr(), o.stride(1), o.stride(0)
+    a.lse = lse.data_ptr()
+    a.B, a.H, a.Lq, a.Lk, a.d, a.scale = B, heads, Lq, k.shape[1], d, scale
+    return a
+
+
+def attn_fwd(q, k, v, o, lse, heads: int, d: int, scale: float) -> None:
+    """o = softmax(q k^T * scale) v per head, lse[B, H, Lq] = log-sum-exp of the scaled logits (fused tcgen05 kernel)."""
+    a = _attn_desc(q, k, v, o, lse, heads, d, scale)
+    call("attn_fwd", C.byref(a), _stream())
+
+
+def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, heads: int, d: int, scale: float) -> None:
+    """dq, dk, dv (column-slice views like q, k, v) from d_o; the logits are recomputed from q, k and lse."""
+    a = _attn_desc(q, k, v, o, lse, heads, d, scale)
+    for t, what in ((d_o, "d_o"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
+        _need(t, BF16, "attention " + what)
+        assert t.dim() == 3 and t.stride(2) == 1, (what, t.shape, t.stride())
+    assert dk.stride() == dv.stride()
+    delta = torch.empty_like(lse)
+    a.d_o, a.do_rs, a.do_bs = d_o.data_ptr(), d_o.stride(1), d_o.stride(0)
+    a.dq, a.dq_rs, a.dq_bs = dq.data_ptr(), dq.stride(1), dq.stride(0)
+    a.dk, a.dv, a.dkv_rs, a.dkv_bs = dk.data_ptr(), dv.data_ptr(), dk.stride(1), dk.stride(0)
+    a.delta = delta.data_ptr()
+    call("attn_bwd", C.byref(a), _stream())
+
+
 def geglu_fwd(u2d):
     M, F2 = u2d.shape
     y = torch.empty(M, F2 // 2, dtype=BF16, device=u2d.device)
