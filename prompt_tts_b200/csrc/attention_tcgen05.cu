@@ -22,6 +22,8 @@
 // MN-major as the B operand of stage 2 (only the UMMA descriptor differs).
 #include <math.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -48,28 +50,42 @@ template <int MODE, int DP>
 struct ACfg {
   static constexpr int NX = MODE == MODE_FWD ? 1 : 2;       // stage-1 products per tile
   static constexpr int NACC = MODE == MODE_DKV ? 2 : 1;     // stage-2 accumulators
-  static constexpr int XBUF = (MODE == MODE_DKV && DP > 128) ? 1 : 2;   // TMEM budget: 2*2*64 + 2*192 > 512
+  static constexpr int XBUF = (MODE == MODE_DKV && DP > 128) ? 1 : 2;   // TMEM budget: 2*128 + 2*192 > 512
   static constexpr int KB = DP / 64;                         // 64-element blocks along the head dimension
   static constexpr int R_BYTES = BM * DP * 2;
   static constexpr int S_BYTES = BN * DP * 2;
   static constexpr int STAGE_BYTES = 2 * S_BYTES;
   static constexpr int T_BYTES = BM * BN * 2;
   static constexpr int FIXED = NX * R_BYTES + XBUF * NACC * T_BYTES;
-  static constexpr int NSTAGE = (FIXED + 2 * STAGE_BYTES <= 200 * 1024) ? 2 : 1;
+  static constexpr int BUDGET = 222 * 1024;                  // of 227 KB: leaves room for alignment slack, barriers, statistics
+  static constexpr int NSTAGE_FIT = (BUDGET - FIXED) / STAGE_BYTES;
+  static constexpr int NSTAGE = NSTAGE_FIT >= 4 ? 4 : NSTAGE_FIT;
+  static constexpr int LOOKAHEAD = XBUF == 2 ? (NSTAGE >= 3 ? 2 : (NSTAGE >= 2 ? 1 : 0)) : 0;   // stage-1 MMAs issued ahead of stage 2
   static constexpr int OFF_S = NX * R_BYTES;
   static constexpr int OFF_T = OFF_S + NSTAGE * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_T + XBUF * NACC * T_BYTES;
   static constexpr int OFF_STAT = OFF_BAR + 256;
   static constexpr int STAT_BYTES = 2 * 2 * 2 * BN * 4 + 2 * BM * 4;   // DKV column stats [g][buf][2][BN] + row reduce [2][BM]
   static constexpr int SMEM_BYTES = 1024 + OFF_STAT + STAT_BYTES;
-  static constexpr int X_COLS = XBUF * NX * BN;
+  static constexpr int XW = 128;                             // TMEM columns per X buffer (two 64-column products)
+  static constexpr int X_COLS = XBUF * XW;
   static constexpr int ACC_STRIDE = DP;
   static constexpr int TMEM_USED = X_COLS + NACC * ACC_STRIDE;
   static constexpr int TMEM_COLS = TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512));
+  static_assert(NSTAGE >= 1, "smem budget");
   static_assert(TMEM_USED <= 512, "TMEM budget");
   static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 };
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -99,10 +115,27 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// FWD sweep 2, 32 columns: P = exp2(x * c2 - mc) -> bf16 -> 4 swizzled 16-byte chunks of this thread's T row
+template <bool PARTIAL>
+__device__ __forceinline__ void fwd_chunk(const uint32_t* v, int c, int ncol, float c2, float mc, float& rsum, uint32_t tt, int rsw) {
+  float pv[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float e = ex2f(fmaf(__uint_as_float(v[i]), c2, -mc));
+    if (PARTIAL && c * 32 + i >= ncol) e = 0.f;
+    pv[i] = e;
+    rsum += e;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    sts128(tt + (uint32_t)(((c * 4 + u) ^ rsw) << 4), pack2(pv[u * 8], pv[u * 8 + 1]), pack2(pv[u * 8 + 2], pv[u * 8 + 3]),
+           pack2(pv[u * 8 + 4], pv[u * 8 + 5]), pack2(pv[u * 8 + 6], pv[u * 8 + 7]));
+}
+
 template <int MODE, int DP>
 __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AParams p) {
   using C = ACfg<MODE, DP>;
-  constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE;
+  constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE, LA = C::LOOKAHEAD;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -110,19 +143,20 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
   // barriers
   const uint32_t r_full = bar0;
   auto s_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto s_empty = [&](int s) { return bar0 + 8u * (3 + s); };
-  auto x_full = [&](int g) { return bar0 + 8u * (5 + g); };
-  auto x_empty = [&](int g) { return bar0 + 8u * (7 + g); };
-  auto t_full = [&](int g) { return bar0 + 8u * (9 + g); };
-  auto t_empty = [&](int g) { return bar0 + 8u * (11 + g); };
-  const uint32_t acc_full = bar0 + 8u * 13;
-  const uint32_t tmem_slot = bar0 + 8u * 14;
+  auto s_empty = [&](int s) { return bar0 + 8u * (5 + s); };
+  auto x_full = [&](int g) { return bar0 + 8u * (9 + g); };
+  auto x_empty = [&](int g) { return bar0 + 8u * (11 + g); };
+  auto t_full = [&](int g) { return bar0 + 8u * (13 + g); };
+  auto t_empty = [&](int g) { return bar0 + 8u * (15 + g); };
+  const uint32_t acc_full = bar0 + 8u * 17;
+  const uint32_t tmem_slot = bar0 + 8u * 18;
   float* sstat = reinterpret_cast<float*>(sgen + C::OFF_STAT);          // [g][buf][2][BN]
   float* sred = sstat + 2 * 2 * 2 * BN;                                 // [2][BM]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.Ls + BN - 1) / BN;
+  const int n_tiles1 = (p.Ls + 2 * BN - 1) / (2 * BN);   // FWD sweep 1 walks 128 streamed rows per step
   const int ks1 = (p.D + 15) >> 4;            // stage-1 k-steps (head dim, zero padded to a multiple of 16)
   const int nd = ks1 << 4;                    // stage-2 N
 
@@ -130,9 +164,11 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
     for (int i = 0; i < NX; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmR[i])) : "memory");
     for (int i = 0; i < 2; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmS[i])) : "memory");
     mbar_init(r_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(s_full(s), 1);
       mbar_init(s_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(x_full(s), 1);
       mbar_init(x_empty(s), 128);
       mbar_init(t_full(s), 128);
@@ -148,91 +184,118 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 14);
-  auto xcol = [&](int g, int x) { return (uint32_t)((g * NX + x) * BN); };
+  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 18);
+  auto xcol = [&](int g, int x) { return (uint32_t)(g * C::XW + x * BN); };
   auto acccol = [&](int a) { return (uint32_t)(C::X_COLS + a * C::ACC_STRIDE); };
   auto tT = [&](int g, int a) { return sT + (uint32_t)((g * NACC + a) * C::T_BYTES); };
+  auto gsel = [&](int j) { return XBUF == 2 ? (j & 1) : 0; };
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform control flow, one elected lane issues)
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(r_full, NX * C::R_BYTES);
+#pragma unroll
       for (int x = 0; x < NX; ++x)
+#pragma unroll
         for (int kb = 0; kb < KB; ++kb) tma_load_4d(sR + x * C::R_BYTES + kb * (BM * 128), &p.tmR[x], r_full, kb * 64, r0, h, b);
-      int it = 0;
-      constexpr int NPASS = MODE == MODE_FWD ? 2 : 1;
-      for (int pass = 0; pass < NPASS; ++pass) {
-        const bool first_only = MODE == MODE_FWD && pass == 0;
-        for (int j = 0; j < n_tiles; ++j, ++it) {
-          const int s = it % NSTAGE;
-          mbar_wait(s_empty(s), ((it / NSTAGE) & 1) ^ 1);
-          mbar_expect_tx(s_full(s), first_only ? C::S_BYTES : 2 * C::S_BYTES);
-          const uint32_t dst = sS + s * C::STAGE_BYTES;
-          for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + kb * (BN * 128), &p.tmS[0], s_full(s), kb * 64, j * BN, h, b);
-          if (!first_only)
-            for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + C::S_BYTES + kb * (BN * 128), &p.tmS[1], s_full(s), kb * 64, j * BN, h, b);
-        }
-      }
     }
+    int s = 0, ph = 1;   // ring position / parity to wait for on s_empty
+    auto load_tile = [&](const CUtensorMap* t0, const CUtensorMap* t1, int row0, int row1) {
+      mbar_wait(s_empty(s), ph);
+      if (leader) {
+        mbar_expect_tx(s_full(s), 2 * C::S_BYTES);
+        const uint32_t dst = sS + s * C::STAGE_BYTES;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + kb * (BN * 128), t0, s_full(s), kb * 64, row0, h, b);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + C::S_BYTES + kb * (BN * 128), t1, s_full(s), kb * 64, row1, h, b);
+      }
+      if (++s == NSTAGE) s = 0, ph ^= 1;
+    };
+    if (MODE == MODE_FWD)   // sweep 1: both slots of a stage hold consecutive 64-row tiles of K
+      for (int j = 0; j < n_tiles1; ++j) load_tile(&p.tmS[0], &p.tmS[0], 2 * j * BN, (2 * j + 1) * BN);
+    for (int j = 0; j < n_tiles; ++j) load_tile(&p.tmS[0], &p.tmS[1], j * BN, j * BN);
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc1 = idesc_f16(0, 0, BN, BM);
-      const uint32_t idesc2 = idesc_f16(0, 1, nd, BM);
-      int kx[2] = {0, 0}, kt[2] = {0, 0};
-      mbar_wait(r_full, 0);
-      auto mma1 = [&](int it, int g) {
-        const int s = it % NSTAGE;
-        mbar_wait(s_full(s), (it / NSTAGE) & 1);
-        mbar_wait(x_empty(g), (kx[g] & 1) ^ 1);
-        fence_after();
-        const uint32_t st = sS + s * C::STAGE_BYTES;
-        for (int x = 0; x < NX; ++x)
-          for (int k = 0; k < ks1; ++k) {
-            const uint64_t ad = umma_desc(sR + x * C::R_BYTES + (k >> 2) * (BM * 128) + (k & 3) * 32, 0, 1024);
-            const uint64_t bd = umma_desc(st + x * C::S_BYTES + (k >> 2) * (BN * 128) + (k & 3) * 32, 0, 1024);
-            umma_f16(tmem + xcol(g, x), ad, bd, idesc1, k > 0 ? 1u : 0u);
-          }
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
+    const bool leader = elect_one();
+    const uint32_t idesc1 = idesc_f16(0, 0, BN, BM);
+    const uint32_t idesc2 = idesc_f16(0, 1, nd, BM);
+    // UMMA descriptors are linear in the shared-memory address: precompute the bases, add (bytes >> 4) per use
+    const uint64_t dR = umma_desc(sR, 0, 1024);            // resident tiles, K-major
+    const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view (stage 1)
+    const uint64_t dSmn = umma_desc(sS, BN * 128, 1024);   // streamed tiles, MN-major view (stage 2)
+    const uint64_t dT = umma_desc(sT, 0, 1024);            // transformed tiles, K-major
+    mbar_wait(r_full, 0);
+    int s1 = 0, ph1 = 0;   // ring position / parity of the next stage-1 tile
+    // stage 1 of one tile into X[g]; `use` = how many times X[g] was filled before
+    auto mma1 = [&](int g, int use, auto sweep1) {
+      constexpr bool SWEEP1 = decltype(sweep1)::value;
+      mbar_wait(s_full(s1), ph1);
+      mbar_wait(x_empty(g), (use & 1) ^ 1);
+      fence_after();
+      if (leader) {
+        const uint64_t bS = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
+#pragma unroll
+        for (int x = 0; x < (SWEEP1 ? 2 : NX); ++x) {
+          const uint64_t a0 = dR + (uint64_t)((SWEEP1 ? 0 : x) * (C::R_BYTES >> 4));
+          const uint64_t b0 = bS + (uint64_t)(x * (C::S_BYTES >> 4));
+          const uint32_t dcol = tmem + xcol(g, x);
+#pragma unroll
+          for (int k = 0; k < DP / 16; ++k)
+            if (k < ks1)
+              umma_f16(dcol, a0 + (uint64_t)((k >> 2) * (BM * 128 >> 4) + (k & 3) * 2), b0 + (uint64_t)((k >> 2) * (BN * 128 >> 4) + (k & 3) * 2),
+                       idesc1, k > 0 ? 1u : 0u);
+        }
         umma_commit(x_full(g));
-        ++kx[g];
-      };
-      auto mma2 = [&](int it, int g, bool first) {
-        const int s = it % NSTAGE;
-        mbar_wait(t_full(g), kt[g] & 1);
-        fence_after();
-        const uint32_t st = sS + s * C::STAGE_BYTES;
+        if (SWEEP1) umma_commit(s_empty(s1));
+      }
+      __syncwarp();
+      if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
+    };
+    int s2 = 0;            // ring position of the next stage-2 tile
+    auto mma2 = [&](int g, int use, bool first) {
+      mbar_wait(t_full(g), use & 1);
+      fence_after();
+      if (leader) {
+        const uint64_t bS = dSmn + (uint64_t)(s2 * (C::STAGE_BYTES >> 4));
 #pragma unroll
         for (int a = 0; a < NACC; ++a) {
           // B operand of stage 2, MN-major view of a streamed tile: FWD -> V (S2); DQ -> K (S1); DKV: dV <- dO (S2), dK <- Q (S1)
+          constexpr int dummy = 0;
           const int cs = MODE == MODE_FWD ? 1 : (MODE == MODE_DQ ? 0 : (a == 0 ? 1 : 0));
+          const uint64_t a0 = dT + (uint64_t)((g * NACC + a) * (C::T_BYTES >> 4));
+          const uint64_t b0 = bS + (uint64_t)(cs * (C::S_BYTES >> 4));
+          const uint32_t dcol = tmem + acccol(a);
+          (void)dummy;
 #pragma unroll
-          for (int k = 0; k < BN / 16; ++k) {
-            const uint64_t ad = umma_desc(tT(g, a) + k * 32, 0, 1024);
-            const uint64_t bd = umma_desc(st + cs * C::S_BYTES + k * 2048, BN * 128, 1024);
-            umma_f16(tmem + acccol(a), ad, bd, idesc2, (first && k == 0) ? 0u : 1u);
-          }
+          for (int k = 0; k < BN / 16; ++k) umma_f16(dcol, a0 + (uint64_t)(k * 2), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (first && k == 0) ? 0u : 1u);
         }
         umma_commit(t_empty(g));
-        ++kt[g];
-        umma_commit(s_empty(s));
-      };
-      int it = 0;
-      if (MODE == MODE_FWD) {
-        for (int j = 0; j < n_tiles; ++j, ++it) {
-          mma1(it, XBUF == 2 ? (j & 1) : 0);
-          umma_commit(s_empty(it % NSTAGE));
-        }
+        umma_commit(s_empty(s2));
       }
-      constexpr bool LOOKAHEAD = NSTAGE >= 2 && XBUF == 2;
-      mma1(it, 0);
-      for (int j = 0; j < n_tiles; ++j, ++it) {
-        const int g = XBUF == 2 ? (j & 1) : 0;
-        if (LOOKAHEAD && j + 1 < n_tiles) mma1(it + 1, (j + 1) & 1);
-        mma2(it, g, j == 0);
-        if (!LOOKAHEAD && j + 1 < n_tiles) mma1(it + 1, XBUF == 2 ? ((j + 1) & 1) : 0);
-      }
-      umma_commit(acc_full);
+      __syncwarp();
+      if (++s2 == NSTAGE) s2 = 0;
+    };
+    // X[g] fill counts: sweep-1 step j is fill (j >> 1) of X[j & 1]; main tile j is fill base[g] + (j >> 1)  (XBUF == 1: fill j of X[0])
+    int base0 = 0, base1 = 0;
+    if (MODE == MODE_FWD) {
+      for (int j = 0; j < n_tiles1; ++j) mma1(j & 1, j >> 1, std::true_type{});
+      base0 = (n_tiles1 + 1) >> 1;
+      base1 = n_tiles1 >> 1;
+      s2 = s1;   // the main sweep continues on the ring where sweep 1 stopped
     }
+    auto xuse = [&](int j) { return XBUF == 2 ? ((j & 1) ? base1 : base0) + (j >> 1) : j; };
+    auto tuse = [&](int j) { return XBUF == 2 ? (j >> 1) : j; };
+#pragma unroll
+    for (int a = 0; a < LA; ++a)
+      if (a < n_tiles) mma1(gsel(a), xuse(a), std::false_type{});
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + LA < n_tiles) mma1(gsel(j + LA), xuse(j + LA), std::false_type{});
+      mma2(gsel(j), tuse(j), j == 0);
+    }
+    if (leader) umma_commit(acc_full);
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ transform groups (warps 2-5, 6-9)
     const int g = (warp - 2) >> 2;
@@ -249,30 +312,32 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
     uint32_t v1[32], v2[32];
 
     if (MODE == MODE_FWD) {
-      // ---- sweep 1: exact row maximum of the raw logits
+      // ---- sweep 1: exact row maximum of the raw logits, 128 columns per step
       float m = -INFINITY;
-      if (active)
-        for (int j = g; j < n_tiles; j += jstep) {
-          mbar_wait(x_full(g), kx & 1);
-          fence_after();
-          const int ncol = min(BN, p.Ls - j * BN);
+      for (int j = g; j < n_tiles1; j += 2) {
+        mbar_wait(x_full(g), kx & 1);
+        fence_after();
+        const int ncol = min(2 * BN, p.Ls - j * 2 * BN);
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
-            tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
-            tmem_wait_ld();
-            if (ncol >= (c + 1) * 32) {
+        for (int c = 0; c < 4; c += 2) {
+          tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
+          tmem_ld32(tl + xcol(g, 0) + (c + 1) * 32, v2);
+          tmem_wait_ld();
+          if (ncol >= (c + 2) * 32) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v1[i]));
-            } else {
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
+          } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i < ncol) m = fmaxf(m, __uint_as_float(v1[i]));
+            for (int i = 0; i < 32; ++i) {
+              if (c * 32 + i < ncol) m = fmaxf(m, __uint_as_float(v1[i]));
+              if ((c + 1) * 32 + i < ncol) m = fmaxf(m, __uint_as_float(v2[i]));
             }
           }
-          fence_before();
-          mbar_arrive(x_empty(g));
-          ++kx;
         }
+        fence_before();
+        mbar_arrive(x_empty(g));
+        ++kx;
+      }
       sred[g * BM + row] = m;
       asm volatile("bar.sync 2, 256;" ::: "memory");
       m = fmaxf(sred[row], sred[BM + row]);
@@ -280,37 +345,29 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
       const float mc = m * c2;
       // ---- sweep 2: P = exp(s - m) -> T[g] (bf16, K-major, SWIZZLE_128B) ; partial row sums
       float rsum = 0.f;
-      if (active)
-        for (int j = g; j < n_tiles; j += jstep) {
-          mbar_wait(x_full(g), kx & 1);
-          fence_after();
-          mbar_wait(t_empty(g), (kt & 1) ^ 1);
-          const int ncol = min(BN, p.Ls - j * BN);
-          const uint32_t tt = tT(g, 0) + trow;
-#pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
-            tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
-            tmem_wait_ld();
-            float pv[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float e = ex2f(fmaf(__uint_as_float(v1[i]), c2, -mc));
-              if (ncol < BN && c * 32 + i >= ncol) e = 0.f;
-              pv[i] = e;
-              rsum += e;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              sts128(tt + (uint32_t)(((c * 4 + u) ^ rsw) << 4), pack2(pv[u * 8], pv[u * 8 + 1]), pack2(pv[u * 8 + 2], pv[u * 8 + 3]),
-                     pack2(pv[u * 8 + 4], pv[u * 8 + 5]), pack2(pv[u * 8 + 6], pv[u * 8 + 7]));
-          }
-          fence_before();
-          mbar_arrive(x_empty(g));
-          fence_async_smem();
-          mbar_arrive(t_full(g));
-          ++kx;
-          ++kt;
+      for (int j = g; j < n_tiles; j += 2) {
+        mbar_wait(x_full(g), kx & 1);
+        fence_after();
+        tmem_ld32(tl + xcol(g, 0), v1);
+        tmem_ld32(tl + xcol(g, 0) + 32, v2);
+        tmem_wait_ld();
+        fence_before();
+        mbar_arrive(x_empty(g));
+        mbar_wait(t_empty(g), (kt & 1) ^ 1);
+        const int ncol = min(BN, p.Ls - j * BN);
+        const uint32_t tt = tT(g, 0) + trow;
+        if (ncol == BN) {
+          fwd_chunk<false>(v1, 0, ncol, c2, mc, rsum, tt, rsw);
+          fwd_chunk<false>(v2, 1, ncol, c2, mc, rsum, tt, rsw);
+        } else {
+          fwd_chunk<true>(v1, 0, ncol, c2, mc, rsum, tt, rsw);
+          fwd_chunk<true>(v2, 1, ncol, c2, mc, rsum, tt, rsw);
         }
+        fence_async_smem();
+        mbar_arrive(t_full(g));
+        ++kx;
+        ++kt;
+      }
       sred[g * BM + row] = rsum;
       asm volatile("bar.sync 2, 256;" ::: "memory");
       rsum = sred[row] + sred[BM + row];
@@ -347,7 +404,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
       }
       if (active)
         for (int j = g; j < n_tiles; j += jstep) {
-          const float* cst = nullptr;
+          const float4* cst = nullptr;
           if (MODE == MODE_DKV) {
             // column statistics of this tile (columns = query rows): lse * log2(e) (+inf masks the column), delta * scale
             float* st = sstat + ((g * 2 + (kx & 1)) * 2) * BN;
@@ -363,11 +420,10 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
               st[BN + tg] = d;
             }
             asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
-            cst = st;
+            cst = reinterpret_cast<const float4*>(st);
           }
           mbar_wait(x_full(g), kx & 1);
           fence_after();
-          mbar_wait(t_empty(g), (kt & 1) ^ 1);
           const uint32_t tt0 = tT(g, 0) + trow;
           const uint32_t tt1 = tT(g, NACC - 1) + trow;
 #pragma unroll
@@ -375,20 +431,31 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
             tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
             tmem_ld32(tl + xcol(g, 1) + c * 32, v2);
             tmem_wait_ld();
+            if (c == BN / 32 - 1) {
+              fence_before();
+              mbar_arrive(x_empty(g));
+            }
+            if (c == 0) mbar_wait(t_empty(g), (kt & 1) ^ 1);
             uint32_t pp[16], dd[16];
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float pe[2], de[2];
+            for (int i = 0; i < 32; i += 4) {
+              float l4[4] = {lse2, lse2, lse2, lse2}, d4[4] = {dl, dl, dl, dl};
+              if (MODE == MODE_DKV) {
+                const float4 a = cst[(c * 32 + i) >> 2], d = cst[(BN + c * 32 + i) >> 2];
+                l4[0] = a.x, l4[1] = a.y, l4[2] = a.z, l4[3] = a.w;
+                d4[0] = d.x, d4[1] = d.y, d4[2] = d.z, d4[3] = d.w;
+              }
+              float pe[4], de[4];
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const float l2 = MODE == MODE_DKV ? cst[c * 32 + i + u] : lse2;
-                const float dv = MODE == MODE_DKV ? cst[BN + c * 32 + i + u] : dl;
-                const float e = ex2f(fmaf(__uint_as_float(v1[i + u]), c2, -l2));
+              for (int u = 0; u < 4; ++u) {
+                const float e = ex2f(fmaf(__uint_as_float(v1[i + u]), c2, -l4[u]));
                 pe[u] = e;
-                de[u] = e * fmaf(__uint_as_float(v2[i + u]), p.scale, -dv);
+                de[u] = e * fmaf(__uint_as_float(v2[i + u]), p.scale, -d4[u]);
               }
               pp[i >> 1] = pack2(pe[0], pe[1]);
+              pp[(i >> 1) + 1] = pack2(pe[2], pe[3]);
               dd[i >> 1] = pack2(de[0], de[1]);
+              dd[(i >> 1) + 1] = pack2(de[2], de[3]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -397,8 +464,6 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
               sts128(tt1 + off, dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
             }
           }
-          fence_before();
-          mbar_arrive(x_empty(g));
           fence_async_smem();
           mbar_arrive(t_full(g));
           ++kx;

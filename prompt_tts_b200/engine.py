@@ -296,55 +296,28 @@ def layernorm(tape: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor, eps: 
 # ------------------------------------------------------------------------------------------------ attention core
 def attention_core(tape: Tape, q_src: Var, q_off: int, kv_src: Var, k_off: int, v_off: int, heads: int, C: int) -> Var:
     """softmax(Q K^T / sqrt(d)) V with Q = q_src[..., q_off:q_off+C], K/V column slices of kv_src (no mask, no dropout:
-    diffusers AttnProcessor2_0 as the reference uses it).  q_src [B, Lq, Wq], kv_src [B, Lk, Wkv]."""
+    diffusers AttnProcessor2_0 as the reference uses it).  q_src [B, Lq, Wq], kv_src [B, Lk, Wkv].  One fused tcgen05
+    kernel forward (logits stay in TMEM), three backward (delta, dQ, dK/dV) that recompute the logits from the saved
+    log-sum-exp; gradients land in place in column slices of fused-projection-shaped buffers."""
     qd, kvd = q_src.data, kv_src.data
-    B, Lq, Wq = qd.shape
-    Lk, Wkv = kvd.shape[1], kvd.shape[2]
+    B, Lq, _ = qd.shape
     d = C // heads
     scale = d ** -0.5
-    Lkp = (Lk + 7) // 8 * 8
-
-    def heads_view(t, off):       # [B, L, W] -> [B, H, L, d] strided view
-        return t[:, :, off:off + C].unflatten(2, (heads, d)).permute(0, 2, 1, 3)
-
-    qv, kv_, vv = heads_view(qd, q_off), heads_view(kvd, k_off), heads_view(kvd, v_off)
-    S = torch.empty(B, heads, Lq, Lkp, dtype=F32, device=qd.device)
-    ops.gemm([ops.operand(qv, True, batched=True)], [ops.operand(kv_, True, batched=True)], [ops.segment(d)], Lq, Lk, S,
-             out_strides=(Lkp, Lq * Lkp, heads * Lq * Lkp), out_mode=OUT_F32, nz2=heads, nz3=B, alpha=scale)
-    P = torch.empty(B, heads, Lq, Lkp, dtype=BF16, device=qd.device)
-    ops.softmax_fwd(S, P, B * heads * Lq, Lk, Lkp)
-    del S
+    qv, kv_, vv = qd[:, :, q_off:q_off + C], kvd[:, :, k_off:k_off + C], kvd[:, :, v_off:v_off + C]
     o = torch.empty(B, Lq, C, dtype=BF16, device=qd.device)
-    Pv = P[..., :Lk]
-    ops.gemm([ops.operand(Pv, True, batched=True)], [ops.operand(vv, False, batched=True)], [ops.segment(Lk)], Lq, d, o,
-             out_strides=(C, d, Lq * C), nz2=heads, nz3=B)
+    lse = torch.empty(B, heads, Lq, dtype=F32, device=qd.device)
+    ops.attn_fwd(qv, kv_, vv, o, lse, heads, d, scale)
     y = Var(o)
 
     def bwd():
         do = y.grad
         if do is None:
             return
-        dov = do.unflatten(2, (heads, d)).permute(0, 2, 1, 3)            # [B, H, Lq, d]
         same = q_src is kv_src
         dq_buf = torch.empty_like(qd)
         dkv_buf = dq_buf if same else torch.empty_like(kvd)
-        dqv, dkv, dvv = heads_view(dq_buf, q_off), heads_view(dkv_buf, k_off), heads_view(dkv_buf, v_off)
-        # dV = P^T dO
-        ops.gemm([ops.operand(Pv, False, batched=True)], [ops.operand(dov, False, batched=True)], [ops.segment(Lq)], Lk, d, dvv,
-                 out_strides=(Wkv, d, Lk * Wkv), nz2=heads, nz3=B)
-        # dP = dO V^T  (fp32)
-        dP = torch.empty(B, heads, Lq, Lkp, dtype=F32, device=qd.device)
-        ops.gemm([ops.operand(dov, True, batched=True)], [ops.operand(vv, True, batched=True)], [ops.segment(d)], Lq, Lk, dP,
-                 out_strides=(Lkp, Lq * Lkp, heads * Lq * Lkp), out_mode=OUT_F32, nz2=heads, nz3=B)
-        dS = torch.empty(B, heads, Lq, Lkp, dtype=BF16, device=qd.device)
-        ops.softmax_bwd(dP, P, dS, B * heads * Lq, Lk, Lkp, scale)
-        del dP
-        dSv = dS[..., :Lk]
-        # dQ = dS K ; dK = dS^T Q
-        ops.gemm([ops.operand(dSv, True, batched=True)], [ops.operand(kv_, False, batched=True)], [ops.segment(Lk)], Lq, d, dqv,
-                 out_strides=(Wq, d, Lq * Wq), nz2=heads, nz3=B)
-        ops.gemm([ops.operand(dSv, False, batched=True)], [ops.operand(qv, False, batched=True)], [ops.segment(Lq)], Lk, d, dkv,
-                 out_strides=(Wkv, d, Lk * Wkv), nz2=heads, nz3=B)
+        ops.attn_bwd(qv, kv_, vv, o, lse, do, dq_buf[:, :, q_off:q_off + C], dkv_buf[:, :, k_off:k_off + C],
+                     dkv_buf[:, :, v_off:v_off + C], heads, d, scale)
         accum(q_src, dq_buf, owned=True)
         if not same:
             accum(kv_src, dkv_buf, owned=True)
