@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0 && n_iters > 0) {
+    // ------------------------------------------------------------ TMA producer (warp-uniform control flow, one elected lane issues)
+    if (n_iters > 0) {
+      const bool leader = elect_one();
       // locate (seg, rep, kb) of it_begin
       int seg = 0, rep = 0, kb = 0, skip = it_begin;
       while (true) {
@@ -132,33 +133,35 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
         ++seg;
       }
       const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_kmajor ? BN * BK * 2 : C::B_STAGE_BYTES);
+      int s = 0;
+      uint32_t ph = 1;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (it / C::STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), tx_bytes);
+        mbar_wait(empty_bar(s), ph);
         const pt_segment_t& sg = p.seg[seg];
-        const uint32_t sa = smem_base + s * C::STAGE_BYTES;
-        const uint32_t sb = sa + A_STAGE_BYTES;
-        const CUtensorMap* ta = &p.tmA[sg.a_idx];
-        const CUtensorMap* tb = &p.tmB[sg.b_idx];
-        const int bz2 = sg.rep_is_batch ? (sg.rep_c2_0 + rep) : z2;
-        const int a2 = p.a_batched[sg.a_idx] ? bz2 : 0, a3 = p.a_batched[sg.a_idx] ? z3 : 0;
-        const int b2 = p.b_batched[sg.b_idx] ? bz2 : 0, b3 = p.b_batched[sg.b_idx] ? z3 : 0;
-        const int ka = sg.a_k0 + kb * BK, kbb = sg.b_k0 + kb * BK;
-        if (p.a_kmajor) {
-          tma_load_4d(sa, ta, full_bar(s), ka, m0 + sg.a_mn_shift, a2, a3);
-        } else {
+        if (leader) {
+          mbar_expect_tx(full_bar(s), tx_bytes);
+          const uint32_t sa = smem_base + s * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const CUtensorMap* ta = &p.tmA[sg.a_idx];
+          const CUtensorMap* tb = &p.tmB[sg.b_idx];
+          const int bz2 = sg.rep_is_batch ? (sg.rep_c2_0 + rep) : z2;
+          const int a2 = p.a_batched[sg.a_idx] ? bz2 : 0, a3 = p.a_batched[sg.a_idx] ? z3 : 0;
+          const int b2 = p.b_batched[sg.b_idx] ? bz2 : 0, b3 = p.b_batched[sg.b_idx] ? z3 : 0;
+          const int ka = sg.a_k0 + kb * BK, kbb = sg.b_k0 + kb * BK;
+          if (p.a_kmajor) {
+            tma_load_4d(sa, ta, full_bar(s), ka, m0 + sg.a_mn_shift, a2, a3);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_4d(sa + j * (BK * 128), ta, full_bar(s), m0 + sg.a_mn_shift + j * 64, ka, a2, a3);
-        }
-        if (p.b_kmajor) {
-          tma_load_4d(sb, tb, full_bar(s), kbb, n0 + sg.b_mn_shift, b2, b3);
-        } else {
+            for (int j = 0; j < BM / 64; ++j) tma_load_4d(sa + j * (BK * 128), ta, full_bar(s), m0 + sg.a_mn_shift + j * 64, ka, a2, a3);
+          }
+          if (p.b_kmajor) {
+            tma_load_4d(sb, tb, full_bar(s), kbb, n0 + sg.b_mn_shift, b2, b3);
+          } else {
 #pragma unroll
-          for (int j = 0; j < C::BN_S / 64; ++j) tma_load_4d(sb + j * (BK * 128), tb, full_bar(s), n0 + sg.b_mn_shift + j * 64, kbb, b2, b3);
+            for (int j = 0; j < C::BN_S / 64; ++j) tma_load_4d(sb + j * (BK * 128), tb, full_bar(s), n0 + sg.b_mn_shift + j * 64, kbb, b2, b3);
+          }
         }
-        // advance (seg, rep, kb)
+        // advance (seg, rep, kb) and the ring position
         const int nkb = (sg.nk + BK - 1) / BK;
         if (++kb == nkb) {
           kb = 0;
@@ -167,32 +170,36 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
             ++seg;
           }
         }
+        if (++s == C::STAGES) s = 0, ph ^= 1;
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && n_iters > 0) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
+    if (n_iters > 0) {
+      const bool leader = elect_one();
       // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((p.a_kmajor ? 0u : 1u) << 15) | ((p.b_kmajor ? 0u : 1u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = idesc_f16(p.a_kmajor ? 0 : 1, p.b_kmajor ? 0 : 1, BN, BM);
       const uint32_t a_lbo = p.a_kmajor ? 0u : (uint32_t)(BK * 128), b_lbo = p.b_kmajor ? 0u : (uint32_t)(BK * 128);
-      const uint32_t a_kstep = p.a_kmajor ? 32u : 2048u, b_kstep = p.b_kmajor ? 32u : 2048u;  // bytes per UMMA_K=16
+      const uint32_t a_kstep = p.a_kmajor ? 2u : 128u, b_kstep = p.b_kmajor ? 2u : 128u;  // (bytes >> 4) per UMMA_K=16
+      // UMMA descriptors are linear in the shared-memory address: bases once, (bytes >> 4) added per use
+      const uint64_t adesc0 = umma_desc(smem_base, a_lbo, 1024);
+      const uint64_t bdesc0 = umma_desc(smem_base + A_STAGE_BYTES, b_lbo, 1024);
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (it / C::STAGES) & 1;
         mbar_wait(full_bar(s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_base + s * C::STAGE_BYTES;
-        const uint32_t sb = sa + A_STAGE_BYTES;
+        if (leader) {
+          const uint64_t ad = adesc0 + (uint64_t)(s * (C::STAGE_BYTES >> 4));
+          const uint64_t bd = bdesc0 + (uint64_t)(s * (C::STAGE_BYTES >> 4));
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ad = umma_desc(sa + k * a_kstep, a_lbo, 1024);
-          const uint64_t bd = umma_desc(sb + k * b_kstep, b_lbo, 1024);
-          umma_f16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base, ad + (uint64_t)(k * a_kstep), bd + (uint64_t)(k * b_kstep), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+          if (it == n_iters - 1) umma_commit(tmem_full_bar);
         }
-        umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+        __syncwarp();
+        if (++s == C::STAGES) s = 0, ph ^= 1;
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
