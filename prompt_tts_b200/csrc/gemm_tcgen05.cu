@@ -42,8 +42,9 @@ struct alignas(64) KParams {
   int nseg;
   int a_kmajor, b_kmajor;
   int a_batched[2], b_batched[2];
-  int M, N, nz2, nz3, splitk;
-  int total_iters, iters_per_split;
+  int M, N, nz2, nz3;
+  int mt, nt, tiles, work, streamk;
+  int total_iters;
   void* out;
   int out_dtype;
   long long osm, osz2, osz3;
@@ -61,40 +62,76 @@ struct Cfg {
   static constexpr int BN_S = (BN + 63) / 64 * 64;       // smem rows reserved for B (MN-major needs whole 64-blocks)
   static constexpr int B_STAGE_BYTES = BN_S * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BN <= 64 ? 4 : (BN <= 128 ? 3 : 4);
-  static constexpr int TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
-  static constexpr int EPI_COLS = (BN >= 160 && BN % 64 == 0) ? 64 : 32;   // columns per epilogue pass (BN <= 128 keeps 2 CTAs per SM)
-  static constexpr int EPI_BYTES = 4 * 32 * (EPI_COLS * 2 + 16);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/ + 1024 /*bias*/ + EPI_BYTES;
+  static constexpr int CTAS_PER_SM = BN <= 128 ? 2 : 1;  // narrow tiles: two persistent CTAs per SM hide each other's issue latency
+  static constexpr int EPI_COLS = (BN % 64 == 0 && CTAS_PER_SM == 1) ? 64 : 32;   // columns per epilogue pass
+  static constexpr int EPI_BF16_BYTES = 4 * 32 * (EPI_COLS * 2 + 16);
+  static constexpr int EPI_F32_BYTES = CTAS_PER_SM == 1 ? 4 * 32 * 33 * 4 : 4 * 32 * 17 * 4;   // fp32 transpose tile per warp: 32 x 32 (+1) or 32 x 16 (+1)
+  static constexpr int EPI_BYTES = EPI_BF16_BYTES > EPI_F32_BYTES ? EPI_BF16_BYTES : EPI_F32_BYTES;
+  static constexpr int F32_COLS = CTAS_PER_SM == 1 ? 32 : 16;   // columns per transpose pass of the atomic epilogue
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int BIAS_BYTES = 1024;
+  static constexpr int AUX_BYTES = 1024 /*align slack*/ + BAR_BYTES + BIAS_BYTES + EPI_BYTES;
+  static constexpr int STAGES_FIT = (227 * 1024 / CTAS_PER_SM - AUX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // two accumulators
+};
+
+// Work distribution of the persistent kernel.  Data-parallel: CTA c takes output tiles c, c+G, ... whole.
+// Stream-K (fp32 atomic-accumulate outputs only): the (tile, k-iteration) space is cut into G equal contiguous ranges,
+// so every SM gets the same number of MMA iterations whatever the tile count; a range that crosses a tile boundary
+// yields one segment per tile, each flushed with atomic adds.
+struct Sched {
+  int total_iters, streamk, cursor, end, stride;
+  __device__ __forceinline__ Sched(const KParams& p) {
+    total_iters = p.total_iters;
+    streamk = p.streamk;
+    if (streamk) {
+      const int per = (p.work + (int)gridDim.x - 1) / (int)gridDim.x;
+      cursor = min(p.work, (int)blockIdx.x * per);
+      end = min(p.work, cursor + per);
+      stride = 0;
+    } else {
+      cursor = blockIdx.x;
+      end = p.tiles;
+      stride = gridDim.x;
+    }
+  }
+  __device__ __forceinline__ bool next(int& tile, int& it_begin, int& it_end) {
+    if (cursor >= end) return false;
+    if (streamk) {
+      tile = cursor / total_iters;
+      it_begin = cursor - tile * total_iters;
+      it_end = min(total_iters, it_begin + (end - cursor));
+      cursor += it_end - it_begin;
+    } else {
+      tile = cursor;
+      it_begin = 0;
+      it_end = total_iters;
+      cursor += stride;
+    }
+    return true;
+  }
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const __grid_constant__ KParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
-  // barriers: full[S], empty[S], tmem_full ; then tmem ptr slot
+  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2] ; then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 1);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  float* sbias = reinterpret_cast<float*>(sgen + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+  uint8_t* sepi = sgen + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::BIAS_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
-  int z = blockIdx.z;
-  const int zs = z % p.splitk;
-  z /= p.splitk;
-  const int z2 = z % p.nz2;
-  const int z3 = z / p.nz2;
-
-  const int it_begin = zs * p.iters_per_split;
-  const int it_end = min(p.total_iters, it_begin + p.iters_per_split);
-  const int n_iters = it_end - it_begin;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA[p.seg[0].a_idx])) : "memory");
@@ -103,7 +140,10 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -113,12 +153,32 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(sgen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+  // tile index -> (m0, n0, z2, z3); m fastest so that concurrently running CTAs share one B (weight) tile through L2
+  auto decode = [&](int tile, int& m0, int& n0, int& z2, int& z3) {
+    const int mt = tile % p.mt;
+    int r = tile / p.mt;
+    const int nt = r % p.nt;
+    r /= p.nt;
+    m0 = mt * BM;
+    n0 = nt * BN;
+    z2 = r % p.nz2;
+    z3 = r / p.nz2;
+  };
+
+  Sched sched(p);
+  int tile, it_begin, it_end;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform control flow, one elected lane issues)
-    if (n_iters > 0) {
-      const bool leader = elect_one();
+    const bool leader = elect_one();
+    const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_kmajor ? BN * BK * 2 : C::B_STAGE_BYTES);
+    int s = 0;
+    uint32_t ph = 1;
+    while (sched.next(tile, it_begin, it_end)) {
+      int m0, n0, z2, z3;
+      decode(tile, m0, n0, z2, z3);
       // locate (seg, rep, kb) of it_begin
       int seg = 0, rep = 0, kb = 0, skip = it_begin;
       while (true) {
@@ -132,10 +192,7 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
         skip -= cnt;
         ++seg;
       }
-      const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_kmajor ? BN * BK * 2 : C::B_STAGE_BYTES);
-      int s = 0;
-      uint32_t ph = 1;
-      for (int it = 0; it < n_iters; ++it) {
+      for (int it = it_begin; it < it_end; ++it) {
         mbar_wait(empty_bar(s), ph);
         const pt_segment_t& sg = p.seg[seg];
         if (leader) {
@@ -175,174 +232,218 @@ __global__ void __launch_bounds__(192) gemm_kernel(const __grid_constant__ KPara
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
-    if (n_iters > 0) {
-      const bool leader = elect_one();
-      // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
-      const uint32_t idesc = idesc_f16(p.a_kmajor ? 0 : 1, p.b_kmajor ? 0 : 1, BN, BM);
-      const uint32_t a_lbo = p.a_kmajor ? 0u : (uint32_t)(BK * 128), b_lbo = p.b_kmajor ? 0u : (uint32_t)(BK * 128);
-      const uint32_t a_kstep = p.a_kmajor ? 2u : 128u, b_kstep = p.b_kmajor ? 2u : 128u;  // (bytes >> 4) per UMMA_K=16
-      // UMMA descriptors are linear in the shared-memory address: bases once, (bytes >> 4) added per use
-      const uint64_t adesc0 = umma_desc(smem_base, a_lbo, 1024);
-      const uint64_t bdesc0 = umma_desc(smem_base + A_STAGE_BYTES, b_lbo, 1024);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_iters; ++it) {
+    const bool leader = elect_one();
+    // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+    const uint32_t idesc = idesc_f16(p.a_kmajor ? 0 : 1, p.b_kmajor ? 0 : 1, BN, BM);
+    const uint32_t a_lbo = p.a_kmajor ? 0u : (uint32_t)(BK * 128), b_lbo = p.b_kmajor ? 0u : (uint32_t)(BK * 128);
+    const uint32_t a_kstep = p.a_kmajor ? 2u : 128u, b_kstep = p.b_kmajor ? 2u : 128u;  // (bytes >> 4) per UMMA_K=16
+    // UMMA descriptors are linear in the shared-memory address: bases once, (bytes >> 4) added per use
+    const uint64_t adesc0 = umma_desc(smem_base, a_lbo, 1024);
+    const uint64_t bdesc0 = umma_desc(smem_base + A_STAGE_BYTES, b_lbo, 1024);
+    int s = 0;
+    uint32_t ph = 0;
+    int segi = 0;
+    while (sched.next(tile, it_begin, it_end)) {
+      const int acc = segi & 1;
+      mbar_wait(tmem_empty_bar(acc), ((segi >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t dcol = tmem_base + (uint32_t)(acc * BN);
+      for (int it = it_begin; it < it_end; ++it) {
         mbar_wait(full_bar(s), ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (leader) {
           const uint64_t ad = adesc0 + (uint64_t)(s * (C::STAGE_BYTES >> 4));
           const uint64_t bd = bdesc0 + (uint64_t)(s * (C::STAGE_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base, ad + (uint64_t)(k * a_kstep), bd + (uint64_t)(k * b_kstep), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(dcol, ad + (uint64_t)(k * a_kstep), bd + (uint64_t)(k * b_kstep), idesc, (it > it_begin || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
-          if (it == n_iters - 1) umma_commit(tmem_full_bar);
+          if (it == it_end - 1) umma_commit(tmem_full_bar(acc));
         }
         __syncwarp();
         if (++s == C::STAGES) s = 0, ph ^= 1;
       }
+      ++segi;
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    // While the mainloop runs: stage the per-column additive term (bias + per-batch time shift) in shared memory.
+    // ------------------------------------------------------------ epilogue (warps 2..5), overlapped with the next segment's mainloop
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int et = threadIdx.x - 64;
-    float* sbias = reinterpret_cast<float*>(smem_raw + (bar_base + 128 - smem_u32(smem_raw)));
-    {
-      const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.bz2_stride : nullptr;
-      for (int j = et; j < BN; j += 128) {
-        const int n = n0 + j;
-        float b = 0.f;
-        if (n < p.N) {
-          if (p.bias) b += __ldg(p.bias + n);
-          if (bz) b += __ldg(bz + n);
+    int segi = 0;
+    while (sched.next(tile, it_begin, it_end)) {
+      int m0, n0, z2, z3;
+      decode(tile, m0, n0, z2, z3);
+      const int acc = segi & 1;
+      // stage the per-column additive term (bias + per-batch time shift) in shared memory
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with the previous segment's sbias
+      {
+        const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.bz2_stride : nullptr;
+        for (int j = et; j < BN; j += 128) {
+          const int n = n0 + j;
+          float bsum = 0.f;
+          if (n < p.N) {
+            if (p.bias) bsum += __ldg(p.bias + n);
+            if (bz) bsum += __ldg(bz + n);
+          }
+          sbias[j] = bsum;
         }
-        sbias[j] = b;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    if (n_iters > 0 && p.out_dtype == PT_OUT_BF16) {
-      // ---- bf16 output (+ optional bf16 residual): every global access is a full 64/128-byte row segment.
-      // Accumulator rows live one per thread; a warp-private padded smem tile transposes between "thread = row"
-      // and "8 (or 4) lanes = one contiguous row segment".
-      constexpr int CH = C::EPI_COLS;            // columns per pass (64 or 32)
-      constexpr int NPASS = BN / CH;
-      constexpr int VPR = CH / 8;                // 16-byte vectors per row segment
-      constexpr int RPI = 32 / VPR;              // rows covered by one warp-wide access
-      constexpr int NIT = 32 / RPI;              // accesses per pass
-      constexpr int PITCH = CH * 2 + 16;         // bytes, padded: conflict-free for both access patterns
-      uint8_t* stg = smem_raw + (bar_base + 128 + 1024 - smem_u32(smem_raw)) + q * (32 * PITCH);
-      const int mw = m0 + q * 32;                // first row of this warp
-      const int crow = lane / VPR, cvec = lane % VPR;
-      const long long zoff_o = (long long)z2 * p.osz2 + (long long)z3 * p.osz3;
-      const long long zoff_r = (long long)z2 * p.rsz2 + (long long)z3 * p.rsz3;
-      bf16* outp = reinterpret_cast<bf16*>(p.out);
-      const bool has_res = p.res != nullptr;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-      uint32_t v[2][CH];
-      bf16x8 rr[2][NIT];
-      auto load_res = [&](int pass, bf16x8* dst) {
-        const int nb = n0 + pass * CH + cvec * 8;
-#pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-          const int m = mw + crow + i * RPI;
-          if (m < p.M && nb < p.N) dst[i] = *reinterpret_cast<const bf16x8*>(p.res + zoff_r + (long long)m * p.rsm + nb);
-        }
-      };
-      if (has_res) load_res(0, rr[0]);
-      mbar_wait(tmem_full_bar, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int h = 0; h < CH / 32; ++h) tmem_ld32(tbase + h * 32, v[0] + h * 32);
-#pragma unroll
-      for (int c = 0; c < NPASS; ++c) {
-        const int nb = n0 + c * CH;
-        if (nb < p.N) {  // warp-uniform
-          __syncwarp();
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (c + 1 < NPASS && nb + CH < p.N) {
-#pragma unroll
-            for (int h = 0; h < CH / 32; ++h) tmem_ld32(tbase + (uint32_t)((c + 1) * CH + h * 32), v[(c + 1) & 1] + h * 32);
-            if (has_res) load_res(c + 1, rr[(c + 1) & 1]);
-          }
-          if (has_res) {
-#pragma unroll
-            for (int i = 0; i < NIT; ++i) *reinterpret_cast<bf16x8*>(stg + (crow + i * RPI) * PITCH + cvec * 16) = rr[c & 1][i];
-            __syncwarp();
-          }
-#pragma unroll
-          for (int g = 0; g < VPR; ++g) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][g * 8 + j]), p.alpha, sbias[c * CH + g * 8 + j]);
-            bf16x8* cell = reinterpret_cast<bf16x8*>(stg + lane * PITCH + g * 16);   // this thread's row, vector g
-            if (has_res) {
-              const bf16x8 t = *cell;
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const float2 u = __bfloat1622float2(t.v[h]);
-                f[2 * h] += u.x;
-                f[2 * h + 1] += u.y;
-              }
-            }
-            bf16x8 t;
-#pragma unroll
-            for (int h = 0; h < 4; ++h) t.v[h] = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
-            *cell = t;
-          }
-          __syncwarp();
-          const int ncol = nb + cvec * 8;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t full_parity = (segi >> 1) & 1;
+      if (p.out_dtype == PT_OUT_BF16) {
+        // ---- bf16 output (+ optional bf16 residual): every global access is a full 64/128-byte row segment.
+        // Accumulator rows live one per thread; a warp-private padded smem tile transposes between "thread = row"
+        // and "8 (or 4) lanes = one contiguous row segment".
+        constexpr int CH = C::EPI_COLS;            // columns per pass (64 or 32)
+        constexpr int NPASS = BN / CH;
+        constexpr int VPR = CH / 8;                // 16-byte vectors per row segment
+        constexpr int RPI = 32 / VPR;              // rows covered by one warp-wide access
+        constexpr int NIT = 32 / RPI;              // accesses per pass
+        constexpr int PITCH = CH * 2 + 16;         // bytes, padded: conflict-free for both access patterns
+        uint8_t* stg = sepi + q * (32 * PITCH);
+        const int mw = m0 + q * 32;                // first row of this warp
+        const int crow = lane / VPR, cvec = lane % VPR;
+        const long long zoff_o = (long long)z2 * p.osz2 + (long long)z3 * p.osz3;
+        const long long zoff_r = (long long)z2 * p.rsz2 + (long long)z3 * p.rsz3;
+        bf16* outp = reinterpret_cast<bf16*>(p.out);
+        const bool has_res = p.res != nullptr;
+        const int last_c = min(NPASS, (p.N - n0 + CH - 1) / CH) - 1;   // last pass with columns inside N
+        uint32_t v[2][CH];
+        bf16x8 rr[2][NIT];
+        auto load_res = [&](int pass, bf16x8* dst) {
+          const int nb = n0 + pass * CH + cvec * 8;
 #pragma unroll
           for (int i = 0; i < NIT; ++i) {
             const int m = mw + crow + i * RPI;
-            if (m < p.M && ncol < p.N)
-              *reinterpret_cast<bf16x8*>(outp + zoff_o + (long long)m * p.osm + ncol) =
-                  *reinterpret_cast<const bf16x8*>(stg + (crow + i * RPI) * PITCH + cvec * 16);
+            if (m < p.M && nb < p.N) dst[i] = *reinterpret_cast<const bf16x8*>(p.res + zoff_r + (long long)m * p.rsm + nb);
           }
-        }
-      }
-    } else if (n_iters > 0) {
-      // ---- fp32 store / fp32 atomic accumulate (logits, tiny MLP outputs, weight gradients): one row per thread
-      const int m = m0 + q * 32 + lane;
-      const bool m_ok = m < p.M;
-      const long long out_off = (long long)z2 * p.osz2 + (long long)z3 * p.osz3 + (long long)m * p.osm;
-      constexpr int NCH = BN / 32;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-      uint32_t v[2][32];
-      mbar_wait(tmem_full_bar, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tmem_ld32(tbase, v[0]);
+        };
+        if (has_res) load_res(0, rr[0]);
+        mbar_wait(tmem_full_bar(acc), full_parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int nb = n0 + c * 32;
-        if (nb < p.N) {  // warp-uniform
-          __syncwarp();
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (c + 1 < NCH && nb + 32 < p.N) tmem_ld32(tbase + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
-          float f[32];
+        for (int h = 0; h < CH / 32; ++h) tmem_ld32(tbase + h * 32, v[0] + h * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][j]), p.alpha, sbias[c * 32 + j]);
-          if (m_ok) {
-            if (p.out_dtype == PT_OUT_F32) {
-              float* o = reinterpret_cast<float*>(p.out) + out_off + nb;
+        for (int c = 0; c < NPASS; ++c) {
+          const int nb = n0 + c * CH;
+          if (c <= last_c) {  // warp-uniform
+            __syncwarp();
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c < last_c) {
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (nb + g * 4 + 4 <= p.N) {
-                  *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
-                } else {
+              for (int h = 0; h < CH / 32; ++h) tmem_ld32(tbase + (uint32_t)((c + 1) * CH + h * 32), v[(c + 1) & 1] + h * 32);
+              if (has_res) load_res(c + 1, rr[(c + 1) & 1]);
+            } else {
+              // the accumulator is in registers: hand the TMEM buffer back to the MMA warp
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              mbar_arrive(tmem_empty_bar(acc));
+            }
+            if (has_res) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (nb + g * 4 + j < p.N) o[g * 4 + j] = f[g * 4 + j];
+              for (int i = 0; i < NIT; ++i) *reinterpret_cast<bf16x8*>(stg + (crow + i * RPI) * PITCH + cvec * 16) = rr[c & 1][i];
+              __syncwarp();
+            }
+#pragma unroll
+            for (int g = 0; g < VPR; ++g) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][g * 8 + j]), p.alpha, sbias[c * CH + g * 8 + j]);
+              bf16x8* cell = reinterpret_cast<bf16x8*>(stg + lane * PITCH + g * 16);   // this thread's row, vector g
+              if (has_res) {
+                const bf16x8 t = *cell;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const float2 u = __bfloat1622float2(t.v[h]);
+                  f[2 * h] += u.x;
+                  f[2 * h + 1] += u.y;
                 }
               }
-            } else {
-              float* o = reinterpret_cast<float*>(p.out) + out_off + (long long)nb * p.osn;
+              bf16x8 t;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) atomicAdd(o + j * p.osn, f[j]);
+              for (int h = 0; h < 4; ++h) t.v[h] = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
+              *cell = t;
+            }
+            __syncwarp();
+            const int ncol = nb + cvec * 8;
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+              const int m = mw + crow + i * RPI;
+              if (m < p.M && ncol < p.N)
+                *reinterpret_cast<bf16x8*>(outp + zoff_o + (long long)m * p.osm + ncol) =
+                    *reinterpret_cast<const bf16x8*>(stg + (crow + i * RPI) * PITCH + cvec * 16);
+            }
+          }
+        }
+      } else {
+        // ---- fp32 store / fp32 atomic accumulate (tiny MLP outputs, weight gradients): one row per thread
+        const int m = m0 + q * 32 + lane;
+        const bool m_ok = m < p.M;
+        const long long out_off = (long long)z2 * p.osz2 + (long long)z3 * p.osz3 + (long long)m * p.osm;
+        constexpr int NCH = BN / 32;
+        const int last_c = min(NCH, (p.N - n0 + 31) / 32) - 1;
+        uint32_t v[2][32];
+        mbar_wait(tmem_full_bar(acc), full_parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_ld32(tbase, v[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int nb = n0 + c * 32;
+          if (c <= last_c) {  // warp-uniform
+            __syncwarp();
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c < last_c) {
+              tmem_ld32(tbase + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
+            } else {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              mbar_arrive(tmem_empty_bar(acc));
+            }
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][j]), p.alpha, sbias[c * 32 + j]);
+            if (m_ok) {
+              if (p.out_dtype == PT_OUT_F32) {
+                float* o = reinterpret_cast<float*>(p.out) + out_off + nb;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  if (nb + g * 4 + 4 <= p.N) {
+                    *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      if (nb + g * 4 + j < p.N) o[g * 4 + j] = f[g * 4 + j];
+                  }
+                }
+              }
+            }
+            if (p.out_dtype == PT_OUT_F32_ATOMIC_ADD) {
+              // transpose through a warp-private tile so that one warp-wide RED covers consecutive columns of one row
+              // (8 floats per 32-byte L2 sector instead of 1)
+              constexpr int FC = C::F32_COLS;
+              float* tile = reinterpret_cast<float*>(sepi) + q * (32 * (FC + 1));
+              const int mrow0 = m0 + q * 32;
+              const long long zoff = (long long)z2 * p.osz2 + (long long)z3 * p.osz3;
+#pragma unroll
+              for (int hh = 0; hh < 32 / FC; ++hh) {
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < FC; ++j) tile[lane * (FC + 1) + j] = f[hh * FC + j];
+                __syncwarp();
+                const int col = lane % FC, rsub = lane / FC;          // FC == 32: one row per instruction; FC == 16: two rows
+                const int n = nb + hh * FC + col;
+                if (n < p.N) {
+                  float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)n * p.osn;
+#pragma unroll 8
+                  for (int r = rsub; r < 32; r += 32 / FC) {
+                    if (mrow0 + r < p.M) atomicAdd(o + (long long)(mrow0 + r) * p.osm, tile[r * (FC + 1) + col]);
+                  }
+                }
+              }
             }
           }
         }
       }
+      ++segi;
     }
   }
 
@@ -406,10 +507,8 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   PT_REQUIRE(g != nullptr, "pt_gemm: null descriptor");
   PT_REQUIRE(g->nseg >= 1 && g->nseg <= 8, "pt_gemm: nseg=%d", g->nseg);
   PT_REQUIRE(g->M >= 1 && g->N >= 1, "pt_gemm: M=%d N=%d", g->M, g->N);
-  PT_REQUIRE(g->nz2 >= 1 && g->nz3 >= 1 && g->splitk >= 1, "pt_gemm: bad batch/split");
+  PT_REQUIRE(g->nz2 >= 1 && g->nz3 >= 1, "pt_gemm: bad batch extents");
   PT_REQUIRE(g->out != nullptr, "pt_gemm: null output");
-  PT_REQUIRE(g->splitk == 1 || g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: split-K needs PT_OUT_F32_ATOMIC_ADD");
-  PT_REQUIRE(g->splitk == 1 || (g->bias == nullptr && g->bias_z2 == nullptr && g->residual == nullptr), "pt_gemm: split-K with bias/residual");
   if (g->out_dtype == PT_OUT_BF16) {
     PT_REQUIRE(g->N % 8 == 0 && g->out_stride_m % 8 == 0 && g->out_stride_z2 % 8 == 0 && g->out_stride_z3 % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(g->out) & 15) == 0,
@@ -449,16 +548,37 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
     if (b_used[i]) PT_REQUIRE(g->b[i].kmajor == kp.b_kmajor, "pt_gemm: B operands must share one majorness");
   }
 
-  // tile width
+  // tile width: cost model fitted to tools/gemm_sweep.py on B200 (profiles/r01_gemm_sweep.txt).  One k-iteration (BK = 64) of a
+  // 128 x bn tile costs ~800 / 640 / 430 / 260 cycles for bn = 256 / 160 / 128 / 64 (operand delivery from L2 dominates,
+  // which favours wide tiles).  Data-parallel launches are paced by the busiest SM (ceil(tiles / SMs) tiles); stream-K
+  // launches are balanced but pay one atomic flush of a tile per segment (~0.65 cycles per flushed column-row).
+  const bool streamk = g->out_dtype == PT_OUT_F32_ATOMIC_ADD;
+  PT_REQUIRE(!streamk || (g->bias == nullptr && g->bias_z2 == nullptr && g->residual == nullptr),
+             "pt_gemm: PT_OUT_F32_ATOMIC_ADD outputs are scheduled stream-K and take no bias/residual");
   int bn = g->block_n;
   const long long mt = (g->M + BM - 1) / BM;
-  const long long zz = (long long)g->nz2 * g->nz3 * g->splitk;
+  const long long zz = (long long)g->nz2 * g->nz3;
+  const int sms = pt_num_sms();
   if (bn == 0) {
-    const int sms = pt_num_sms();
-    if (g->N % 256 == 0 && mt * (g->N / 256) * zz >= sms) bn = 256;
-    else if (kp.b_kmajor && g->N % 160 == 0 && g->N % 128 != 0 && mt * (g->N / 160) * zz >= sms / 2) bn = 160;
-    else if (g->N > 64 && (g->N % 128 == 0 || g->N % 128 > 64 || g->N > 512)) bn = 128;
-    else bn = 64;
+    const int cand[4] = {256, 128, 64, 160};
+    const double cyc[4] = {800.0, 430.0, 260.0, 640.0};
+    double best = 1e300;
+    for (int i = 0; i < 4; ++i) {
+      const int c = cand[i];
+      if (c == 160 && !(g->N % 160 == 0 && g->N % 128 != 0 && g->N <= 640)) continue;   // only where it removes ragged waste
+      const long long tiles_c = mt * ((g->N + c - 1) / c) * zz;
+      double cost;
+      if (streamk) {
+        const double slots_c = (double)sms * (c <= 128 ? 2 : 1);
+        cost = (double)tiles_c * (double)total * cyc[i] / sms + 0.65 * ((double)tiles_c + slots_c) * c;
+      } else {
+        cost = (double)((tiles_c + sms - 1) / sms) * ((double)total * cyc[i] + 1500.0);
+      }
+      if (cost < best * 0.97) {   // ties go to the earlier (wider) candidate
+        best = cost;
+        bn = c;
+      }
+    }
   }
   PT_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "pt_gemm: block_n=%d", bn);
 
@@ -480,8 +600,14 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   kp.nz2 = g->nz2;
   kp.nz3 = g->nz3;
   kp.total_iters = (int)total;
-  kp.iters_per_split = (int)((total + g->splitk - 1) / g->splitk);
-  kp.splitk = (int)((total + kp.iters_per_split - 1) / kp.iters_per_split);
+  const long long nt = (g->N + bn - 1) / bn;
+  const long long tiles = mt * nt * zz;
+  PT_REQUIRE(tiles * total < (1ll << 31), "pt_gemm: work space too large");
+  kp.mt = (int)mt;
+  kp.nt = (int)nt;
+  kp.tiles = (int)tiles;
+  kp.work = (int)(tiles * total);
+  kp.streamk = streamk ? 1 : 0;
   kp.out = g->out;
   kp.out_dtype = g->out_dtype;
   kp.osm = g->out_stride_m;
@@ -498,11 +624,11 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   kp.osn = g->out_stride_n ? g->out_stride_n : 1;
   PT_REQUIRE(kp.osn == 1 || g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: out_stride_n needs PT_OUT_F32_ATOMIC_ADD");
 
-  const long long gz = (long long)g->nz2 * g->nz3 * kp.splitk;
-  PT_REQUIRE(gz <= 65535, "pt_gemm: grid.z=%lld too large", gz);
-  const long long gy = (g->N + bn - 1) / bn;
-  PT_REQUIRE(gy <= 65535, "pt_gemm: grid.y too large");
-  dim3 grid((unsigned)mt, (unsigned)gy, (unsigned)gz);
+  // persistent grid: one CTA per SM for the wide tiles, two for the narrow ones (fewer when there is less work)
+  const long long slots = (long long)sms * (bn <= 128 ? 2 : 1);
+  long long G = streamk ? (kp.work / 4 > 0 ? kp.work / 4 : 1) : tiles;
+  if (G > slots) G = slots;
+  dim3 grid((unsigned)G, 1, 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
     case 64: return launch<64>(kp, grid, st);
