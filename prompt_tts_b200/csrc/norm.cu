@@ -5,59 +5,107 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm statistics.  grid = (column blocks of 256 channels, row chunks, batch).  A warp reads 32 consecutive
-// 16-byte vectors of a row; the 8 warps take rows w, w+8, ... four at a time, so per-channel partials stay in
-// registers; they are folded into per-group sums through shared memory and one atomicAdd per (CTA, group).
+// GroupNorm.  All four kernels share one mapping: grid = (row chunks, batch); a CTA has nvec * rpp threads
+// (nvec = C / 8 sixteen-byte vectors per row); thread t owns vector t % nvec of rows r0 + t / nvec, + rpp, ...
+// Consecutive threads touch consecutive 16-byte vectors (also across a row boundary), so every warp access is one
+// contiguous 512-byte segment, and everything that depends only on the channel -- folded normalisation coefficients,
+// per-channel partial sums -- lives in registers for the whole row loop.  Reductions go registers -> shared memory
+// (one slot per thread, no atomics) -> per-channel -> per-group, then one global atomic per value per CTA.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ sums, int L, int C, int G,
-                                                       int rows_per_cta) {
-  extern __shared__ float sh[];  // [2*G]
-  const int b = blockIdx.z;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 256 + lane * 8;
-  const int r0 = blockIdx.y * rows_per_cta;
-  const int r1 = min(L, r0 + rows_per_cta);
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  if (c < C) {
-    float s[8], q[8];
+__device__ __forceinline__ float sigmoid_fast(float z) {   // one MUFU op (exp + rcp would be two: these kernels are MUFU-bound otherwise)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  return fmaf(0.5f, t, 0.5f);
+}
+
+struct GnMap {
+  int nvec, rpp, threads, v, rsub;
+};
+__device__ __forceinline__ GnMap gn_map(int C) {
+  GnMap m;
+  m.nvec = C >> 3;
+  m.threads = blockDim.x;
+  m.rpp = m.threads / m.nvec;
+  m.v = threadIdx.x % m.nvec;
+  m.rsub = threadIdx.x / m.nvec;
+  return m;
+}
+
+// per-channel (a, b) with  gn(x) * gamma + beta = x * a + b  for this thread's 8 channels
+__device__ __forceinline__ void gn_coeffs(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int b,
+                                          int c0, int cpg, int G, float* a1, float* b1, float* rs, float* ms) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    const bf16* xb = x + ((long long)b * L) * C + c;
-    int r = r0 + warp;
-    for (; r + 24 < r1; r += 32) {
-      float f[4][8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) load8(xb + (long long)(r + 8 * u) * C, f[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s[j] += f[u][j];
-          q[j] += f[u][j] * f[u][j];
-        }
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
+    const float gm = gamma[c0 + j];
+    a1[j] = rstd * gm;
+    b1[j] = beta[c0 + j] - mean * rstd * gm;
+    if (rs) {
+      rs[j] = rstd;
+      ms[j] = -mean * rstd;
     }
-    for (; r < r1; r += 8) {
-      float f[8];
-      load8(xb + (long long)r * C, f);
+  }
+}
+
+__global__ void __launch_bounds__(320) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ sums, int L, int C, int G, int rows_per_cta) {
+  extern __shared__ float sh[];  // [threads][16] partials, reused as [C][2]
+  const GnMap m = gn_map(C);
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(L, r0 + rows_per_cta);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const bf16* xb = x + ((long long)b * L) * C + m.v * 8;
+  int r = r0 + m.rsub;
+  for (; r + 3 * m.rpp < r1; r += 4 * m.rpp) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(xb + (long long)(r + u * m.rpp) * C, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        q[j] += f[j] * f[j];
+        s[j] += f[u][j];
+        q[j] = fmaf(f[u][j], f[u][j], q[j]);
       }
-    }
-    const int cpg = C / G;
+  }
+  for (; r < r1; r += m.rpp) {
+    float f[8];
+    load8(xb + (long long)r * C, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      atomicAdd(&sh[2 * g], s[j]);
-      atomicAdd(&sh[2 * g + 1], q[j]);
+      s[j] += f[j];
+      q[j] = fmaf(f[j], f[j], q[j]);
     }
+  }
+  // fold the rpp row-phases: slot [rsub][channel][2]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh[((m.rsub * C) + m.v * 8 + j) * 2] = s[j];
+    sh[((m.rsub * C) + m.v * 8 + j) * 2 + 1] = q[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += m.threads) {
+    float a = sh[c * 2], d = sh[c * 2 + 1];
+    for (int k = 1; k < m.rpp; ++k) {
+      a += sh[(k * C + c) * 2];
+      d += sh[(k * C + c) * 2 + 1];
+    }
+    sh[c * 2] = a;
+    sh[c * 2 + 1] = d;
   }
   __syncthreads();
   const int cpg = C / G;
-  const int g0 = (blockIdx.x * 256) / cpg, g1 = min(G - 1, (min(C, blockIdx.x * 256 + 256) - 1) / cpg);
-  for (int i = 2 * g0 + threadIdx.x; i <= 2 * g1 + 1; i += blockDim.x) atomicAdd(&sums[(long long)b * 2 * G + i], sh[i]);
+  for (int g = threadIdx.x; g < G; g += m.threads) {
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      a += sh[(g * cpg + k) * 2];
+      d += sh[(g * cpg + k) * 2 + 1];
+    }
+    atomicAdd(&sums[((long long)b * G + g) * 2], a);
+    atomicAdd(&sums[((long long)b * G + g) * 2 + 1], d);
+  }
 }
 
 __global__ void gn_finalize_kernel(float* __restrict__ stats, int n, float inv_count, float eps) {
@@ -70,218 +118,198 @@ __global__ void gn_finalize_kernel(float* __restrict__ stats, int n, float inv_c
   }
 }
 
-// y = act(x * a[c] + b[c]) with a = rstd*gamma, b = beta - mean*a held in shared memory per batch element.
-__global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, bf16* __restrict__ y, int L, int C, int G, int rows_per_cta, int act) {
-  extern __shared__ float sh[];  // a[C], b[C]
-  float* sa = sh;
-  float* sb = sh + C;
+// y = act(x * a[c] + b[c]) with a = rstd*gamma, b = beta - mean*a
+__global__ void __launch_bounds__(320) gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, bf16* __restrict__ y, int L, int C, int G, int rows_per_cta,
+                                                       int act) {
+  const GnMap m = gn_map(C);
   const int b = blockIdx.y;
-  const int cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
-    const float a = rstd * gamma[c];
-    sa[c] = a;
-    sb[c] = beta[c] - mean * a;
-  }
-  __syncthreads();
-  const int nvec = C >> 3;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(L, r0 + rows_per_cta);
-  const bf16* xb = x + ((long long)b * L + r0) * C;
-  bf16* yb = y + ((long long)b * L + r0) * C;
-  const int total = (r1 - r0) * nvec;   // the chunk is contiguous: vector i covers elements [8i, 8i+8)
-  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(L, r0 + rows_per_cta);
+  float a1[8], b1[8];
+  gn_coeffs(stats, gamma, beta, b, m.v * 8, C / G, G, a1, b1, nullptr, nullptr);
+  const long long base = ((long long)b * L) * C + m.v * 8;
+  int r = r0 + m.rsub;
+  for (; r + 3 * m.rpp < r1; r += 4 * m.rpp) {
     float f[4][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < total) load8(xb + (long long)i * 8, f[u]);
-    }
+    for (int u = 0; u < 4; ++u) load8(x + base + (long long)(r + u * m.rpp) * C, f[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < total) {
-        const int v = i % nvec;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float z = f[u][j] * sa[v * 8 + j] + sb[v * 8 + j];
-          f[u][j] = act ? silu_f(z) : z;
-        }
-        store8(yb + (long long)i * 8, f[u]);
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(f[u][j], a1[j], b1[j]);
+        f[u][j] = act ? z * sigmoid_fast(z) : z;
       }
+      store8(y + base + (long long)(r + u * m.rpp) * C, f[u]);
     }
+  }
+  for (; r < r1; r += m.rpp) {
+    float f[8];
+    load8(x + base + (long long)r * C, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(f[j], a1[j], b1[j]);
+      f[j] = act ? z * sigmoid_fast(z) : z;
+    }
+    store8(y + base + (long long)r * C, f);
   }
 }
 
 // backward pass 1: per-channel sum(dz), sum(dz*xhat) -> dgamma/dbeta (global atomics) and
-// per-(b,g) s1 = sum(dz*gamma), s2 = sum(dz*gamma*xhat) -> scratch.  Same tiling as gn_stats_kernel.
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
+// per-(b,g) s1 = sum(dz*gamma), s2 = sum(dz*gamma*xhat) -> scratch.
+__global__ void __launch_bounds__(320) gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ scratch,
                                                             int L, int C, int G, int rows_per_cta, int act) {
-  extern __shared__ float sh[];  // [2*G] group sums, then [8][256][2] per-warp channel partials
-  float* chp = sh + 2 * G;
-  const int b = blockIdx.z;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 256 + lane * 8;
-  const int r0 = blockIdx.y * rows_per_cta;
-  const int r1 = min(L, r0 + rows_per_cta);
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
+  extern __shared__ float sh[];  // [rpp][C][2]
+  const GnMap m = gn_map(C);
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(L, r0 + rows_per_cta);
   const int cpg = C / G;
-  float sdz[8], sdzx[8];
+  float a1[8], b1[8], rs[8], ms[8], sdz[8], sdzx[8];
+  gn_coeffs(stats, gamma, beta, b, m.v * 8, cpg, G, a1, b1, rs, ms);
 #pragma unroll
   for (int j = 0; j < 8; ++j) sdz[j] = sdzx[j] = 0.f;
-  if (c < C) {
-    float mean[8], rstd[8], gm[8], bt[8];
+  const long long base = ((long long)b * L) * C + m.v * 8;
+  auto body = [&](const float* fx, const float* fd) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      mean[j] = stats[((long long)b * G + g) * 2];
-      rstd[j] = stats[((long long)b * G + g) * 2 + 1];
-      gm[j] = gamma[c + j];
-      bt[j] = beta[c + j];
-    }
-    const long long base = ((long long)b * L) * C + c;
-    int r = r0 + warp;
-    for (; r + 8 < r1; r += 16) {
-      float fx[2][8], fd[2][8];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        load8(x + base + (long long)(r + 8 * u) * C, fx[u]);
-        load8(dy + base + (long long)(r + 8 * u) * C, fd[u]);
+      float dz = fd[j];
+      if (act) {
+        const float z = fmaf(fx[j], a1[j], b1[j]);
+        const float sg = sigmoid_fast(z);
+        dz *= sg * fmaf(z, 1.f - sg, 1.f);
       }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (fx[u][j] - mean[j]) * rstd[j];
-          float dz = fd[u][j];
-          if (act) dz *= silu_grad_f(xh * gm[j] + bt[j]);
-          sdz[j] += dz;
-          sdzx[j] += dz * xh;
-        }
+      sdz[j] += dz;
+      sdzx[j] = fmaf(dz, fmaf(fx[j], rs[j], ms[j]), sdzx[j]);
     }
-    for (; r < r1; r += 8) {
-      float fx[8], fd[8];
-      load8(x + base + (long long)r * C, fx);
-      load8(dy + base + (long long)r * C, fd);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (fx[j] - mean[j]) * rstd[j];
-        float dz = fd[j];
-        if (act) dz *= silu_grad_f(xh * gm[j] + bt[j]);
-        sdz[j] += dz;
-        sdzx[j] += dz * xh;
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    chp[(warp * 256 + lane * 8 + j) * 2] = sdz[j];
-    chp[(warp * 256 + lane * 8 + j) * 2 + 1] = sdzx[j];
-  }
-  __syncthreads();
-  const int cc = blockIdx.x * 256 + threadIdx.x;
-  if (cc < C) {
-    float a = 0.f, bsum = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      a += chp[(w * 256 + threadIdx.x) * 2];
-      bsum += chp[(w * 256 + threadIdx.x) * 2 + 1];
-    }
-    atomicAdd(&dbeta[cc], a);
-    atomicAdd(&dgamma[cc], bsum);
-    const int g = cc / cpg;
-    const float gmc = gamma[cc];
-    atomicAdd(&sh[2 * g], a * gmc);
-    atomicAdd(&sh[2 * g + 1], bsum * gmc);
-  }
-  __syncthreads();
-  const int g0 = (blockIdx.x * 256) / cpg, g1 = min(G - 1, (min(C, blockIdx.x * 256 + 256) - 1) / cpg);
-  for (int i = 2 * g0 + threadIdx.x; i <= 2 * g1 + 1; i += blockDim.x) atomicAdd(&scratch[(long long)b * 2 * G + i], sh[i]);
-}
-
-// backward pass 2: dx = rstd * (dz*gamma - s1/n - xhat * s2/n)
-__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
-                                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scratch,
-                                    bf16* __restrict__ dx, int L, int C, int G, int rows_per_cta, int act) {
-  extern __shared__ float sh[];  // per channel: mean, rstd, gamma, beta, k1 (= s1/n), k2 (= s2/n)
-  float* s_mean = sh;
-  float* s_rstd = sh + C;
-  float* s_g = sh + 2 * C;
-  float* s_b = sh + 3 * C;
-  float* s_k1 = sh + 4 * C;
-  float* s_k2 = sh + 5 * C;
-  const int b = blockIdx.y;
-  const int cpg = C / G;
-  const float inv_n = 1.f / ((float)cpg * (float)L);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    s_mean[c] = stats[((long long)b * G + g) * 2];
-    s_rstd[c] = stats[((long long)b * G + g) * 2 + 1];
-    s_g[c] = gamma[c];
-    s_b[c] = beta[c];
-    s_k1[c] = scratch[((long long)b * G + g) * 2] * inv_n;
-    s_k2[c] = scratch[((long long)b * G + g) * 2 + 1] * inv_n;
-  }
-  __syncthreads();
-  const int nvec = C >> 3;
-  const int r0 = blockIdx.x * rows_per_cta;
-  const int r1 = min(L, r0 + rows_per_cta);
-  const long long base = ((long long)b * L + r0) * C;
-  const int total = (r1 - r0) * nvec;
-  for (int i0 = threadIdx.x; i0 < total; i0 += 2 * blockDim.x) {
+  };
+  int r = r0 + m.rsub;
+  for (; r + m.rpp < r1; r += 2 * m.rpp) {
     float fx[2][8], fd[2][8];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < total) {
-        load8(x + base + (long long)i * 8, fx[u]);
-        load8(dy + base + (long long)i * 8, fd[u]);
+      load8(x + base + (long long)(r + u * m.rpp) * C, fx[u]);
+      load8(dy + base + (long long)(r + u * m.rpp) * C, fd[u]);
+    }
+    body(fx[0], fd[0]);
+    body(fx[1], fd[1]);
+  }
+  for (; r < r1; r += m.rpp) {
+    float fx[8], fd[8];
+    load8(x + base + (long long)r * C, fx);
+    load8(dy + base + (long long)r * C, fd);
+    body(fx, fd);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sh[((m.rsub * C) + m.v * 8 + j) * 2] = sdz[j];
+    sh[((m.rsub * C) + m.v * 8 + j) * 2 + 1] = sdzx[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += m.threads) {
+    float a = sh[c * 2], d = sh[c * 2 + 1];
+    for (int k = 1; k < m.rpp; ++k) {
+      a += sh[(k * C + c) * 2];
+      d += sh[(k * C + c) * 2 + 1];
+    }
+    atomicAdd(&dbeta[c], a);
+    atomicAdd(&dgamma[c], d);
+    const float gmc = gamma[c];
+    sh[c * 2] = a * gmc;
+    sh[c * 2 + 1] = d * gmc;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += m.threads) {
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      a += sh[(g * cpg + k) * 2];
+      d += sh[(g * cpg + k) * 2 + 1];
+    }
+    atomicAdd(&scratch[((long long)b * G + g) * 2], a);
+    atomicAdd(&scratch[((long long)b * G + g) * 2 + 1], d);
+  }
+}
+
+// backward pass 2: dx = rstd * (dz*gamma - s1/n - xhat * s2/n)  =  dz * a1 + x * c2 + c3   (per-channel coefficients in registers)
+__global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ scratch, bf16* __restrict__ dx, int L, int C, int G,
+                                                           int rows_per_cta, int act) {
+  const GnMap m = gn_map(C);
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(L, r0 + rows_per_cta);
+  const int cpg = C / G;
+  const float inv_n = 1.f / ((float)cpg * (float)L);
+  float a1[8], b1[8], c2[8], c3[8];
+  {
+    float rs[8], ms[8];
+    gn_coeffs(stats, gamma, beta, b, m.v * 8, cpg, G, a1, b1, rs, ms);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (m.v * 8 + j) / cpg;
+      const float k1 = scratch[((long long)b * G + g) * 2] * inv_n, k2 = scratch[((long long)b * G + g) * 2 + 1] * inv_n;
+      c2[j] = -rs[j] * rs[j] * k2;            // -rstd^2 k2
+      c3[j] = -rs[j] * k1 - ms[j] * rs[j] * k2;   // -rstd k1 + mean rstd^2 k2   (ms = -mean rstd)
+    }
+  }
+  const long long base = ((long long)b * L) * C + m.v * 8;
+  auto body = [&](const float* fx, float* fd) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float dz = fd[j];
+      if (act) {
+        const float z = fmaf(fx[j], a1[j], b1[j]);
+        const float sg = sigmoid_fast(z);
+        dz *= sg * fmaf(z, 1.f - sg, 1.f);
       }
+      fd[j] = fmaf(dz, a1[j], fmaf(fx[j], c2[j], c3[j]));
+    }
+  };
+  int r = r0 + m.rsub;
+  for (; r + m.rpp < r1; r += 2 * m.rpp) {
+    float fx[2][8], fd[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      load8(x + base + (long long)(r + u * m.rpp) * C, fx[u]);
+      load8(dy + base + (long long)(r + u * m.rpp) * C, fd[u]);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < total) {
-        const int v = i % nvec;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = v * 8 + j;
-          const float xh = (fx[u][j] - s_mean[c]) * s_rstd[c];
-          float dz = fd[u][j];
-          if (act) dz *= silu_grad_f(xh * s_g[c] + s_b[c]);
-          fd[u][j] = s_rstd[c] * (dz * s_g[c] - s_k1[c] - xh * s_k2[c]);
-        }
-        store8(dx + base + (long long)i * 8, fd[u]);
-      }
+      body(fx[u], fd[u]);
+      store8(dx + base + (long long)(r + u * m.rpp) * C, fd[u]);
     }
+  }
+  for (; r < r1; r += m.rpp) {
+    float fx[8], fd[8];
+    load8(x + base + (long long)r * C, fx);
+    load8(dy + base + (long long)r * C, fd);
+    body(fx, fd);
+    store8(dx + base + (long long)r * C, fd);
   }
 }
 
 struct GnGeom {
-  int rpp, threads, rows_per_cta, chunks;   // elementwise passes: grid (chunks, B)
-  int cblocks, red_rows, red_chunks;         // reduction passes: grid (cblocks, red_chunks, B)
+  int threads, rpp;
+  int rows_apply, chunks_apply;   // elementwise passes: grid (chunks, B)
+  int rows_red, chunks_red;       // reduction passes (fewer CTAs: each flushes 2C + 2G atomics)
 };
 int gn_geom(int B, int L, int C, GnGeom* g) {
   const int nvec = C / 8;
-  PT_REQUIRE(C % 8 == 0 && nvec <= 1024, "groupnorm: C=%d must be a multiple of 8 and <= 8192", C);
-  g->rpp = nvec >= 256 ? 1 : 256 / nvec;
-  g->threads = (nvec * g->rpp + 31) / 32 * 32;
-  int want = (4 * pt_num_sms() + B - 1) / B;  // chunks per batch element
-  int rows = (L + want - 1) / want;
-  rows = (rows + g->rpp - 1) / g->rpp * g->rpp;
-  if (rows < 4 * g->rpp) rows = 4 * g->rpp;
-  g->rows_per_cta = rows;
-  g->chunks = (L + rows - 1) / rows;
-  g->cblocks = (C + 255) / 256;
-  int rwant = (8 * pt_num_sms() + B * g->cblocks - 1) / (B * g->cblocks);
-  int rr = (L + rwant - 1) / rwant;
-  if (rr < 32) rr = 32;
-  g->red_rows = rr;
-  g->red_chunks = (L + rr - 1) / rr;
+  PT_REQUIRE(C % 8 == 0 && nvec >= 1 && nvec <= 320, "groupnorm: C=%d must be a multiple of 8 and <= 2560", C);
+  g->rpp = nvec >= 160 ? 1 : (256 / nvec > 0 ? 256 / nvec : 1);
+  if (g->rpp > L) g->rpp = L;
+  g->threads = nvec * g->rpp;
+  auto pick = [&](int target_ctas, int min_rows_per_thread, int* rows, int* chunks) {
+    int want = (target_ctas + B - 1) / B;
+    int r = (L + want - 1) / want;
+    if (r < min_rows_per_thread * g->rpp) r = min_rows_per_thread * g->rpp;
+    r = (r + g->rpp - 1) / g->rpp * g->rpp;
+    *rows = r;
+    *chunks = (L + r - 1) / r;
+  };
+  pick(6 * pt_num_sms(), 4, &g->rows_apply, &g->chunks_apply);
+  pick(3 * pt_num_sms(), 8, &g->rows_red, &g->chunks_red);
   return PT_OK;
 }
 
@@ -290,51 +318,67 @@ int gn_geom(int B, int L, int C, GnGeom* g) {
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 8;
 
-template <int NV>
+template <int NV, int ROWS>
 __global__ void ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                               bf16* __restrict__ y, float* __restrict__ rowstats, long long M, int C, float eps) {
+  // one warp per ROWS consecutive rows, all of them in flight at once (small C: one row is too few bytes per warp)
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= M) return;
   const int nvec = C >> 3;
-  float f[NV][8];
-  float s = 0.f;
+  float f[ROWS][NV][8];
+  float s[ROWS];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      load8(x + row * C + v * 8, f[i]);
+  for (int r = 0; r < ROWS; ++r) {
+    s[r] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[i][j];
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec && row0 + r < M) load8(x + (row0 + r) * C + v * 8, f[r][i]);
     }
   }
-  const float mean = warp_sum(s) / (float)C;
-  float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
+  for (int r = 0; r < ROWS; ++r) {
+    if (row0 + r >= M) break;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[i][j] - mean;
-        q += d * d;
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[r] += f[r][i][j];
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    const float mean = warp_sum(s[r]) / (float)C;
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      float o[8];
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * __ldg(gamma + v * 8 + j) + __ldg(beta + v * 8 + j);
-      store8(y + row * C + v * 8, o);
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[r][i][j] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
     }
-  }
-  if (lane == 0) {
-    rowstats[2 * row] = mean;
-    rowstats[2 * row + 1] = rstd;
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((f[r][i][j] - mean) * rstd, gm[j], bt[j]);
+        store8(y + (row0 + r) * C + v * 8, o);
+      }
+    }
+    if (lane == 0) {
+      rowstats[2 * (row0 + r)] = mean;
+      rowstats[2 * (row0 + r) + 1] = rstd;
+    }
   }
 }
 
@@ -344,9 +388,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ rowstats,
                               const float* __restrict__ gamma, const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
                               float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C) {
-  extern __shared__ float sh[];  // [2*C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float sh[];  // [warps][2*C]: one private slot per warp, no atomics
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
@@ -397,21 +439,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
       }
     }
   }
+  float* slot = sh + (threadIdx.x >> 5) * 2 * C;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sh[v * 8 + j], ag[i][j]);
-        atomicAdd(&sh[C + v * 8 + j], ab[i][j]);
+        slot[v * 8 + j] = ag[i][j];
+        slot[C + v * 8 + j] = ab[i][j];
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(&dgamma[i], sh[i]);
-    atomicAdd(&dbeta[i], sh[C + i]);
+  const int nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = 0.f;
+    for (int w = 0; w < nw; ++w) a += sh[w * 2 * C + i];
+    atomicAdd(i < C ? &dgamma[i] : &dbeta[i - C], a);
   }
 }
 
@@ -423,7 +468,7 @@ extern "C" int pt_groupnorm_stats(const void* x, float* stats, int B, int L, int
   if (int r = gn_geom(B, L, C, &g)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   PT_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * G, st));
-  gn_stats_kernel<<<dim3(g.cblocks, g.red_chunks, B), 256, 2 * G * sizeof(float), st>>>((const bf16*)x, stats, L, C, G, g.red_rows);
+  gn_stats_kernel<<<dim3(g.chunks_red, B), g.threads, g.threads * 16 * sizeof(float), st>>>((const bf16*)x, stats, L, C, G, g.rows_red);
   PT_LAUNCH_CHECK();
   const int n = B * G;
   gn_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(stats, n, 1.f / ((float)(C / G) * (float)L), eps);
@@ -436,8 +481,8 @@ extern "C" int pt_groupnorm_apply(const void* x, const float* stats, const float
   PT_REQUIRE(B > 0 && L > 0 && G > 0 && C % G == 0, "groupnorm_apply: B=%d L=%d C=%d G=%d", B, L, C, G);
   GnGeom g;
   if (int r = gn_geom(B, L, C, &g)) return r;
-  gn_apply_kernel<<<dim3(g.chunks, B), 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, L, C, G,
-                                                                                          g.rows_per_cta, act);
+  gn_apply_kernel<<<dim3(g.chunks_apply, B), g.threads, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, L, C, G,
+                                                                                  g.rows_apply, act);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
@@ -449,17 +494,11 @@ extern "C" int pt_groupnorm_bwd(const void* dy, const void* x, const float* stat
   if (int r = gn_geom(B, L, C, &g)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   PT_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * G, st));
-  gn_bwd_reduce_kernel<<<dim3(g.cblocks, g.red_chunks, B), 256, (2 * G + 8 * 256 * 2) * sizeof(float), st>>>(
-      (const bf16*)dy, (const bf16*)x, stats, gamma, beta, dgamma, dbeta, scratch, L, C, G, g.red_rows, act);
+  gn_bwd_reduce_kernel<<<dim3(g.chunks_red, B), g.threads, g.threads * 16 * sizeof(float), st>>>(
+      (const bf16*)dy, (const bf16*)x, stats, gamma, beta, dgamma, dbeta, scratch, L, C, G, g.rows_red, act);
   PT_LAUNCH_CHECK();
-  PT_REQUIRE(6 * C * sizeof(float) <= 160 * 1024, "groupnorm_bwd: C=%d too large", C);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CUDA_OK(cudaFuncSetAttribute(gn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
-  gn_bwd_apply_kernel<<<dim3(g.chunks, B), 256, 6 * C * sizeof(float), st>>>((const bf16*)dy, (const bf16*)x, stats, gamma, beta, scratch,
-                                                                            (bf16*)dx, L, C, G, g.rows_per_cta, act);
+  gn_bwd_apply_kernel<<<dim3(g.chunks_apply, B), g.threads, 0, st>>>((const bf16*)dy, (const bf16*)x, stats, gamma, beta, scratch, (bf16*)dx, L,
+                                                                     C, G, g.rows_apply, act);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
@@ -467,15 +506,16 @@ extern "C" int pt_groupnorm_bwd(const void* dy, const void* x, const float* stat
 extern "C" int pt_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* rowstats, int64_t M, int C, float eps,
                                 void* stream) {
   PT_REQUIRE(M > 0 && C % 8 == 0 && C / 8 <= 32 * LN_MAXV, "layernorm_fwd: M=%lld C=%d", (long long)M, C);
+  PT_REQUIRE(((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "layernorm_fwd: gamma/beta must be 16-byte aligned");
   const int wpb = 8;
   const int nv = (C / 8 + 31) / 32;
-#define LN_FWD(NV_)                                                                                                                  \
-  case NV_:                                                                                                                          \
-    ln_fwd_kernel<NV_><<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, (bf16*)y, \
-                                                                                               rowstats, M, C, eps);                 \
+#define LN_FWD(NV_, R_)                                                                                                                   \
+  case NV_:                                                                                                                               \
+    ln_fwd_kernel<NV_, R_><<<(unsigned)((M + wpb * R_ - 1) / (wpb * R_)), wpb * 32, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, \
+                                                                                                              (bf16*)y, rowstats, M, C, eps); \
     break;
   switch (nv) {
-    LN_FWD(1) LN_FWD(2) LN_FWD(3) LN_FWD(4) LN_FWD(5) LN_FWD(6) LN_FWD(7) LN_FWD(8)
+    LN_FWD(1, 4) LN_FWD(2, 4) LN_FWD(3, 2) LN_FWD(4, 2) LN_FWD(5, 2) LN_FWD(6, 1) LN_FWD(7, 1) LN_FWD(8, 1)
   }
 #undef LN_FWD
   PT_LAUNCH_CHECK();
@@ -490,11 +530,17 @@ extern "C" int pt_layernorm_bwd(const void* dy, const void* x, const float* rows
   const long long cap = 2ll * pt_num_sms();
   if (blocks > cap) blocks = cap;
   const int nv = (C / 8 + 31) / 32;
+  const size_t smem = (size_t)wpb * 2 * C * sizeof(float);
 #define LN_BWD(NV_)                                                                                                            \
-  case NV_:                                                                                                                    \
-    ln_bwd_kernel<NV_><<<(unsigned)blocks, wpb * 32, 2 * C * sizeof(float), (cudaStream_t)stream>>>(                            \
+  case NV_: {                                                                                                                  \
+    static bool attr_set = false;                                                                                              \
+    if (!attr_set) {                                                                                                           \
+      PT_CUDA_OK(cudaFuncSetAttribute(ln_bwd_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * NV_ * 256 * 4)); \
+      attr_set = true;                                                                                                         \
+    }                                                                                                                          \
+    ln_bwd_kernel<NV_><<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(                                             \
         (const bf16*)dy, (const bf16*)x, rowstats, gamma, (const bf16*)dx_add, (bf16*)dx, dgamma, dbeta, M, C);                \
-    break;
+  } break;
   switch (nv) {
     LN_BWD(1) LN_BWD(2) LN_BWD(3) LN_BWD(4) LN_BWD(5) LN_BWD(6) LN_BWD(7) LN_BWD(8)
   }
