@@ -15,7 +15,7 @@
 // FWD makes two sweeps over the streamed side: sweep 1 only takes the row maximum of the logits (exact softmax,
 // no accumulator rescaling), sweep 2 does the work.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-5 and 6-9 two
+// Warp roles (352 threads): warp 0 TMA producer, warp 1 stage-1 MMA issuer, warp 10 stage-2 MMA issuer, warps 2-5 and 6-9 two
 // transform groups that ping-pong over the streamed tiles (group g owns TMEM buffer X[g] and smem tile T[g]),
 // so the tensor core computes the logits of tile j+1 while the CUDA cores exponentiate tile j.
 // Every streamed tile is used twice from the same shared-memory bytes: K-major as the B operand of stage 1 and
@@ -59,7 +59,7 @@ struct ACfg {
   static constexpr int FIXED = NX * R_BYTES + XBUF * NACC * T_BYTES;
   static constexpr int BUDGET = 222 * 1024;                  // of 227 KB: leaves room for alignment slack, barriers, statistics
   static constexpr int NSTAGE_FIT = (BUDGET - FIXED) / STAGE_BYTES;
-  static constexpr int NSTAGE = NSTAGE_FIT >= 4 ? 4 : NSTAGE_FIT;
+  static constexpr int NSTAGE = NSTAGE_FIT >= 8 ? 8 : NSTAGE_FIT;   // deep ring: bytes in flight must cover the TMA round trip
   static constexpr int LOOKAHEAD = XBUF == 2 ? (NSTAGE >= 3 ? 2 : (NSTAGE >= 2 ? 1 : 0)) : 0;   // stage-1 MMAs issued ahead of stage 2
   static constexpr int OFF_S = NX * R_BYTES;
   static constexpr int OFF_T = OFF_S + NSTAGE * STAGE_BYTES;
@@ -121,9 +121,9 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t* v, int c, int ncol, fl
 }
 
 template <int MODE, int DP>
-__global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AParams p) {
+__global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AParams p) {
   using C = ACfg<MODE, DP>;
-  constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE, LA = C::LOOKAHEAD;
+  constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -131,13 +131,13 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
   // barriers
   const uint32_t r_full = bar0;
   auto s_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto s_empty = [&](int s) { return bar0 + 8u * (5 + s); };
-  auto x_full = [&](int g) { return bar0 + 8u * (9 + g); };
-  auto x_empty = [&](int g) { return bar0 + 8u * (11 + g); };
-  auto t_full = [&](int g) { return bar0 + 8u * (13 + g); };
-  auto t_empty = [&](int g) { return bar0 + 8u * (15 + g); };
-  const uint32_t acc_full = bar0 + 8u * 17;
-  const uint32_t tmem_slot = bar0 + 8u * 18;
+  auto s_empty = [&](int s) { return bar0 + 8u * (9 + s); };
+  auto x_full = [&](int g, int slot) { return bar0 + 8u * (17 + g * 2 + slot); };
+  auto x_empty = [&](int g, int slot) { return bar0 + 8u * (21 + g * 2 + slot); };
+  auto t_full = [&](int g) { return bar0 + 8u * (25 + g); };
+  auto t_empty = [&](int g) { return bar0 + 8u * (27 + g); };
+  const uint32_t acc_full = bar0 + 8u * 29;
+  const uint32_t tmem_slot = bar0 + 8u * 30;
   float* sstat = reinterpret_cast<float*>(sgen + C::OFF_STAT);          // [g][buf][2][BN]
   float* sred = sstat + 2 * 2 * 2 * BN;                                 // [2][BM]
 
@@ -152,13 +152,15 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
     for (int i = 0; i < NX; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmR[i])) : "memory");
     for (int i = 0; i < 2; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmS[i])) : "memory");
     mbar_init(r_full, 1);
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(s_full(s), 1);
       mbar_init(s_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(x_full(s), 1);
-      mbar_init(x_empty(s), 128);
+      for (int u = 0; u < 2; ++u) {
+        mbar_init(x_full(s, u), 1);
+        mbar_init(x_empty(s, u), 128);
+      }
       mbar_init(t_full(s), 128);
       mbar_init(t_empty(s), 1);
     }
@@ -172,8 +174,10 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 18);
-  auto xcol = [&](int g, int x) { return (uint32_t)(g * C::XW + x * BN); };
+  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 30);
+  // X buffers: FWD gives each group two 64-column slots (stage 1 runs a whole tile ahead of the group); the backward
+  // modes need X1 | X2 per tile and have TMEM for one 128-column buffer per group only
+  auto xcol = [&](int g, int slot_or_x) { return (uint32_t)(g * C::XW + slot_or_x * BN); };
   auto acccol = [&](int a) { return (uint32_t)(C::X_COLS + a * C::ACC_STRIDE); };
   auto tT = [&](int g, int a) { return sT + (uint32_t)((g * NACC + a) * C::T_BYTES); };
   auto gsel = [&](int j) { return XBUF == 2 ? (j & 1) : 0; };
@@ -205,85 +209,100 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
       for (int j = 0; j < n_tiles1; ++j) load_tile(&p.tmS[0], &p.tmS[0], 2 * j * BN, (2 * j + 1) * BN);
     for (int j = 0; j < n_tiles; ++j) load_tile(&p.tmS[0], &p.tmS[1], j * BN, j * BN);
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
+    // ------------------------------------------------------------------ stage-1 MMA issuer (warp-uniform control flow, one elected lane issues)
+    // Runs ahead of the transform groups as far as the ring and the two X buffers allow; never waits on stage 2.
     const bool leader = elect_one();
     const uint32_t idesc1 = idesc_f16(0, 0, BN, BM);
-    const uint32_t idesc2 = idesc_f16(0, 1, nd, BM);
     // UMMA descriptors are linear in the shared-memory address: precompute the bases, add (bytes >> 4) per use
     const uint64_t dR = umma_desc(sR, 0, 1024);            // resident tiles, K-major
-    const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view (stage 1)
-    const uint64_t dSmn = umma_desc(sS, BN * 128, 1024);   // streamed tiles, MN-major view (stage 2)
-    const uint64_t dT = umma_desc(sT, 0, 1024);            // transformed tiles, K-major
+    const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view
     mbar_wait(r_full, 0);
-    int s1 = 0, ph1 = 0;   // ring position / parity of the next stage-1 tile
-    // stage 1 of one tile into X[g]; `use` = how many times X[g] was filled before
-    auto mma1 = [&](int g, int use, auto sweep1) {
-      constexpr bool SWEEP1 = decltype(sweep1)::value;
-      mbar_wait(s_full(s1), ph1);
-      mbar_wait(x_empty(g), (use & 1) ^ 1);
-      fence_after();
-      if (leader) {
-        const uint64_t bS = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
+    int s1 = 0, ph1 = 0;   // ring position / parity of the next tile
+    if (MODE == MODE_FWD) {
+      // tile t (64 streamed rows) of either sweep goes to group t & 1; that group's k-th tile overall uses slot k & 1.
+      // Sweep 1 (row maxima) reads only K: a ring stage holds two consecutive K tiles; sweep 2 stages hold (K, V).
+      const int per_g0 = (n_tiles + 1) >> 1, per_g1 = n_tiles >> 1;
+      for (int sweep = 0; sweep < 2; ++sweep) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const int g = j & 1;
+          const int k = (sweep ? (g ? per_g1 : per_g0) : 0) + (j >> 1);
+          const int slot = k & 1;
+          const int half = sweep == 0 ? (j & 1) : 0;             // which K tile of the stage
+          if (half == 0) mbar_wait(s_full(s1), ph1);
+          mbar_wait(x_empty(g, slot), ((k >> 1) & 1) ^ 1);
+          fence_after();
+          if (leader) {
+            const uint64_t b0 = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4) + half * (C::S_BYTES >> 4));
+            const uint32_t dcol = tmem + xcol(g, slot);
 #pragma unroll
-        for (int x = 0; x < (SWEEP1 ? 2 : NX); ++x) {
-          const uint64_t a0 = dR + (uint64_t)((SWEEP1 ? 0 : x) * (C::R_BYTES >> 4));
-          const uint64_t b0 = bS + (uint64_t)(x * (C::S_BYTES >> 4));
-          const uint32_t dcol = tmem + xcol(g, x);
-#pragma unroll
-          for (int k = 0; k < DP / 16; ++k)
-            if (k < ks1)
-              umma_f16(dcol, a0 + (uint64_t)((k >> 2) * (BM * 128 >> 4) + (k & 3) * 2), b0 + (uint64_t)((k >> 2) * (BN * 128 >> 4) + (k & 3) * 2),
-                       idesc1, k > 0 ? 1u : 0u);
+            for (int kk = 0; kk < DP / 16; ++kk)
+              if (kk < ks1)
+                umma_f16(dcol, dR + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2), b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2),
+                         idesc1, kk > 0 ? 1u : 0u);
+            umma_commit(x_full(g, slot));
+            if (sweep == 0 && (half == 1 || j == n_tiles - 1)) umma_commit(s_empty(s1));
+          }
+          __syncwarp();
+          if (sweep == 1 || half == 1 || j == n_tiles - 1)
+            if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
         }
-        umma_commit(x_full(g));
-        if (SWEEP1) umma_commit(s_empty(s1));
       }
-      __syncwarp();
-      if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
-    };
-    int s2 = 0;            // ring position of the next stage-2 tile
-    auto mma2 = [&](int g, int use, bool first) {
-      mbar_wait(t_full(g), use & 1);
+    } else {
+      for (int j = 0; j < n_tiles; ++j) {
+        const int g = gsel(j);
+        const int use = XBUF == 2 ? (j >> 1) : j;
+        mbar_wait(s_full(s1), ph1);
+        mbar_wait(x_empty(g, 0), (use & 1) ^ 1);
+        fence_after();
+        if (leader) {
+          const uint64_t bS = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
+#pragma unroll
+          for (int x = 0; x < NX; ++x) {
+            const uint64_t a0 = dR + (uint64_t)(x * (C::R_BYTES >> 4));
+            const uint64_t b0 = bS + (uint64_t)(x * (C::S_BYTES >> 4));
+            const uint32_t dcol = tmem + xcol(g, x);
+#pragma unroll
+            for (int kk = 0; kk < DP / 16; ++kk)
+              if (kk < ks1)
+                umma_f16(dcol, a0 + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2), b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2),
+                         idesc1, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(x_full(g, 0));
+        }
+        __syncwarp();
+        if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ stage-2 MMA issuer: ACC += T[g] * S (MN-major view), frees the ring slot
+    const bool leader = elect_one();
+    const uint32_t idesc2 = idesc_f16(0, 1, nd, BM);
+    const uint64_t dSmn = umma_desc(sS, BN * 128, 1024);   // streamed tiles, MN-major view
+    const uint64_t dT = umma_desc(sT, 0, 1024);            // transformed tiles, K-major
+    int s2 = MODE == MODE_FWD ? n_tiles1 % NSTAGE : 0;     // the main sweep continues on the ring where sweep 1 stopped
+    for (int j = 0; j < n_tiles; ++j) {
+      const int g = gsel(j);
+      mbar_wait(t_full(g), (XBUF == 2 ? (j >> 1) : j) & 1);
       fence_after();
       if (leader) {
         const uint64_t bS = dSmn + (uint64_t)(s2 * (C::STAGE_BYTES >> 4));
 #pragma unroll
         for (int a = 0; a < NACC; ++a) {
-          // B operand of stage 2, MN-major view of a streamed tile: FWD -> V (S2); DQ -> K (S1); DKV: dV <- dO (S2), dK <- Q (S1)
-          constexpr int dummy = 0;
+          // B operand: FWD -> V (S2); DQ -> K (S1); DKV: dV <- dO (S2), dK <- Q (S1)
           const int cs = MODE == MODE_FWD ? 1 : (MODE == MODE_DQ ? 0 : (a == 0 ? 1 : 0));
           const uint64_t a0 = dT + (uint64_t)((g * NACC + a) * (C::T_BYTES >> 4));
           const uint64_t b0 = bS + (uint64_t)(cs * (C::S_BYTES >> 4));
           const uint32_t dcol = tmem + acccol(a);
-          (void)dummy;
 #pragma unroll
-          for (int k = 0; k < BN / 16; ++k) umma_f16(dcol, a0 + (uint64_t)(k * 2), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (first && k == 0) ? 0u : 1u);
+          for (int k = 0; k < BN / 16; ++k) umma_f16(dcol, a0 + (uint64_t)(k * 2), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (j == 0 && k == 0) ? 0u : 1u);
         }
         umma_commit(t_empty(g));
         umma_commit(s_empty(s2));
+        if (j == n_tiles - 1) umma_commit(acc_full);
       }
       __syncwarp();
       if (++s2 == NSTAGE) s2 = 0;
-    };
-    // X[g] fill counts: sweep-1 step j is fill (j >> 1) of X[j & 1]; main tile j is fill base[g] + (j >> 1)  (XBUF == 1: fill j of X[0])
-    int base0 = 0, base1 = 0;
-    if (MODE == MODE_FWD) {
-      for (int j = 0; j < n_tiles1; ++j) mma1(j & 1, j >> 1, std::true_type{});
-      base0 = (n_tiles1 + 1) >> 1;
-      base1 = n_tiles1 >> 1;
-      s2 = s1;   // the main sweep continues on the ring where sweep 1 stopped
     }
-    auto xuse = [&](int j) { return XBUF == 2 ? ((j & 1) ? base1 : base0) + (j >> 1) : j; };
-    auto tuse = [&](int j) { return XBUF == 2 ? (j >> 1) : j; };
-#pragma unroll
-    for (int a = 0; a < LA; ++a)
-      if (a < n_tiles) mma1(gsel(a), xuse(a), std::false_type{});
-    for (int j = 0; j < n_tiles; ++j) {
-      if (j + LA < n_tiles) mma1(gsel(j + LA), xuse(j + LA), std::false_type{});
-      mma2(gsel(j), tuse(j), j == 0);
-    }
-    if (leader) umma_commit(acc_full);
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ transform groups (warps 2-5, 6-9)
     const int g = (warp - 2) >> 2;
@@ -300,31 +319,29 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
     uint32_t v1[32], v2[32];
 
     if (MODE == MODE_FWD) {
-      // ---- sweep 1: exact row maximum of the raw logits, 128 columns per step
+      // ---- sweep 1: exact row maximum of the raw logits.  This group's k-th tile (of both sweeps) sits in X slot k & 1.
       float m = -INFINITY;
-      for (int j = g; j < n_tiles1; j += 2) {
-        mbar_wait(x_full(g), kx & 1);
+      int k = 0;
+      for (int j = g; j < n_tiles; j += 2, ++k) {
+        const int slot = k & 1;
+        mbar_wait(x_full(g, slot), (k >> 1) & 1);
         fence_after();
-        const int ncol = min(2 * BN, p.Ls - j * 2 * BN);
+        tmem_ld32(tl + xcol(g, slot), v1);
+        tmem_ld32(tl + xcol(g, slot) + 32, v2);
+        tmem_wait_ld();
+        fence_before();
+        mbar_arrive(x_empty(g, slot));
+        const int ncol = min(BN, p.Ls - j * BN);
+        if (ncol == BN) {
 #pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
-          tmem_ld32(tl + xcol(g, 0) + (c + 1) * 32, v2);
-          tmem_wait_ld();
-          if (ncol >= (c + 2) * 32) {
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (c * 32 + i < ncol) m = fmaxf(m, __uint_as_float(v1[i]));
-              if ((c + 1) * 32 + i < ncol) m = fmaxf(m, __uint_as_float(v2[i]));
-            }
+          for (int i = 0; i < 32; ++i) {
+            if (i < ncol) m = fmaxf(m, __uint_as_float(v1[i]));
+            if (32 + i < ncol) m = fmaxf(m, __uint_as_float(v2[i]));
           }
         }
-        fence_before();
-        mbar_arrive(x_empty(g));
-        ++kx;
       }
       sred[g * BM + row] = m;
       asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -333,14 +350,15 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
       const float mc = m * c2;
       // ---- sweep 2: P = exp(s - m) -> T[g] (bf16, K-major, SWIZZLE_128B) ; partial row sums
       float rsum = 0.f;
-      for (int j = g; j < n_tiles; j += 2) {
-        mbar_wait(x_full(g), kx & 1);
+      for (int j = g; j < n_tiles; j += 2, ++k) {
+        const int slot = k & 1;
+        mbar_wait(x_full(g, slot), (k >> 1) & 1);
         fence_after();
-        tmem_ld32(tl + xcol(g, 0), v1);
-        tmem_ld32(tl + xcol(g, 0) + 32, v2);
+        tmem_ld32(tl + xcol(g, slot), v1);
+        tmem_ld32(tl + xcol(g, slot) + 32, v2);
         tmem_wait_ld();
         fence_before();
-        mbar_arrive(x_empty(g));
+        mbar_arrive(x_empty(g, slot));
         mbar_wait(t_empty(g), (kt & 1) ^ 1);
         const int ncol = min(BN, p.Ls - j * BN);
         const uint32_t tt = tT(g, 0) + trow;
@@ -353,7 +371,6 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
         }
         fence_async_smem();
         mbar_arrive(t_full(g));
-        ++kx;
         ++kt;
       }
       sred[g * BM + row] = rsum;
@@ -410,7 +427,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
             asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
             cst = reinterpret_cast<const float4*>(st);
           }
-          mbar_wait(x_full(g), kx & 1);
+          mbar_wait(x_full(g, 0), kx & 1);
           fence_after();
           const uint32_t tt0 = tT(g, 0) + trow;
           const uint32_t tt1 = tT(g, NACC - 1) + trow;
@@ -421,7 +438,7 @@ __global__ void __launch_bounds__(320, 1) attn_kernel(const __grid_constant__ AP
             tmem_wait_ld();
             if (c == BN / 32 - 1) {
               fence_before();
-              mbar_arrive(x_empty(g));
+              mbar_arrive(x_empty(g, 0));
             }
             if (c == 0) mbar_wait(t_empty(g), (kt & 1) ^ 1);
             uint32_t pp[16], dd[16];
@@ -543,7 +560,7 @@ int launch_attn(const AParams& ap, dim3 grid, cudaStream_t st) {
     PT_CUDA_OK(cudaFuncSetAttribute(attn_kernel<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<MODE, DP>::SMEM_BYTES));
     attr_set = true;
   }
-  attn_kernel<MODE, DP><<<grid, 320, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
+  attn_kernel<MODE, DP><<<grid, 352, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
