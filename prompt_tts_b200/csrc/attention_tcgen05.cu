@@ -37,7 +37,7 @@ constexpr int BN = 64;   // streamed rows per tile (= one SWIZZLE_128B row of bf
 struct alignas(64) AParams {
   CUtensorMap tmR[2];
   CUtensorMap tmS[2];
-  int Lr, Ls, H, D;
+  int Lr, Ls, H, D, B;
   float scale;
   bf16* out0;
   bf16* out1;
@@ -57,14 +57,14 @@ struct ACfg {
   static constexpr int STAGE_BYTES = 2 * S_BYTES;
   static constexpr int T_BYTES = BM * BN * 2;
   static constexpr int FIXED = NX * R_BYTES + XBUF * NACC * T_BYTES;
-  static constexpr int BUDGET = 222 * 1024;                  // of 227 KB: leaves room for alignment slack, barriers, statistics
+  static constexpr int BUDGET = 221 * 1024;                  // of 227 KB: leaves room for alignment slack, barriers, statistics
   static constexpr int NSTAGE_FIT = (BUDGET - FIXED) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_FIT >= 8 ? 8 : NSTAGE_FIT;   // deep ring: bytes in flight must cover the TMA round trip
   static constexpr int LOOKAHEAD = XBUF == 2 ? (NSTAGE >= 3 ? 2 : (NSTAGE >= 2 ? 1 : 0)) : 0;   // stage-1 MMAs issued ahead of stage 2
   static constexpr int OFF_S = NX * R_BYTES;
   static constexpr int OFF_T = OFF_S + NSTAGE * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_T + XBUF * NACC * T_BYTES;
-  static constexpr int OFF_STAT = OFF_BAR + 256;
+  static constexpr int OFF_STAT = OFF_BAR + 512;
   static constexpr int STAT_BYTES = 2 * 2 * 2 * BN * 4 + 2 * BM * 4;   // DKV column stats [g][buf][2][BN] + row reduce [2][BM]
   static constexpr int SMEM_BYTES = 1024 + OFF_STAT + STAT_BYTES;
   static constexpr int XW = 128;                             // TMEM columns per X buffer (two 64-column products)
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t sR = sbase, sS = sbase + C::OFF_S, sT = sbase + C::OFF_T, bar0 = sbase + C::OFF_BAR;
-  // barriers
+  // barriers (every one of them is reused across work items with a running phase)
   const uint32_t r_full = bar0;
   auto s_full = [&](int s) { return bar0 + 8u * (1 + s); };
   auto s_empty = [&](int s) { return bar0 + 8u * (9 + s); };
@@ -137,21 +137,32 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   auto t_full = [&](int g) { return bar0 + 8u * (25 + g); };
   auto t_empty = [&](int g) { return bar0 + 8u * (27 + g); };
   const uint32_t acc_full = bar0 + 8u * 29;
-  const uint32_t tmem_slot = bar0 + 8u * 30;
+  const uint32_t acc_empty = bar0 + 8u * 30;
+  const uint32_t r_empty = bar0 + 8u * 31;
+  const uint32_t tmem_slot = bar0 + 8u * 32;
   float* sstat = reinterpret_cast<float*>(sgen + C::OFF_STAT);          // [g][buf][2][BN]
   float* sred = sstat + 2 * 2 * 2 * BN;                                 // [2][BM]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.Ls + BN - 1) / BN;
-  const int n_tiles1 = (p.Ls + 2 * BN - 1) / (2 * BN);   // FWD sweep 1 walks 128 streamed rows per step
+  const int n_tiles1 = (n_tiles + 1) >> 1;    // FWD sweep 1: ring stages (two K tiles each)
   const int ks1 = (p.D + 15) >> 4;            // stage-1 k-steps (head dim, zero padded to a multiple of 16)
   const int nd = ks1 << 4;                    // stage-2 N
+  // persistent CTA: work item w -> (resident row block, head, batch), row block fastest (neighbouring CTAs share K/V in L2)
+  const int n_rblk = (p.Lr + BM - 1) / BM;
+  const int total_work = n_rblk * p.H * p.B;
+  auto decode = [&](int w, int& r0, int& h, int& b) {
+    r0 = (w % n_rblk) * BM;
+    w /= n_rblk;
+    h = w % p.H;
+    b = w / p.H;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < NX; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmR[i])) : "memory");
     for (int i = 0; i < 2; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmS[i])) : "memory");
     mbar_init(r_full, 1);
+    mbar_init(r_empty, 1);
     for (int s = 0; s < 8; ++s) {
       mbar_init(s_full(s), 1);
       mbar_init(s_empty(s), 1);
@@ -165,6 +176,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       mbar_init(t_empty(s), 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -174,103 +186,120 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 30);
+  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 32);
   // X buffers: FWD gives each group two 64-column slots (stage 1 runs a whole tile ahead of the group); the backward
   // modes need X1 | X2 per tile and have TMEM for one 128-column buffer per group only
   auto xcol = [&](int g, int slot_or_x) { return (uint32_t)(g * C::XW + slot_or_x * BN); };
   auto acccol = [&](int a) { return (uint32_t)(C::X_COLS + a * C::ACC_STRIDE); };
   auto tT = [&](int g, int a) { return sT + (uint32_t)((g * NACC + a) * C::T_BYTES); };
   auto gsel = [&](int j) { return XBUF == 2 ? (j & 1) : 0; };
+  // tiles of one sweep handled by group g
+  const int per_g0 = XBUF == 2 ? (n_tiles + 1) >> 1 : n_tiles, per_g1 = XBUF == 2 ? n_tiles >> 1 : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform control flow, one elected lane issues)
     const bool leader = elect_one();
-    if (leader) {
-      mbar_expect_tx(r_full, NX * C::R_BYTES);
-#pragma unroll
-      for (int x = 0; x < NX; ++x)
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) tma_load_4d(sR + x * C::R_BYTES + kb * (BM * 128), &p.tmR[x], r_full, kb * 64, r0, h, b);
-    }
     int s = 0, ph = 1;   // ring position / parity to wait for on s_empty
-    auto load_tile = [&](const CUtensorMap* t0, const CUtensorMap* t1, int row0, int row1) {
-      mbar_wait(s_empty(s), ph);
+    int wi = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
+      int r0, h, b;
+      decode(w, r0, h, b);
+      mbar_wait(r_empty, (wi & 1) ^ 1);   // stage 1 of the previous work item has finished reading the resident tiles
       if (leader) {
-        mbar_expect_tx(s_full(s), 2 * C::S_BYTES);
-        const uint32_t dst = sS + s * C::STAGE_BYTES;
+        mbar_expect_tx(r_full, NX * C::R_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + kb * (BN * 128), t0, s_full(s), kb * 64, row0, h, b);
+        for (int x = 0; x < NX; ++x)
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + C::S_BYTES + kb * (BN * 128), t1, s_full(s), kb * 64, row1, h, b);
+          for (int kb = 0; kb < KB; ++kb) tma_load_4d(sR + x * C::R_BYTES + kb * (BM * 128), &p.tmR[x], r_full, kb * 64, r0, h, b);
       }
-      if (++s == NSTAGE) s = 0, ph ^= 1;
-    };
-    if (MODE == MODE_FWD)   // sweep 1: both slots of a stage hold consecutive 64-row tiles of K
-      for (int j = 0; j < n_tiles1; ++j) load_tile(&p.tmS[0], &p.tmS[0], 2 * j * BN, (2 * j + 1) * BN);
-    for (int j = 0; j < n_tiles; ++j) load_tile(&p.tmS[0], &p.tmS[1], j * BN, j * BN);
+      auto load_tile = [&](const CUtensorMap* t0, const CUtensorMap* t1, int row0, int row1) {
+        mbar_wait(s_empty(s), ph);
+        if (leader) {
+          mbar_expect_tx(s_full(s), 2 * C::S_BYTES);
+          const uint32_t dst = sS + s * C::STAGE_BYTES;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + kb * (BN * 128), t0, s_full(s), kb * 64, row0, h, b);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) tma_load_4d(dst + C::S_BYTES + kb * (BN * 128), t1, s_full(s), kb * 64, row1, h, b);
+        }
+        if (++s == NSTAGE) s = 0, ph ^= 1;
+      };
+      if (MODE == MODE_FWD)   // sweep 1: both slots of a stage hold consecutive 64-row tiles of K
+        for (int j = 0; j < n_tiles1; ++j) load_tile(&p.tmS[0], &p.tmS[0], 2 * j * BN, (2 * j + 1) * BN);
+      for (int j = 0; j < n_tiles; ++j) load_tile(&p.tmS[0], &p.tmS[1], j * BN, j * BN);
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ stage-1 MMA issuer (warp-uniform control flow, one elected lane issues)
-    // Runs ahead of the transform groups as far as the ring and the two X buffers allow; never waits on stage 2.
+    // Runs ahead of the transform groups as far as the ring and the X buffers allow; never waits on stage 2.
     const bool leader = elect_one();
     const uint32_t idesc1 = idesc_f16(0, 0, BN, BM);
     // UMMA descriptors are linear in the shared-memory address: precompute the bases, add (bytes >> 4) per use
     const uint64_t dR = umma_desc(sR, 0, 1024);            // resident tiles, K-major
     const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view
-    mbar_wait(r_full, 0);
     int s1 = 0, ph1 = 0;   // ring position / parity of the next tile
-    if (MODE == MODE_FWD) {
-      // tile t (64 streamed rows) of either sweep goes to group t & 1; that group's k-th tile overall uses slot k & 1.
-      // Sweep 1 (row maxima) reads only K: a ring stage holds two consecutive K tiles; sweep 2 stages hold (K, V).
-      const int per_g0 = (n_tiles + 1) >> 1, per_g1 = n_tiles >> 1;
-      for (int sweep = 0; sweep < 2; ++sweep) {
+    int kb0 = 0, kb1 = 0;  // X fills done by earlier work items, per group
+    int wi = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
+      mbar_wait(r_full, wi & 1);
+      if (MODE == MODE_FWD) {
+        // tile t (64 streamed rows) of either sweep goes to group t & 1; that group's k-th tile overall uses slot k & 1.
+        // Sweep 1 (row maxima) reads only K: a ring stage holds two consecutive K tiles; sweep 2 stages hold (K, V).
+        for (int sweep = 0; sweep < 2; ++sweep) {
+          for (int j = 0; j < n_tiles; ++j) {
+            const int g = j & 1;
+            const int k = (g ? kb1 : kb0) + (sweep ? (g ? per_g1 : per_g0) : 0) + (j >> 1);
+            const int slot = k & 1;
+            const int half = sweep == 0 ? (j & 1) : 0;             // which K tile of the stage
+            if (half == 0) mbar_wait(s_full(s1), ph1);
+            mbar_wait(x_empty(g, slot), ((k >> 1) & 1) ^ 1);
+            fence_after();
+            if (leader) {
+              const uint64_t b0 = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4) + half * (C::S_BYTES >> 4));
+              const uint32_t dcol = tmem + xcol(g, slot);
+#pragma unroll
+              for (int kk = 0; kk < DP / 16; ++kk)
+                if (kk < ks1)
+                  umma_f16(dcol, dR + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2),
+                           b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2), idesc1, kk > 0 ? 1u : 0u);
+              umma_commit(x_full(g, slot));
+              if (sweep == 0 && (half == 1 || j == n_tiles - 1)) umma_commit(s_empty(s1));
+              if (sweep == 1 && j == n_tiles - 1) umma_commit(r_empty);
+            }
+            __syncwarp();
+            if (sweep == 1 || half == 1 || j == n_tiles - 1)
+              if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
+          }
+        }
+        kb0 += 2 * per_g0;
+        kb1 += 2 * per_g1;
+      } else {
         for (int j = 0; j < n_tiles; ++j) {
-          const int g = j & 1;
-          const int k = (sweep ? (g ? per_g1 : per_g0) : 0) + (j >> 1);
-          const int slot = k & 1;
-          const int half = sweep == 0 ? (j & 1) : 0;             // which K tile of the stage
-          if (half == 0) mbar_wait(s_full(s1), ph1);
-          mbar_wait(x_empty(g, slot), ((k >> 1) & 1) ^ 1);
+          const int g = gsel(j);
+          const int use = (g ? kb1 : kb0) + (XBUF == 2 ? (j >> 1) : j);
+          mbar_wait(s_full(s1), ph1);
+          mbar_wait(x_empty(g, 0), (use & 1) ^ 1);
           fence_after();
           if (leader) {
-            const uint64_t b0 = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4) + half * (C::S_BYTES >> 4));
-            const uint32_t dcol = tmem + xcol(g, slot);
+            const uint64_t bS = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
 #pragma unroll
-            for (int kk = 0; kk < DP / 16; ++kk)
-              if (kk < ks1)
-                umma_f16(dcol, dR + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2), b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2),
-                         idesc1, kk > 0 ? 1u : 0u);
-            umma_commit(x_full(g, slot));
-            if (sweep == 0 && (half == 1 || j == n_tiles - 1)) umma_commit(s_empty(s1));
+            for (int x = 0; x < NX; ++x) {
+              const uint64_t a0 = dR + (uint64_t)(x * (C::R_BYTES >> 4));
+              const uint64_t b0 = bS + (uint64_t)(x * (C::S_BYTES >> 4));
+              const uint32_t dcol = tmem + xcol(g, x);
+#pragma unroll
+              for (int kk = 0; kk < DP / 16; ++kk)
+                if (kk < ks1)
+                  umma_f16(dcol, a0 + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2),
+                           b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2), idesc1, kk > 0 ? 1u : 0u);
+            }
+            umma_commit(x_full(g, 0));
+            if (j == n_tiles - 1) umma_commit(r_empty);
           }
           __syncwarp();
-          if (sweep == 1 || half == 1 || j == n_tiles - 1)
-            if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
+          if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
         }
-      }
-    } else {
-      for (int j = 0; j < n_tiles; ++j) {
-        const int g = gsel(j);
-        const int use = XBUF == 2 ? (j >> 1) : j;
-        mbar_wait(s_full(s1), ph1);
-        mbar_wait(x_empty(g, 0), (use & 1) ^ 1);
-        fence_after();
-        if (leader) {
-          const uint64_t bS = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
-#pragma unroll
-          for (int x = 0; x < NX; ++x) {
-            const uint64_t a0 = dR + (uint64_t)(x * (C::R_BYTES >> 4));
-            const uint64_t b0 = bS + (uint64_t)(x * (C::S_BYTES >> 4));
-            const uint32_t dcol = tmem + xcol(g, x);
-#pragma unroll
-            for (int kk = 0; kk < DP / 16; ++kk)
-              if (kk < ks1)
-                umma_f16(dcol, a0 + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2), b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2),
-                         idesc1, kk > 0 ? 1u : 0u);
-          }
-          umma_commit(x_full(g, 0));
-        }
-        __syncwarp();
-        if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
+        kb0 += per_g0;
+        kb1 += per_g1;
       }
     }
   } else if (warp == 10) {
@@ -279,29 +308,40 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     const uint32_t idesc2 = idesc_f16(0, 1, nd, BM);
     const uint64_t dSmn = umma_desc(sS, BN * 128, 1024);   // streamed tiles, MN-major view
     const uint64_t dT = umma_desc(sT, 0, 1024);            // transformed tiles, K-major
-    int s2 = MODE == MODE_FWD ? n_tiles1 % NSTAGE : 0;     // the main sweep continues on the ring where sweep 1 stopped
-    for (int j = 0; j < n_tiles; ++j) {
-      const int g = gsel(j);
-      mbar_wait(t_full(g), (XBUF == 2 ? (j >> 1) : j) & 1);
+    int s2 = 0;
+    int tu0 = 0, tu1 = 0;   // T fills done by earlier work items, per group
+    int wi = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
+      if (MODE == MODE_FWD) s2 = (s2 + n_tiles1) % NSTAGE;   // sweep 1 used these ring stages (released by the stage-1 issuer)
+      mbar_wait(acc_empty, (wi & 1) ^ 1);                    // the epilogue of the previous work item has drained the accumulators
       fence_after();
-      if (leader) {
-        const uint64_t bS = dSmn + (uint64_t)(s2 * (C::STAGE_BYTES >> 4));
+      for (int j = 0; j < n_tiles; ++j) {
+        const int g = gsel(j);
+        const int use = (g ? tu1 : tu0) + (XBUF == 2 ? (j >> 1) : j);
+        mbar_wait(t_full(g), use & 1);
+        fence_after();
+        if (leader) {
+          const uint64_t bS = dSmn + (uint64_t)(s2 * (C::STAGE_BYTES >> 4));
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) {
-          // B operand: FWD -> V (S2); DQ -> K (S1); DKV: dV <- dO (S2), dK <- Q (S1)
-          const int cs = MODE == MODE_FWD ? 1 : (MODE == MODE_DQ ? 0 : (a == 0 ? 1 : 0));
-          const uint64_t a0 = dT + (uint64_t)((g * NACC + a) * (C::T_BYTES >> 4));
-          const uint64_t b0 = bS + (uint64_t)(cs * (C::S_BYTES >> 4));
-          const uint32_t dcol = tmem + acccol(a);
+          for (int a = 0; a < NACC; ++a) {
+            // B operand: FWD -> V (S2); DQ -> K (S1); DKV: dV <- dO (S2), dK <- Q (S1)
+            const int cs = MODE == MODE_FWD ? 1 : (MODE == MODE_DQ ? 0 : (a == 0 ? 1 : 0));
+            const uint64_t a0 = dT + (uint64_t)((g * NACC + a) * (C::T_BYTES >> 4));
+            const uint64_t b0 = bS + (uint64_t)(cs * (C::S_BYTES >> 4));
+            const uint32_t dcol = tmem + acccol(a);
 #pragma unroll
-          for (int k = 0; k < BN / 16; ++k) umma_f16(dcol, a0 + (uint64_t)(k * 2), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (j == 0 && k == 0) ? 0u : 1u);
+            for (int k = 0; k < BN / 16; ++k)
+              umma_f16(dcol, a0 + (uint64_t)(k * 2), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (j == 0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit(t_empty(g));
+          umma_commit(s_empty(s2));
+          if (j == n_tiles - 1) umma_commit(acc_full);
         }
-        umma_commit(t_empty(g));
-        umma_commit(s_empty(s2));
-        if (j == n_tiles - 1) umma_commit(acc_full);
+        __syncwarp();
+        if (++s2 == NSTAGE) s2 = 0;
       }
-      __syncwarp();
-      if (++s2 == NSTAGE) s2 = 0;
+      tu0 += per_g0;
+      tu1 += per_g1;
     }
   } else {
     // ------------------------------------------------------------------ transform groups (warps 2-5, 6-9)
@@ -315,191 +355,196 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     const float c2 = p.scale * 1.4426950408889634f;
     const uint32_t trow = (uint32_t)(row * 128);
     const int rsw = row & 7;
-    int kx = 0, kt = 0;
+    int kx = 0, kt = 0;   // running X / T use counts of this group (across work items)
     uint32_t v1[32], v2[32];
-
-    if (MODE == MODE_FWD) {
-      // ---- sweep 1: exact row maximum of the raw logits.  This group's k-th tile (of both sweeps) sits in X slot k & 1.
-      float m = -INFINITY;
-      int k = 0;
-      for (int j = g; j < n_tiles; j += 2, ++k) {
-        const int slot = k & 1;
-        mbar_wait(x_full(g, slot), (k >> 1) & 1);
-        fence_after();
-        tmem_ld32(tl + xcol(g, slot), v1);
-        tmem_ld32(tl + xcol(g, slot) + 32, v2);
-        tmem_wait_ld();
-        fence_before();
-        mbar_arrive(x_empty(g, slot));
-        const int ncol = min(BN, p.Ls - j * BN);
-        if (ncol == BN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < ncol) m = fmaxf(m, __uint_as_float(v1[i]));
-            if (32 + i < ncol) m = fmaxf(m, __uint_as_float(v2[i]));
-          }
-        }
-      }
-      sred[g * BM + row] = m;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      m = fmaxf(sred[row], sred[BM + row]);
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      const float mc = m * c2;
-      // ---- sweep 2: P = exp(s - m) -> T[g] (bf16, K-major, SWIZZLE_128B) ; partial row sums
-      float rsum = 0.f;
-      for (int j = g; j < n_tiles; j += 2, ++k) {
-        const int slot = k & 1;
-        mbar_wait(x_full(g, slot), (k >> 1) & 1);
-        fence_after();
-        tmem_ld32(tl + xcol(g, slot), v1);
-        tmem_ld32(tl + xcol(g, slot) + 32, v2);
-        tmem_wait_ld();
-        fence_before();
-        mbar_arrive(x_empty(g, slot));
-        mbar_wait(t_empty(g), (kt & 1) ^ 1);
-        const int ncol = min(BN, p.Ls - j * BN);
-        const uint32_t tt = tT(g, 0) + trow;
-        if (ncol == BN) {
-          fwd_chunk<false>(v1, 0, ncol, c2, mc, rsum, tt, rsw);
-          fwd_chunk<false>(v2, 1, ncol, c2, mc, rsum, tt, rsw);
-        } else {
-          fwd_chunk<true>(v1, 0, ncol, c2, mc, rsum, tt, rsw);
-          fwd_chunk<true>(v2, 1, ncol, c2, mc, rsum, tt, rsw);
-        }
-        fence_async_smem();
-        mbar_arrive(t_full(g));
-        ++kt;
-      }
-      sred[g * BM + row] = rsum;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      rsum = sred[row] + sred[BM + row];
-      // ---- epilogue: O = ACC / rowsum ; lse = m * scale + ln(rowsum)
-      mbar_wait(acc_full, 0);
-      fence_after();
-      const float inv = 1.f / rsum;
+    int wi = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
+      int r0, h, b;
+      decode(w, r0, h, b);
       const int r = r0 + row;
-      bf16* orow = p.out0 + (long long)b * p.o_bs + (long long)r * p.o_rs + (long long)h * p.D;
-      for (int cc = g; cc * 16 < p.D; cc += 2) {
-        tmem_ld16(tl + acccol(0) + cc * 16, v1);
-        tmem_wait_ld();
-        if (r < p.Lr) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-            if (cc * 16 + u * 8 < p.D) {
-              uint4 w;
-              w.x = pack2(__uint_as_float(v1[u * 8]) * inv, __uint_as_float(v1[u * 8 + 1]) * inv);
-              w.y = pack2(__uint_as_float(v1[u * 8 + 2]) * inv, __uint_as_float(v1[u * 8 + 3]) * inv);
-              w.z = pack2(__uint_as_float(v1[u * 8 + 4]) * inv, __uint_as_float(v1[u * 8 + 5]) * inv);
-              w.w = pack2(__uint_as_float(v1[u * 8 + 6]) * inv, __uint_as_float(v1[u * 8 + 7]) * inv);
-              *reinterpret_cast<uint4*>(orow + cc * 16 + u * 8) = w;
-            }
-        }
-      }
-      if (g == 0 && r < p.Lr) p.lse[((long long)b * p.H + h) * p.Lr + r] = m * p.scale + __logf(rsum);
-    } else {
-      // ---- backward modes
-      float lse2 = INFINITY, dl = 0.f;   // DQ: this thread's row statistics
-      if (MODE == MODE_DQ && r0 + row < p.Lr) {
-        const long long si = ((long long)b * p.H + h) * p.Lr + r0 + row;
-        lse2 = p.lse[si] * 1.4426950408889634f;
-        dl = p.delta[si] * p.scale;
-      }
-      if (active)
-        for (int j = g; j < n_tiles; j += jstep) {
-          const float4* cst = nullptr;
-          if (MODE == MODE_DKV) {
-            // column statistics of this tile (columns = query rows): lse * log2(e) (+inf masks the column), delta * scale
-            float* st = sstat + ((g * 2 + (kx & 1)) * 2) * BN;
-            if (tg < BN) {
-              const int qi = j * BN + tg;
-              float a = INFINITY, d = 0.f;
-              if (qi < p.Ls) {
-                const long long si = ((long long)b * p.H + h) * p.Ls + qi;
-                a = p.lse[si] * 1.4426950408889634f;
-                d = p.delta[si] * p.scale;
-              }
-              st[tg] = a;
-              st[BN + tg] = d;
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
-            cst = reinterpret_cast<const float4*>(st);
-          }
-          mbar_wait(x_full(g, 0), kx & 1);
+
+      if (MODE == MODE_FWD) {
+        // ---- sweep 1: exact row maximum of the raw logits.  This group's k-th tile (of both sweeps, all work items) sits in X slot k & 1.
+        float m = -INFINITY;
+        for (int j = g; j < n_tiles; j += 2, ++kx) {
+          const int slot = kx & 1;
+          mbar_wait(x_full(g, slot), (kx >> 1) & 1);
           fence_after();
-          const uint32_t tt0 = tT(g, 0) + trow;
-          const uint32_t tt1 = tT(g, NACC - 1) + trow;
+          tmem_ld32(tl + xcol(g, slot), v1);
+          tmem_ld32(tl + xcol(g, slot) + 32, v2);
+          tmem_wait_ld();
+          fence_before();
+          mbar_arrive(x_empty(g, slot));
+          const int ncol = min(BN, p.Ls - j * BN);
+          if (ncol == BN) {
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
-            tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
-            tmem_ld32(tl + xcol(g, 1) + c * 32, v2);
-            tmem_wait_ld();
-            if (c == BN / 32 - 1) {
-              fence_before();
-              mbar_arrive(x_empty(g, 0));
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < ncol) m = fmaxf(m, __uint_as_float(v1[i]));
+              if (32 + i < ncol) m = fmaxf(m, __uint_as_float(v2[i]));
             }
-            if (c == 0) mbar_wait(t_empty(g), (kt & 1) ^ 1);
-            uint32_t pp[16], dd[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float l4[4] = {lse2, lse2, lse2, lse2}, d4[4] = {dl, dl, dl, dl};
-              if (MODE == MODE_DKV) {
-                const float4 a = cst[(c * 32 + i) >> 2], d = cst[(BN + c * 32 + i) >> 2];
-                l4[0] = a.x, l4[1] = a.y, l4[2] = a.z, l4[3] = a.w;
-                d4[0] = d.x, d4[1] = d.y, d4[2] = d.z, d4[3] = d.w;
-              }
-              float pe[4], de[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float e = ex2f(fmaf(__uint_as_float(v1[i + u]), c2, -l4[u]));
-                pe[u] = e;
-                de[u] = e * fmaf(__uint_as_float(v2[i + u]), p.scale, -d4[u]);
-              }
-              pp[i >> 1] = pack2(pe[0], pe[1]);
-              pp[(i >> 1) + 1] = pack2(pe[2], pe[3]);
-              dd[i >> 1] = pack2(de[0], de[1]);
-              dd[(i >> 1) + 1] = pack2(de[2], de[3]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint32_t off = (uint32_t)(((c * 4 + u) ^ rsw) << 4);
-              if (MODE == MODE_DKV) sts128(tt0 + off, pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
-              sts128(tt1 + off, dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
-            }
+          }
+        }
+        sred[g * BM + row] = m;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        m = fmaxf(sred[row], sred[BM + row]);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float mc = m * c2;
+        // ---- sweep 2: P = exp(s - m) -> T[g] (bf16, K-major, SWIZZLE_128B) ; partial row sums
+        float rsum = 0.f;
+        for (int j = g; j < n_tiles; j += 2, ++kx, ++kt) {
+          const int slot = kx & 1;
+          mbar_wait(x_full(g, slot), (kx >> 1) & 1);
+          fence_after();
+          tmem_ld32(tl + xcol(g, slot), v1);
+          tmem_ld32(tl + xcol(g, slot) + 32, v2);
+          tmem_wait_ld();
+          fence_before();
+          mbar_arrive(x_empty(g, slot));
+          mbar_wait(t_empty(g), (kt & 1) ^ 1);
+          const int ncol = min(BN, p.Ls - j * BN);
+          const uint32_t tt = tT(g, 0) + trow;
+          if (ncol == BN) {
+            fwd_chunk<false>(v1, 0, ncol, c2, mc, rsum, tt, rsw);
+            fwd_chunk<false>(v2, 1, ncol, c2, mc, rsum, tt, rsw);
+          } else {
+            fwd_chunk<true>(v1, 0, ncol, c2, mc, rsum, tt, rsw);
+            fwd_chunk<true>(v2, 1, ncol, c2, mc, rsum, tt, rsw);
           }
           fence_async_smem();
           mbar_arrive(t_full(g));
-          ++kx;
-          ++kt;
         }
-      // ---- epilogue: accumulators -> bf16 rows
-      mbar_wait(acc_full, 0);
-      fence_after();
-      const int r = r0 + row;
-#pragma unroll
-      for (int a = 0; a < NACC; ++a) {
-        bf16* obase = (a == 0 ? p.out0 : p.out1) + (long long)b * p.o_bs + (long long)r * p.o_rs + (long long)h * p.D;
-        // DKV: group a writes accumulator a; DQ: the two groups interleave 16-column chunks
-        const int c_begin = MODE == MODE_DKV ? 0 : g, c_step = MODE == MODE_DKV ? 1 : 2;
-        if (MODE == MODE_DKV && g != a) continue;
-        for (int cc = c_begin; cc * 16 < p.D; cc += c_step) {
-          tmem_ld16(tl + acccol(a) + cc * 16, v1);
+        sred[g * BM + row] = rsum;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        rsum = sred[row] + sred[BM + row];
+        // ---- epilogue: O = ACC / rowsum ; lse = m * scale + ln(rowsum)
+        mbar_wait(acc_full, wi & 1);
+        fence_after();
+        const float inv = 1.f / rsum;
+        bf16* orow = p.out0 + (long long)b * p.o_bs + (long long)r * p.o_rs + (long long)h * p.D;
+        for (int cc = g; cc * 16 < p.D; cc += 2) {
+          tmem_ld16(tl + acccol(0) + cc * 16, v1);
           tmem_wait_ld();
           if (r < p.Lr) {
 #pragma unroll
             for (int u = 0; u < 2; ++u)
               if (cc * 16 + u * 8 < p.D) {
-                uint4 w;
-                w.x = pack2(__uint_as_float(v1[u * 8]), __uint_as_float(v1[u * 8 + 1]));
-                w.y = pack2(__uint_as_float(v1[u * 8 + 2]), __uint_as_float(v1[u * 8 + 3]));
-                w.z = pack2(__uint_as_float(v1[u * 8 + 4]), __uint_as_float(v1[u * 8 + 5]));
-                w.w = pack2(__uint_as_float(v1[u * 8 + 6]), __uint_as_float(v1[u * 8 + 7]));
-                *reinterpret_cast<uint4*>(obase + cc * 16 + u * 8) = w;
+                uint4 wv;
+                wv.x = pack2(__uint_as_float(v1[u * 8]) * inv, __uint_as_float(v1[u * 8 + 1]) * inv);
+                wv.y = pack2(__uint_as_float(v1[u * 8 + 2]) * inv, __uint_as_float(v1[u * 8 + 3]) * inv);
+                wv.z = pack2(__uint_as_float(v1[u * 8 + 4]) * inv, __uint_as_float(v1[u * 8 + 5]) * inv);
+                wv.w = pack2(__uint_as_float(v1[u * 8 + 6]) * inv, __uint_as_float(v1[u * 8 + 7]) * inv);
+                *reinterpret_cast<uint4*>(orow + cc * 16 + u * 8) = wv;
               }
           }
         }
+        fence_before();
+        mbar_arrive(acc_empty);
+        if (g == 0 && r < p.Lr) p.lse[((long long)b * p.H + h) * p.Lr + r] = m * p.scale + __logf(rsum);
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // sred is rewritten by the next work item
+      } else {
+        // ---- backward modes
+        float lse2 = INFINITY, dl = 0.f;   // DQ: this thread's row statistics
+        if (MODE == MODE_DQ && r < p.Lr) {
+          const long long si = ((long long)b * p.H + h) * p.Lr + r;
+          lse2 = p.lse[si] * 1.4426950408889634f;
+          dl = p.delta[si] * p.scale;
+        }
+        if (active)
+          for (int j = g; j < n_tiles; j += jstep, ++kx, ++kt) {
+            const float4* cst = nullptr;
+            if (MODE == MODE_DKV) {
+              // column statistics of this tile (columns = query rows): lse * log2(e) (+inf masks the column), delta * scale
+              float* st = sstat + ((g * 2 + (kx & 1)) * 2) * BN;
+              if (tg < BN) {
+                const int qi = j * BN + tg;
+                float a = INFINITY, d = 0.f;
+                if (qi < p.Ls) {
+                  const long long si = ((long long)b * p.H + h) * p.Ls + qi;
+                  a = p.lse[si] * 1.4426950408889634f;
+                  d = p.delta[si] * p.scale;
+                }
+                st[tg] = a;
+                st[BN + tg] = d;
+              }
+              asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
+              cst = reinterpret_cast<const float4*>(st);
+            }
+            mbar_wait(x_full(g, 0), kx & 1);
+            fence_after();
+            const uint32_t tt0 = tT(g, 0) + trow;
+            const uint32_t tt1 = tT(g, NACC - 1) + trow;
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+              tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
+              tmem_ld32(tl + xcol(g, 1) + c * 32, v2);
+              tmem_wait_ld();
+              if (c == BN / 32 - 1) {
+                fence_before();
+                mbar_arrive(x_empty(g, 0));
+              }
+              if (c == 0) mbar_wait(t_empty(g), (kt & 1) ^ 1);
+              uint32_t pp[16], dd[16];
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float l4[4] = {lse2, lse2, lse2, lse2}, d4[4] = {dl, dl, dl, dl};
+                if (MODE == MODE_DKV) {
+                  const float4 a = cst[(c * 32 + i) >> 2], d = cst[(BN + c * 32 + i) >> 2];
+                  l4[0] = a.x, l4[1] = a.y, l4[2] = a.z, l4[3] = a.w;
+                  d4[0] = d.x, d4[1] = d.y, d4[2] = d.z, d4[3] = d.w;
+                }
+                float pe[4], de[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float e = ex2f(fmaf(__uint_as_float(v1[i + u]), c2, -l4[u]));
+                  pe[u] = e;
+                  de[u] = e * fmaf(__uint_as_float(v2[i + u]), p.scale, -d4[u]);
+                }
+                pp[i >> 1] = pack2(pe[0], pe[1]);
+                pp[(i >> 1) + 1] = pack2(pe[2], pe[3]);
+                dd[i >> 1] = pack2(de[0], de[1]);
+                dd[(i >> 1) + 1] = pack2(de[2], de[3]);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t off = (uint32_t)(((c * 4 + u) ^ rsw) << 4);
+                if (MODE == MODE_DKV) sts128(tt0 + off, pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
+                sts128(tt1 + off, dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
+              }
+            }
+            fence_async_smem();
+            mbar_arrive(t_full(g));
+          }
+        // ---- epilogue: accumulators -> bf16 rows
+        mbar_wait(acc_full, wi & 1);
+        fence_after();
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          bf16* obase = (a == 0 ? p.out0 : p.out1) + (long long)b * p.o_bs + (long long)r * p.o_rs + (long long)h * p.D;
+          // DKV: group a writes accumulator a; DQ: the two groups interleave 16-column chunks
+          const int c_begin = MODE == MODE_DKV ? 0 : g, c_step = MODE == MODE_DKV ? 1 : 2;
+          if (MODE == MODE_DKV && g != a) continue;
+          for (int cc = c_begin; cc * 16 < p.D; cc += c_step) {
+            tmem_ld16(tl + acccol(a) + cc * 16, v1);
+            tmem_wait_ld();
+            if (r < p.Lr) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                if (cc * 16 + u * 8 < p.D) {
+                  uint4 wv;
+                  wv.x = pack2(__uint_as_float(v1[u * 8]), __uint_as_float(v1[u * 8 + 1]));
+                  wv.y = pack2(__uint_as_float(v1[u * 8 + 2]), __uint_as_float(v1[u * 8 + 3]));
+                  wv.z = pack2(__uint_as_float(v1[u * 8 + 4]), __uint_as_float(v1[u * 8 + 5]));
+                  wv.w = pack2(__uint_as_float(v1[u * 8 + 6]), __uint_as_float(v1[u * 8 + 7]));
+                  *reinterpret_cast<uint4*>(obase + cc * 16 + u * 8) = wv;
+                }
+            }
+          }
+        }
+        fence_before();
+        mbar_arrive(acc_empty);
       }
     }
   }
@@ -560,7 +605,9 @@ int launch_attn(const AParams& ap, dim3 grid, cudaStream_t st) {
     PT_CUDA_OK(cudaFuncSetAttribute(attn_kernel<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<MODE, DP>::SMEM_BYTES));
     attr_set = true;
   }
-  attn_kernel<MODE, DP><<<grid, 352, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
+  const long long work = (long long)grid.x * grid.y * grid.z;   // (row blocks, heads, batch) -> one persistent CTA per SM
+  const int sms = pt_num_sms();
+  attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 352, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
@@ -594,6 +641,7 @@ extern "C" int pt_attn_fwd(const pt_attn_t* a, void* stream) {
   ap.Lr = a->Lq;
   ap.Ls = a->Lk;
   ap.H = a->H;
+  ap.B = a->B;
   ap.D = a->d;
   ap.scale = a->scale;
   ap.out0 = reinterpret_cast<bf16*>(a->o);
@@ -629,6 +677,7 @@ extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
     ap.Lr = a->Lq;
     ap.Ls = a->Lk;
     ap.H = a->H;
+  ap.B = a->B;
     ap.D = a->d;
     ap.scale = a->scale;
     ap.out0 = reinterpret_cast<bf16*>(a->dq);
@@ -649,6 +698,7 @@ extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
     ap.Lr = a->Lk;
     ap.Ls = a->Lq;
     ap.H = a->H;
+  ap.B = a->B;
     ap.D = a->d;
     ap.scale = a->scale;
     ap.out0 = reinterpret_cast<bf16*>(a->dv);
