@@ -82,6 +82,83 @@ def test_softmax_fwd_bwd(cuda, rows, n):
     assert rel(dS[:, :n], refd) < 6e-3
 
 
+# (B, H, Lq, Lk, d, fused): head dims of the tiny configs (8, 16), the text encoder (64) and the three UNet levels (40, 80, 160);
+# ragged lengths (not multiples of the 64 / 128 tiles), cross attention with Lk != Lq, fused QKV / KV column-slice layouts
+ATTN_CASES = [(2, 8, 24, 24, 8, True), (2, 8, 47, 33, 16, False), (1, 2, 128, 128, 40, True), (2, 3, 200, 150, 40, False),
+              (2, 12, 131, 131, 64, True), (2, 8, 94, 550, 80, False), (2, 8, 188, 188, 160, True), (3, 8, 94, 129, 160, False)]
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d,fused", ATTN_CASES)
+def test_fused_attention_fwd_bwd(cuda, B, H, Lq, Lk, d, fused):
+    """pt_attn_fwd / pt_attn_bwd against the oracle's attention (oracle/ref_model.py:_attn, identity projections) in fp32."""
+    import ref_model
+    from prompt_tts_b200 import ops
+    g = gen(11)
+    C = H * d
+    scale = d ** -0.5
+    if fused:      # self attention on a fused [Q | K | V] projection, gradients written into a fused buffer
+        qkv = bf(torch.randn(B, Lq, 3 * C, device=cuda, generator=g) * 1.5)
+        q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+        dbuf = torch.full_like(qkv, float("nan"))
+        dq, dk, dv = dbuf[:, :, :C], dbuf[:, :, C:2 * C], dbuf[:, :, 2 * C:]
+    else:          # cross attention: Q its own tensor, [K | V] fused
+        q = bf(torch.randn(B, Lq, C, device=cuda, generator=g) * 1.5)
+        kv = bf(torch.randn(B, Lk, 2 * C, device=cuda, generator=g) * 1.5)
+        k, v = kv[:, :, :C], kv[:, :, C:]
+        dq = torch.full_like(q, float("nan"))
+        dkv = torch.full_like(kv, float("nan"))
+        dk, dv = dkv[:, :, :C], dkv[:, :, C:]
+    do = bf(torch.randn(B, Lq, C, device=cuda, generator=g))
+    o = torch.full((B, Lq, C), float("nan"), device=cuda, dtype=torch.bfloat16)
+    lse = torch.full((B, H, Lq), float("nan"), device=cuda)
+    ops.attn_fwd(q, k, v, o, lse, H, d, scale)
+    ops.attn_bwd(q, k, v, o, lse, do, dq, dk, dv, H, d, scale)
+    torch.cuda.synchronize()
+
+    # oracle: _attn with selector projections (to_q = I, to_k = [I 0], to_v = [0 I] on ctx = [k | v], to_out = I), so the
+    # reference function computes exactly softmax(q k^T / sqrt d) v per head on our inputs
+    eye, zero = torch.eye(C, device=cuda), torch.zeros(C, C, device=cuda)
+    sd = {"a.to_q.weight": eye, "a.to_k.weight": torch.cat([eye, zero], 1), "a.to_v.weight": torch.cat([zero, eye], 1),
+          "a.to_out.0.weight": eye, "a.to_out.0.bias": torch.zeros(C, device=cuda)}
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    ref_o = ref_model._attn(sd, "a", qf, torch.cat([kf, vf], -1), H)
+    sc = (qf.view(B, Lq, H, d).transpose(1, 2) @ kf.view(B, Lk, H, d).transpose(1, 2).transpose(-1, -2)) * scale
+    ref_o.backward(do.float())
+    assert rel(o, ref_o) < 4e-3, rel(o, ref_o)
+    assert rel(lse, torch.logsumexp(sc, -1).detach()) < 1e-5
+    assert rel(dq, qf.grad) < 8e-3 and rel(dk, kf.grad) < 8e-3 and rel(dv, vf.grad) < 8e-3, (rel(dq, qf.grad), rel(dk, kf.grad), rel(dv, vf.grad))
+    # nothing outside the written slices was touched / nothing inside was left unwritten
+    assert torch.isfinite(o.float()).all() and torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all() and torch.isfinite(dv.float()).all()
+
+
+def test_fused_attention_properties_full_size(cuda):
+    """Size-independent properties at the bench shape (32 x 8 heads x 752 x 752, d = 40), where a dense reference would
+    need 2.3 GB per [B, H, Lq, Lk] matrix: rows of softmax sum to one (V = 1 -> O = 1), O is linear in V, and permuting the
+    keys together with the values leaves O unchanged."""
+    from prompt_tts_b200 import ops
+    g = gen(12)
+    B, H, L, d = 32, 8, 752, 40
+    C = H * d
+    qkv = bf(torch.randn(B, L, 3 * C, device=cuda, generator=g))
+    q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    lse = torch.empty(B, H, L, device=cuda)
+
+    def run(kk, vv):
+        kv = torch.cat([kk, vv], -1)          # K and V must share one row stride (they are slices of one fused projection)
+        o = torch.empty(B, L, C, device=cuda, dtype=torch.bfloat16)
+        ops.attn_fwd(q, kv[:, :, :C], kv[:, :, C:], o, lse, H, d, d ** -0.5)
+        return o.float()
+
+    ones = torch.ones(B, L, C, device=cuda, dtype=torch.bfloat16)
+    assert (run(k, ones) - 1).abs().max() < 8e-3
+    o1 = run(k, v)
+    o2 = run(k, bf(2 * v.float()))
+    assert rel(o2, 2 * o1) < 4e-3
+    perm = torch.randperm(L, device=cuda, generator=g)
+    o3 = run(k[:, perm].contiguous(), v[:, perm].contiguous())
+    assert rel(o3, o1) < 4e-3
+
+
 def test_geglu_add_upsample_copy(cuda):
     from prompt_tts_b200 import ops
     g = gen(4)
