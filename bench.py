@@ -282,7 +282,15 @@ def run_ours(args):
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down without destroy_process_group(): with NCCL work captured in a live CUDA graph it can block forever.
+        # Everything measured is already printed; leave through a barrier and a hard exit (exit code 0).
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def gemm_profile(step, model, ops, torch):
