@@ -183,7 +183,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     # per-GEMM event timing over one eager step: the roofline of the dominant kernel family (tcgen05 GEMM)
-    gemm_flops, gemm_ms = gemm_profile(step, model, ops, torch)
+    gemm_flops, gemm_ms, attn_flops, attn_ms = gemm_profile(step, model, ops, torch)
 
     use_graph = not args.no_graph
     graph = None
@@ -260,6 +260,13 @@ def run_ours(args):
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        traffic, traffic_note = None, "no ncu capture found under profiles/"
+        try:   # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (not measured live)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            traffic_note = f"{tr['kernel']} {tr['shape']}: {traffic / 1e6:.1f} MB DRAM vs {tr['algorithmic_bytes'] / 1e6:.1f} MB algorithmic; {tr['source']}"
+        except Exception:
+            pass
         h2d = sum(host[k].numel() * host[k].element_size() for k in ("x0", "noise", "t", "ids", "mask"))
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -272,9 +279,13 @@ def run_ours(args):
             "gpu_launches": int(launches_per_step) * args.steps * 2,   # timed value region + timed e2e region
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": ck,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "gemm_kernel<BN> (tcgen05 GEMM family: all conv / linear / attention contractions)",
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "gemm_kernel<BN> (persistent tcgen05 GEMM family: every conv / linear contraction, forward, data- and weight-gradient)",
                          "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_flops / 1e12, "peak_source": peak_src + " (of measured)",
+                         "traffic_note": traffic_note,
+                         "attention": {"kernel": "attn_kernel<mode, DP> (fused tcgen05 softmax attention fwd / dQ / dKV)", "ms_per_step": attn_ms,
+                                       "tflop_per_step": attn_flops / 1e12, "achieved": attn_flops / (attn_ms / 1e3) / 1e12 if attn_ms > 0 else 0.0,
+                                       "bound": "MUFU (exp) + TMEM round trips, not the tensor pipe: see DESIGN.md section 3"},
                          "step_frac": (FLOP_PER_FRAME * BATCH * T_FRAMES / (ms_step / 1e3) / 1e12) / peak},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -294,31 +305,50 @@ def run_ours(args):
 
 
 def gemm_profile(step, model, ops, torch):
-    """One eager step with every pt_gemm bracketed by CUDA events: (algorithmic FLOPs, summed ms) of the GEMM family."""
-    recs = []
-    orig = ops.gemm
+    """One eager step with every pt_gemm / pt_attn_* call bracketed by CUDA events on the launching stream:
+    (algorithmic FLOPs, summed ms) of the GEMM family and of the fused-attention family."""
+    recs, arecs = [], []
+    orig, orig_af, orig_ab = ops.gemm, ops.attn_fwd, ops.attn_bwd
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def timed_gemm(a, b, segs, M, N, out, **kw):
         k_total = sum(s.nk * s.nrep for s in segs)
         flops = 2.0 * M * N * k_total * kw.get("nz2", 1) * kw.get("nz3", 1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = ev()
         e0.record()
         orig(a, b, segs, M, N, out, **kw)
         e1.record()
         recs.append((flops, e0, e1))
 
-    import prompt_tts_b200.engine as eng
-    ops.gemm = timed_gemm
+    def timed_af(q, k, v, o, lse, heads, d, scale):
+        e0, e1 = ev()
+        e0.record()
+        orig_af(q, k, v, o, lse, heads, d, scale)
+        e1.record()
+        arecs.append((4.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * d, e0, e1))
+
+    def timed_ab(q, k, v, o, lse, d_o, dq, dk, dv, heads, d, scale):
+        e0, e1 = ev()
+        e0.record()
+        orig_ab(q, k, v, o, lse, d_o, dq, dk, dv, heads, d, scale)
+        e1.record()
+        arecs.append((10.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * d, e0, e1))
+
+    ops.gemm, ops.attn_fwd, ops.attn_bwd = timed_gemm, timed_af, timed_ab
     try:
         for p in model.parameters():
             p.grad = None
         step()
         torch.cuda.synchronize()
     finally:
-        ops.gemm = orig
+        ops.gemm, ops.attn_fwd, ops.attn_bwd = orig, orig_af, orig_ab
     fl = sum(r[0] for r in recs)
     ms = sum(r[1].elapsed_time(r[2]) for r in recs)
-    return fl, ms
+    afl = sum(r[0] for r in arecs)
+    ams = sum(r[1].elapsed_time(r[2]) for r in arecs)
+    return fl, ms, afl, ams
 
 
 def main():
