@@ -288,6 +288,14 @@ def run_ours(args):
                                        "bound": "MUFU (exp) + TMEM round trips, not the tensor pipe: see DESIGN.md section 3"},
                          "step_frac": (FLOP_PER_FRAME * BATCH * T_FRAMES / (ms_step / 1e3) / 1e12) / peak},
         }
+        if world == 1 and not args.no_sampling:
+            # secondary figure of BASELINE.json's metric (configs[3]): sampling real-time factor, denoiser only
+            del graph
+            graph = None
+            for p in model.parameters():
+                p.grad = None
+            torch.cuda.empty_cache()
+            line["sampling"] = sampling_rtf(model, cfg, dev, torch, peak)
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_step_time(2, 1)
             line["cpu_baseline"] = cb
@@ -302,6 +310,31 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def sampling_rtf(model, cfg, dev, torch, peak_tflops):
+    """BASELINE.json configs[3] / SURVEY 8d config 4: 100 DDPM steps, batch 64 x 20 s utterances (1504 frames at 75 fps) with a
+    3 s (225-frame) speech prompt in-painted at every step; text encoder once, cross-attention K/V cached, one captured denoiser
+    forward replayed per step.  RTF = seconds of GPU time / seconds of audio generated (denoiser only, codec decoder excluded)."""
+    from prompt_tts_b200.sample import DDPMSampler
+    Bs, Ts, P, steps = 64, 1504, 225, 100
+    inp = synth(cfg, Bs, Ts, 4000, dev)
+    prompt = inp["x0"][..., :P].contiguous()
+    smp = DDPMSampler(model, n_infer=steps)
+    model.eval()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    x = smp.sample(inp["ids"], Ts, prompt=prompt, seed=0)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3
+    audio_s = Bs * Ts / 75.0
+    flop = Bs * (45.2e9 + steps * 428.0e9)           # SURVEY 8d: text encoder once + 100 UNet forwards at T = 1504, per utterance
+    return {"rtf": sec / audio_s, "seconds": sec, "audio_seconds": audio_s, "steps": steps, "batch": Bs, "frames": Ts, "prompt_frames": P,
+            "tflops": flop / sec / 1e12, "frac_of_tensor_roofline": flop / sec / 1e12 / peak_tflops,
+            "finite": bool(torch.isfinite(x).all().item()),
+            "note": "includes the one eager warm-up forward and the graph capture of the loop (first two of the 100 steps)"}
 
 
 def gemm_profile(step, model, ops, torch):
@@ -359,6 +392,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sampling", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -28,6 +28,7 @@
  *   pt_rvq_decode      encodec ResidualVectorQuantization.decode   decode_codec.py:16
  *   pt_codes_affine    codes/1023 -> Normalize(0.5,0.5)            tts/dataloader.py:64,77,168-170
  *   pt_add_noise, pt_mse_*        train-step glue                  train.py:96-98,107
+ *   pt_ddpm_step       sampling step (diffusers DDPMScheduler.step; SURVEY 8 row N1, not in the reference tree)
  */
 #ifndef PROMPT_TTS_B200_H
 #define PROMPT_TTS_B200_H
@@ -199,6 +200,12 @@ int pt_text_embed_bwd(const int32_t* ids, const void* dy, float* dE, int B, int 
 /* train-step glue (train.py:96-98,107) */
 int pt_add_noise(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp, const float* sqrt_1macp,
                  float* xt, int B, int64_t per_sample, void* stream);
+/* One DDPM ancestral sampling step (diffusers 0.15 DDPMScheduler.step as the north-star sampling config uses it: epsilon
+ * prediction, clip_sample, fixed_small variance; acp_t / acp_prev = alphas_cumprod at t and at the previous inference
+ * timestep, acp_prev = 1 for the last step, which adds no noise).  x_prev = c_x0 * clamp(x0_hat, -1, 1) + c_xt * x_t + sigma * noise.
+ * known != NULL: the first `keep` frames of every length-T row are overwritten from `known` (speech-prompt in-painting). */
+int pt_ddpm_step(const float* eps, const float* xt, const float* noise, const float* known, float* out, int64_t n, int T, int keep,
+                 float acp_t, float acp_prev, void* stream);
 /* loss += mean((pred - target)^2) ; dpred = 2 (pred - target) / n * gscale ; loss must be zeroed by caller */
 int pt_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, int64_t n, float gscale, void* stream);
 

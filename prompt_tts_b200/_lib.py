@@ -120,6 +120,7 @@ _SIGS = {
     "text_embed_bwd": "pppiiiip",
     "add_noise": "ppppppilp",
     "mse_fwd_bwd": "pppplfp",
+    "ddpm_step": "pppppliiffp",
     "rvq_encode": "pppiiiiip",
     "rvq_encode_ws": "ppppiiiiip",
     "rvq_cb_sq": "ppiiip",

@@ -411,6 +411,24 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+
+// DDPM ancestral step (diffusers 0.15 DDPMScheduler.step, epsilon prediction, clip_sample, fixed_small variance):
+//   x0 = clamp((x_t - sqrt(1-acp_t) eps) / sqrt(acp_t), -1, 1);  x_prev = c_x0 * x0 + c_xt * x_t + sigma * noise
+// with optional in-painting of the first `keep` frames of every [C, T] plane from `known` (speech-prompt protocol of the sampler).
+__global__ void ddpm_step_kernel(const float* __restrict__ eps, const float* xt, const float* __restrict__ noise,
+                                 const float* __restrict__ known, float* out, long long n, int T, int keep, float sqrt_acp,
+                                 float sqrt_1macp, float c_x0, float c_xt, float sigma) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = xt[i];
+    float x0 = (x - sqrt_1macp * eps[i]) / sqrt_acp;
+    x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    float r = c_x0 * x0 + c_xt * x;
+    if (sigma != 0.f) r += sigma * noise[i];
+    if (known != nullptr && (int)(i % T) < keep) r = known[i];
+    out[i] = r;
+  }
+}
+
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
@@ -561,6 +579,24 @@ extern "C" int pt_add_noise(const float* x0, const float* noise, const int64_t* 
   PT_REQUIRE(B > 0 && per_sample > 0, "add_noise: B=%d", B);
   add_noise_kernel<<<grid_for((long long)B * per_sample, 256), 256, 0, ST>>>(x0, noise, t, sqrt_acp, sqrt_1macp, xt, (long long)B * per_sample,
                                                                               per_sample);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+extern "C" int pt_ddpm_step(const float* eps, const float* xt, const float* noise, const float* known, float* out, int64_t n, int T, int keep,
+                            float acp_t, float acp_prev, void* stream) {
+  PT_REQUIRE(n > 0 && T > 0 && keep >= 0 && keep <= T, "ddpm_step: n=%lld T=%d keep=%d", (long long)n, T, keep);
+  PT_REQUIRE(acp_t > 0.f && acp_t < 1.f && acp_prev > 0.f && acp_prev <= 1.f && acp_prev >= acp_t, "ddpm_step: acp_t=%g acp_prev=%g", acp_t, acp_prev);
+  // effective one-step alpha / beta between t and t_prev (set_timesteps(N) over the 1000-step training schedule), in fp32 and
+  // in the order diffusers' DDPMScheduler.step evaluates them: near t -> 0, 1 - a_t / a_prev is ill-conditioned, and parity with
+  // the reference means reproducing its rounding, not improving on it
+  const float a_t = acp_t, a_p = acp_prev;
+  const float b_t = 1.f - a_t, b_p = 1.f - a_p;
+  const float cur_alpha = a_t / a_p, cur_beta = 1.f - cur_alpha;
+  const float c_x0 = sqrtf(a_p) * cur_beta / b_t, c_xt = sqrtf(cur_alpha) * b_p / b_t;
+  float var = b_p / b_t * cur_beta;
+  if (var < 1e-20f) var = 1e-20f;
+  const float sigma = (noise != nullptr && acp_prev < 1.f) ? sqrtf(var) : 0.f;
+  ddpm_step_kernel<<<grid_for(n, 256, 4), 256, 0, ST>>>(eps, xt, noise, known, out, n, T, keep, sqrtf(a_t), sqrtf(b_t), c_x0, c_xt, sigma);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }

@@ -71,6 +71,9 @@ class Tape:
         self.pgrad_order: List[Tuple[Sequence[torch.Tensor], torch.Tensor]] = []   # (params, buffer) in completion order
         self.grad_alloc: Optional[Callable[[Sequence[torch.Tensor]], Optional[torch.Tensor]]] = None   # flat-buffer provider (dp.GradSync)
         self.on_ready: Optional[Callable[[List[Tuple[Sequence[torch.Tensor], torch.Tensor]]], None]] = None
+        # inference only: step-invariant cross-attention K/V projections of the text encoding, keyed by attention module
+        # (the sampler passes the same dict to each of its 100 denoiser forwards)
+        self.kv_cache: Optional[Dict[int, "Var"]] = None
 
     def record(self, fn: Callable[[], None]) -> None:
         if self.recording:

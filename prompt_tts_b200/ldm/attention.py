@@ -37,7 +37,11 @@ class Attention(nn.Module):
             o = E.attention_core(tape, qkv, 0, qkv, C, 2 * C, self.heads, C)
         else:
             q = E.linear(tape, hn, [self.to_q.weight])
-            kv = E.linear(tape, ctx, [self.to_k.weight, self.to_v.weight])                        # fused KV GEMM
+            kv = None if tape.kv_cache is None or tape.recording else tape.kv_cache.get(id(self))
+            if kv is None:
+                kv = E.linear(tape, ctx, [self.to_k.weight, self.to_v.weight])                    # fused KV GEMM
+                if tape.kv_cache is not None and not tape.recording:
+                    tape.kv_cache[id(self)] = kv
             o = E.attention_core(tape, q, 0, kv, 0, C, self.heads, C)
         return E.linear(tape, o, [self.to_out[0].weight], [self.to_out[0].bias], residual=residual)
 
