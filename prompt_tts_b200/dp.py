@@ -72,8 +72,10 @@ class GradSync:
             # first step: learn the completion order, build the flat buffer, and reduce this step's gradients in one go
             order = tape.pgrad_order
             self.layout, off = {}, 0
+            self.groups = []      # (parameters whose gradients share one contiguous slice, offset, numel) in buffer order
             for params, buf in order:
                 self.layout[id(params[0])] = (off, buf.numel())
+                self.groups.append((list(params), off, buf.numel()))
                 off += buf.numel()
             self.total = off
             dev = order[0][1].device

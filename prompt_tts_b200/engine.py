@@ -36,10 +36,11 @@ class PackCache:
 
     def __init__(self):
         self._d: Dict[tuple, Tuple[tuple, torch.Tensor]] = {}
+        self.epoch = 0      # bumped by optimisers that update parameters through raw pointers (no version-counter change)
 
     def get(self, params: Sequence[torch.Tensor], kind: str) -> torch.Tensor:
         key = (kind,) + tuple(id(p) for p in params)
-        ver = tuple((p._version, p.data_ptr()) for p in params)
+        ver = (self.epoch,) + tuple((p._version, p.data_ptr()) for p in params)
         hit = self._d.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
