@@ -80,6 +80,7 @@ typedef struct {
   int32_t nrep;           /* >= 1 */
   int32_t rep_is_batch;   /* 1: c2 := rep_c2_0 + rep (reduction over dim[2]) */
   int32_t rep_c2_0;
+  int32_t b_k0_z2;        /* b_k0 += z2 * b_k0_z2: one launch covers the three taps of a conv weight gradient (z2 = tap) */
 } pt_segment_t;
 
 #define PT_OUT_BF16 0

@@ -19,7 +19,7 @@ class Operand(C.Structure):
 class Segment(C.Structure):
     _fields_ = [("a_idx", C.c_int32), ("b_idx", C.c_int32), ("a_k0", C.c_int32), ("b_k0", C.c_int32),
                 ("a_mn_shift", C.c_int32), ("b_mn_shift", C.c_int32), ("nk", C.c_int32), ("nrep", C.c_int32),
-                ("rep_is_batch", C.c_int32), ("rep_c2_0", C.c_int32)]
+                ("rep_is_batch", C.c_int32), ("rep_c2_0", C.c_int32), ("b_k0_z2", C.c_int32)]
 
 
 class Gemm(C.Structure):

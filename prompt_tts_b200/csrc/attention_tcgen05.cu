@@ -556,25 +556,40 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   }
 }
 
-// delta[b, h, q] = sum_j dO[b, q, h*d + j] * O[b, q, h*d + j]   (one thread per (row, head))
-__global__ void attn_delta_kernel(const bf16* __restrict__ o, long long o_rs, long long o_bs, const bf16* __restrict__ d_o, long long do_rs,
-                                  long long do_bs, float* __restrict__ delta, int B, int H, int L, int D) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)B * L * H) return;
-  const int hh = (int)(i % H);
-  const long long bl = i / H;
-  const int l = (int)(bl % L), bb = (int)(bl / L);
-  const bf16* po = o + (long long)bb * o_bs + (long long)l * o_rs + (long long)hh * D;
-  const bf16* pd = d_o + (long long)bb * do_bs + (long long)l * do_rs + (long long)hh * D;
-  float acc = 0.f;
-  for (int j = 0; j < D; j += 8) {
-    float a[8], c[8];
-    load8(po + j, a);
-    load8(pd + j, c);
+// delta[b, h, q] = sum_j dO[b, q, h*d + j] * O[b, q, h*d + j].  A CTA takes DELTA_ROWS rows; consecutive threads read consecutive
+// 16-byte vectors of a row (coalesced), each vector lies inside one head (d % 8 == 0), partial dots meet in shared memory.
+constexpr int DELTA_ROWS = 8;
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long o_rs, long long o_bs, const bf16* __restrict__ d_o,
+                                                         long long do_rs, long long do_bs, float* __restrict__ delta, int B, int H, int L, int D) {
+  __shared__ float acc[DELTA_ROWS * 64];   // [row][head], H <= 64
+  const long long row0 = (long long)blockIdx.x * DELTA_ROWS;
+  const long long nrows = (long long)B * L;
+  const int nvec = (H * D) >> 3, vph = D >> 3;
+  for (int i = threadIdx.x; i < DELTA_ROWS * H; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < DELTA_ROWS * nvec; i += blockDim.x) {
+    const int rl = i / nvec, v = i - rl * nvec;
+    const long long row = row0 + rl;
+    if (row < nrows) {
+      const int bb = (int)(row / L), l = (int)(row - (long long)bb * L);
+      float a[8], c[8];
+      load8(o + (long long)bb * o_bs + (long long)l * o_rs + v * 8, a);
+      load8(d_o + (long long)bb * do_bs + (long long)l * do_rs + v * 8, c);
+      float t = 0.f;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc = fmaf(a[u], c[u], acc);
+      for (int u = 0; u < 8; ++u) t = fmaf(a[u], c[u], t);
+      atomicAdd(&acc[rl * H + v / vph], t);
+    }
   }
-  delta[((long long)bb * H + hh) * L + l] = acc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < DELTA_ROWS * H; i += blockDim.x) {
+    const int rl = i / H, hh = i - rl * H;
+    const long long row = row0 + rl;
+    if (row < nrows) {
+      const int bb = (int)(row / L), l = (int)(row - (long long)bb * L);
+      delta[((long long)bb * H + hh) * L + l] = acc[i];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -661,10 +676,11 @@ extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
              "pt_attn_bwd: alignment");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   {
-    const long long n = (long long)a->B * a->Lq * a->H;
-    attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(a->o), a->o_rs, a->o_bs,
-                                                                   reinterpret_cast<const bf16*>(a->d_o), a->do_rs, a->do_bs, a->delta, a->B, a->H,
-                                                                   a->Lq, a->d);
+    PT_REQUIRE(a->H <= 64, "pt_attn_bwd: at most 64 heads (H=%d)", a->H);
+    const long long nrows = (long long)a->B * a->Lq;
+    attn_delta_kernel<<<(unsigned)((nrows + DELTA_ROWS - 1) / DELTA_ROWS), 256, 0, st>>>(
+        reinterpret_cast<const bf16*>(a->o), a->o_rs, a->o_bs, reinterpret_cast<const bf16*>(a->d_o), a->do_rs, a->do_bs, a->delta, a->B, a->H,
+        a->Lq, a->d);
     PT_LAUNCH_CHECK();
   }
   {  // dQ: resident Q, dO ; streamed K, V

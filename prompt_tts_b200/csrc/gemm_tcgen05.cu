@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
           const int bz2 = sg.rep_is_batch ? (sg.rep_c2_0 + rep) : z2;
           const int a2 = p.a_batched[sg.a_idx] ? bz2 : 0, a3 = p.a_batched[sg.a_idx] ? z3 : 0;
           const int b2 = p.b_batched[sg.b_idx] ? bz2 : 0, b3 = p.b_batched[sg.b_idx] ? z3 : 0;
-          const int ka = sg.a_k0 + kb * BK, kbb = sg.b_k0 + kb * BK;
+          const int ka = sg.a_k0 + kb * BK, kbb = sg.b_k0 + z2 * sg.b_k0_z2 + kb * BK;
           if (p.a_kmajor) {
             tma_load_4d(sa, ta, full_bar(s), ka, m0 + sg.a_mn_shift, a2, a3);
           } else {

@@ -231,12 +231,17 @@ def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: 
         # (fp32 atomic accumulate with column stride 3 -- no packed temporary, no un-pack pass)
         g3 = tape.pgrad(wparam).view(Co, Ci * 3)
         dy_op = ops.operand(dy, False, batched=True)
-        for t, (ai, sh) in enumerate(taps):
-            xs = xd if stride == 1 else (xd[:, 0::2] if ai == 0 else xd[:, 1::2])
-            seg = ops.segment(Lo, b_k0=sh, nrep=B, rep_is_batch=True)
-            tiles = ((Co + 127) // 128) * ((Ci + 127) // 128)
-            ops.gemm([dy_op], [ops.operand(xs, False, batched=True)], [seg], Co, Ci, g3[:, t:],
-                     out_strides=(3 * Ci, 0, 0), out_mode=OUT_F32_ATOMIC_ADD, splitk=_splitk(tiles, B * ((Lo + 63) // 64)), out_stride_n=3)
+        if stride == 1:
+            # the three taps in ONE stream-K launch: z2 = tap shifts the rows of x by tap - 1 and the output column by tap
+            seg = ops.segment(Lo, b_k0=-1, b_k0_z2=1, nrep=B, rep_is_batch=True)
+            ops.gemm([dy_op], [ops.operand(xd, False, batched=True)], [seg], Co, Ci, g3, out_strides=(3 * Ci, 1, 0), nz2=3,
+                     out_mode=OUT_F32_ATOMIC_ADD, out_stride_n=3)
+        else:
+            for t, (ai, sh) in enumerate(taps):
+                xs = xd[:, 0::2] if ai == 0 else xd[:, 1::2]
+                seg = ops.segment(Lo, b_k0=sh, nrep=B, rep_is_batch=True)
+                ops.gemm([dy_op], [ops.operand(xs, False, batched=True)], [seg], Co, Ci, g3[:, t:],
+                         out_strides=(3 * Ci, 0, 0), out_mode=OUT_F32_ATOMIC_ADD, out_stride_n=3)
         if x.needs_grad:
             dy_k = ops.operand(dy, True, batched=True)
             wp_mn = ops.operand(wp, False)

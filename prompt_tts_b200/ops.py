@@ -49,8 +49,9 @@ def operand(t: torch.Tensor, kmajor: bool, batched: bool = False) -> Operand:
     return op
 
 
-def segment(nk, a_idx=0, b_idx=0, a_k0=0, b_k0=0, a_shift=0, b_shift=0, nrep=1, rep_is_batch=False, rep_c2_0=0) -> Segment:
+def segment(nk, a_idx=0, b_idx=0, a_k0=0, b_k0=0, a_shift=0, b_shift=0, nrep=1, rep_is_batch=False, rep_c2_0=0, b_k0_z2=0) -> Segment:
     s = Segment()
+    s.b_k0_z2 = b_k0_z2
     s.a_idx, s.b_idx, s.a_k0, s.b_k0 = a_idx, b_idx, a_k0, b_k0
     s.a_mn_shift, s.b_mn_shift, s.nk, s.nrep = a_shift, b_shift, nk, nrep
     s.rep_is_batch, s.rep_c2_0 = (1 if rep_is_batch else 0), rep_c2_0
