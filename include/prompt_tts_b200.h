@@ -141,7 +141,8 @@ int pt_softmax_bwd(const float* dP, const void* P, void* dS, int64_t rows, int n
  * tts/ldm/transformer_1d.py:258-265 and tts/models.py:95-100).  q/k/v/o/d_o/dq/dk/dv point at the head-0 column of
  * bf16 [B, L, W] tensors (row stride *_rs, batch stride *_bs, in elements; head h occupies columns [h*d, (h+1)*d)),
  * so fused QKV / KV projections are consumed and their gradients produced in place.  d: multiple of 8, <= 192.
- * lse [B, H, Lq] fp32 = log-sum-exp of the scaled logits (written by fwd, read by bwd); delta: bwd scratch [B, H, Lq]. */
+ * lse [B, H, Lq] fp32 = log-sum-exp of the scaled logits (written by fwd, read by bwd); delta: bwd scratch [B, H, Lq].
+ * pt_attn_bwd: Lq <= 1984 (the per-query statistics of one (batch, head) are staged in shared memory). */
 typedef struct {
   const void* q; int64_t q_rs, q_bs;
   const void* k; const void* v; int64_t kv_rs, kv_bs;

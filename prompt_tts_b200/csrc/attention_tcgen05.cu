@@ -57,7 +57,7 @@ struct ACfg {
   static constexpr int STAGE_BYTES = 2 * S_BYTES;
   static constexpr int T_BYTES = BM * BN * 2;
   static constexpr int FIXED = NX * R_BYTES + XBUF * NACC * T_BYTES;
-  static constexpr int BUDGET = 221 * 1024;                  // of 227 KB: leaves room for alignment slack, barriers, statistics
+  static constexpr int BUDGET = (MODE == MODE_DKV ? 205 : 221) * 1024;                  // of 227 KB: leaves room for alignment slack, barriers, statistics
   static constexpr int NSTAGE_FIT = (BUDGET - FIXED) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_FIT >= 8 ? 8 : NSTAGE_FIT;   // deep ring: bytes in flight must cover the TMA round trip
   static constexpr int LOOKAHEAD = XBUF == 2 ? (NSTAGE >= 3 ? 2 : (NSTAGE >= 2 ? 1 : 0)) : 0;   // stage-1 MMAs issued ahead of stage 2
@@ -65,7 +65,8 @@ struct ACfg {
   static constexpr int OFF_T = OFF_S + NSTAGE * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_T + XBUF * NACC * T_BYTES;
   static constexpr int OFF_STAT = OFF_BAR + 512;
-  static constexpr int STAT_BYTES = 2 * 2 * 2 * BN * 4 + 2 * BM * 4;   // DKV column stats [g][buf][2][BN] + row reduce [2][BM]
+  static constexpr int STAT_COLS = 2048;                     // DKV: query rows whose statistics fit in shared memory
+  static constexpr int STAT_BYTES = (MODE == MODE_DKV ? 2 * STAT_COLS * 4 : 0) + 2 * BM * 4;   // DKV column stats [2][STAT_COLS] + row reduce [2][BM]
   static constexpr int SMEM_BYTES = 1024 + OFF_STAT + STAT_BYTES;
   static constexpr int XW = 128;                             // TMEM columns per X buffer (two 64-column products)
   static constexpr int X_COLS = XBUF * XW;
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   const uint32_t acc_empty = bar0 + 8u * 30;
   const uint32_t r_empty = bar0 + 8u * 31;
   const uint32_t tmem_slot = bar0 + 8u * 32;
-  float* sstat = reinterpret_cast<float*>(sgen + C::OFF_STAT);          // [g][buf][2][BN]
-  float* sred = sstat + 2 * 2 * 2 * BN;                                 // [2][BM]
+  float* sstat = reinterpret_cast<float*>(sgen + C::OFF_STAT);          // DKV: [2][STAT_COLS] column statistics of the work item
+  float* sred = sstat + (MODE == MODE_DKV ? 2 * C::STAT_COLS : 0);      // [2][BM]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.Ls + BN - 1) / BN;
@@ -452,26 +453,25 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
           lse2 = p.lse[si] * 1.4426950408889634f;
           dl = p.delta[si] * p.scale;
         }
+        if (MODE == MODE_DKV) {
+          // column statistics of the whole work item (columns = query rows), once: lse * log2(e) (+inf masks a column), delta * scale
+          asm volatile("bar.sync 2, 256;" ::: "memory");     // everyone has finished reading the previous work item's statistics
+          const long long sb = ((long long)b * p.H + h) * p.Ls;
+          for (int qi = threadIdx.x - 64; qi < n_tiles * BN; qi += 256) {
+            float a = INFINITY, d = 0.f;
+            if (qi < p.Ls) {
+              a = __ldg(p.lse + sb + qi) * 1.4426950408889634f;
+              d = __ldg(p.delta + sb + qi) * p.scale;
+            }
+            sstat[qi] = a;
+            sstat[C::STAT_COLS + qi] = d;
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
         if (active)
           for (int j = g; j < n_tiles; j += jstep, ++kx, ++kt) {
-            const float4* cst = nullptr;
-            if (MODE == MODE_DKV) {
-              // column statistics of this tile (columns = query rows): lse * log2(e) (+inf masks the column), delta * scale
-              float* st = sstat + ((g * 2 + (kx & 1)) * 2) * BN;
-              if (tg < BN) {
-                const int qi = j * BN + tg;
-                float a = INFINITY, d = 0.f;
-                if (qi < p.Ls) {
-                  const long long si = ((long long)b * p.H + h) * p.Ls + qi;
-                  a = p.lse[si] * 1.4426950408889634f;
-                  d = p.delta[si] * p.scale;
-                }
-                st[tg] = a;
-                st[BN + tg] = d;
-              }
-              asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
-              cst = reinterpret_cast<const float4*>(st);
-            }
+            const float4* cst = reinterpret_cast<const float4*>(sstat + j * BN);
+            const float4* cdl = reinterpret_cast<const float4*>(sstat + C::STAT_COLS + j * BN);
             mbar_wait(x_full(g, 0), kx & 1);
             fence_after();
             const uint32_t tt0 = tT(g, 0) + trow;
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
               for (int i = 0; i < 32; i += 4) {
                 float l4[4] = {lse2, lse2, lse2, lse2}, d4[4] = {dl, dl, dl, dl};
                 if (MODE == MODE_DKV) {
-                  const float4 a = cst[(c * 32 + i) >> 2], d = cst[(BN + c * 32 + i) >> 2];
+                  const float4 a = cst[(c * 32 + i) >> 2], d = cdl[(c * 32 + i) >> 2];
                   l4[0] = a.x, l4[1] = a.y, l4[2] = a.z, l4[3] = a.w;
                   d4[0] = d.x, d4[1] = d.y, d4[2] = d.z, d4[3] = d.w;
                 }
@@ -670,6 +670,7 @@ extern "C" int pt_attn_fwd(const pt_attn_t* a, void* stream) {
 extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
   if (int r = check_common(a)) return r;
   PT_REQUIRE(a->o && a->d_o && a->dq && a->dk && a->dv && a->delta, "pt_attn_bwd: null pointer");
+  PT_REQUIRE(a->Lq <= 2048 - BN, "pt_attn_bwd: Lq=%d exceeds the %d query rows whose statistics are staged in shared memory", a->Lq, 2048 - BN);
   PT_REQUIRE((reinterpret_cast<uintptr_t>(a->o) & 15) == 0 && a->o_rs % 8 == 0 && a->o_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(a->dq) & 15) == 0 &&
                  a->dq_rs % 8 == 0 && a->dq_bs % 8 == 0 && (reinterpret_cast<uintptr_t>(a->dk) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(a->dv) & 15) == 0 && a->dkv_rs % 8 == 0 && a->dkv_bs % 8 == 0,
