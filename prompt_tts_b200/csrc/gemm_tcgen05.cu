@@ -270,13 +270,15 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int et = threadIdx.x - 64;
     int segi = 0;
+    int staged_n0 = -1, staged_z2 = -1;
     while (sched.next(tile, it_begin, it_end)) {
       int m0, n0, z2, z3;
       decode(tile, m0, n0, z2, z3);
       const int acc = segi & 1;
-      // stage the per-column additive term (bias + per-batch time shift) in shared memory
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with the previous segment's sbias
-      {
+      // stage the per-column additive term (bias + per-batch time shift) in shared memory -- only when the column block (or the
+      // batch element of a time shift) differs from what is already there: tiles are walked m-fastest, so this is rare
+      if (n0 != staged_n0 || (p.bias_z2 != nullptr && z2 != staged_z2)) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with the previous contents
         const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.bz2_stride : nullptr;
         for (int j = et; j < BN; j += 128) {
           const int n = n0 + j;
@@ -287,8 +289,10 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
           }
           sbias[j] = bsum;
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        staged_n0 = n0;
+        staged_z2 = z2;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const uint32_t full_parity = (segi >> 1) & 1;
       if (p.out_dtype == PT_OUT_BF16) {
