@@ -50,7 +50,9 @@ template <int MODE, int DP>
 struct ACfg {
   static constexpr int NX = MODE == MODE_FWD ? 1 : 2;       // stage-1 products per tile
   static constexpr int NACC = MODE == MODE_DKV ? 2 : 1;     // stage-2 accumulators
-  static constexpr int XBUF = (MODE == MODE_DKV && DP > 128) ? 1 : 2;   // TMEM budget: 2*128 + 2*192 > 512
+  // one X buffer / one transform group: DKV at DP = 192 for TMEM (2*128 + 2*192 > 512); DQ at DP = 192 so that shared memory
+  // holds two ring stages (a single stage serialises the TMA round trip with every tile)
+  static constexpr int XBUF = (MODE != MODE_FWD && DP > 128) ? 1 : 2;
   static constexpr int KB = DP / 64;                         // 64-element blocks along the head dimension
   static constexpr int R_BYTES = BM * DP * 2;
   static constexpr int S_BYTES = BN * DP * 2;
