@@ -43,7 +43,7 @@ struct alignas(64) KParams {
   int a_kmajor, b_kmajor;
   int a_batched[2], b_batched[2];
   int M, N, nz2, nz3;
-  int mt, nt, tiles, work, streamk;
+  int mt, nt, tiles, work, streamk;   // mt counts groups of MC row tiles when the kernel runs as clusters of MC CTAs
   int total_iters;
   void* out;
   int out_dtype;
@@ -83,18 +83,20 @@ struct Cfg {
 // yields one segment per tile, each flushed with atomic adds.
 struct Sched {
   int total_iters, streamk, cursor, end, stride;
-  __device__ __forceinline__ Sched(const KParams& p) {
+  // `mc` CTAs of a cluster walk the same schedule in lockstep (they share B tiles by TMA multicast)
+  __device__ __forceinline__ Sched(const KParams& p, int mc) {
     total_iters = p.total_iters;
     streamk = p.streamk;
+    const int nclu = (int)gridDim.x / mc, clu = (int)blockIdx.x / mc;
     if (streamk) {
-      const int per = (p.work + (int)gridDim.x - 1) / (int)gridDim.x;
-      cursor = min(p.work, (int)blockIdx.x * per);
+      const int per = (p.work + nclu - 1) / nclu;
+      cursor = min(p.work, clu * per);
       end = min(p.work, cursor + per);
       stride = 0;
     } else {
-      cursor = blockIdx.x;
+      cursor = clu;
       end = p.tiles;
-      stride = gridDim.x;
+      stride = nclu;
     }
   }
   __device__ __forceinline__ bool next(int& tile, int& it_begin, int& it_end) {
@@ -114,9 +116,13 @@ struct Sched {
   }
 };
 
-template <int BN>
+// MC = 1: independent CTAs.  MC = 2: clusters of two CTAs work on vertically adjacent 128-row tiles of the same column block;
+// each loads its own A tile and HALF of the B tile, multicast into both CTAs' shared memory, which halves the B traffic from L2
+// (operand delivery, ~64 B/clk/SM, is what limits the 256-wide tiles).  A stage is reusable when BOTH CTAs' MMAs have retired.
+template <int BN, int MC>
 __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const __grid_constant__ KParams p) {
   using C = Cfg<BN>;
+  const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB[p.seg[0].b_idx])) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC);      // one tcgen05.commit arrival per CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
@@ -152,6 +158,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (MC > 1) cluster_sync_all();      // the peer's barriers are initialised before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(sgen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
@@ -161,13 +168,13 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
     int r = tile / p.mt;
     const int nt = r % p.nt;
     r /= p.nt;
-    m0 = mt * BM;
+    m0 = (mt * MC + crank) * BM;
     n0 = nt * BN;
     z2 = r % p.nz2;
     z3 = r / p.nz2;
   };
 
-  Sched sched(p);
+  Sched sched(p, MC);
   int tile, it_begin, it_end;
 
   if (warp == 0) {
@@ -211,11 +218,25 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_4d(sa + j * (BK * 128), ta, full_bar(s), m0 + sg.a_mn_shift + j * 64, ka, a2, a3);
           }
-          if (p.b_kmajor) {
-            tma_load_4d(sb, tb, full_bar(s), kbb, n0 + sg.b_mn_shift, b2, b3);
-          } else {
+          if (MC == 1) {
+            if (p.b_kmajor) {
+              tma_load_4d(sb, tb, full_bar(s), kbb, n0 + sg.b_mn_shift, b2, b3);
+            } else {
 #pragma unroll
-            for (int j = 0; j < C::BN_S / 64; ++j) tma_load_4d(sb + j * (BK * 128), tb, full_bar(s), n0 + sg.b_mn_shift + j * 64, kbb, b2, b3);
+              for (int j = 0; j < C::BN_S / 64; ++j) tma_load_4d(sb + j * (BK * 128), tb, full_bar(s), n0 + sg.b_mn_shift + j * 64, kbb, b2, b3);
+            }
+          } else {
+            // this CTA fetches its half of the B tile and multicasts it to both CTAs of the pair (tensor map box = BN / 2 rows)
+            constexpr int HB = BN / MC;
+            if (p.b_kmajor) {
+              tma_load_4d_mc(sb + crank * (HB * 128), tb, full_bar(s), kbb, n0 + sg.b_mn_shift + crank * HB, b2, b3, (uint16_t)((1 << MC) - 1));
+            } else {
+#pragma unroll
+              for (int j = 0; j < HB / 64; ++j) {
+                const int jj = crank * (HB / 64) + j;
+                tma_load_4d_mc(sb + jj * (BK * 128), tb, full_bar(s), n0 + sg.b_mn_shift + jj * 64, kbb, b2, b3, (uint16_t)((1 << MC) - 1));
+              }
+            }
           }
         }
         // advance (seg, rep, kb) and the ring position
@@ -257,7 +278,8 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_f16(dcol, ad + (uint64_t)(k * a_kstep), bd + (uint64_t)(k * b_kstep), idesc, (it > it_begin || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+          if (MC == 1) umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+          else umma_commit_mc(empty_bar(s), (uint16_t)((1 << MC) - 1));   // ... in both CTAs: the peer multicasts into this stage too
           if (it == it_end - 1) umma_commit(tmem_full_bar(acc));
         }
         __syncwarp();
@@ -453,6 +475,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (MC > 1) cluster_sync_all();      // do not leave while the peer can still multicast into / arrive on this CTA's shared memory
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
@@ -493,14 +516,30 @@ int encode_operand(CUtensorMap* tm, const pt_operand_t& op, int box_rows_kmajor,
   return PT_OK;
 }
 
-template <int BN>
+template <int BN, int MC>
 int launch(const KParams& kp, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    PT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    PT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_kernel<BN><<<grid, 192, Cfg<BN>::SMEM_BYTES, st>>>(kp);
+  if (MC == 1) {
+    gemm_kernel<BN, MC><<<grid, 192, Cfg<BN>::SMEM_BYTES, st>>>(kp);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(192, 1, 1);
+    cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = MC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, MC>, kp));
+  }
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
@@ -559,13 +598,14 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   const bool streamk = g->out_dtype == PT_OUT_F32_ATOMIC_ADD;
   PT_REQUIRE(!streamk || (g->bias == nullptr && g->bias_z2 == nullptr && g->residual == nullptr),
              "pt_gemm: PT_OUT_F32_ATOMIC_ADD outputs are scheduled stream-K and take no bias/residual");
-  int bn = g->block_n;
+  int bn = g->block_n & ~1;                 // bit 0 of block_n: 1 = do not form clusters (calibration runs)
+  const bool allow_cluster = (g->block_n & 1) == 0;
   const long long mt = (g->M + BM - 1) / BM;
   const long long zz = (long long)g->nz2 * g->nz3;
   const int sms = pt_num_sms();
   if (bn == 0) {
     const int cand[4] = {256, 128, 64, 160};
-    const double cyc[4] = {800.0, 430.0, 260.0, 640.0};
+    const double cyc[4] = {mt >= 2 && allow_cluster && !streamk ? 780.0 : 800.0, 430.0, 260.0, 640.0};   // paired 256-wide tiles share B (+1-3 %)
     double best = 1e300;
     for (int i = 0; i < 4; ++i) {
       const int c = cand[i];
@@ -586,6 +626,9 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   }
   PT_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "pt_gemm: block_n=%d", bn);
 
+  // clusters of two CTAs (TMA multicast of the B tile) for the 256-wide tiles whenever there are two row tiles to pair
+  // (measured: +1-3 % on the large data-parallel shapes, -4 % on stream-K ones, so only the former use it)
+  const int mc = (bn == 256 && mt >= 2 && allow_cluster && !streamk) ? 2 : 1;
   for (int i = 0; i < 2; ++i) {
     if (a_used[i]) {
       int r = encode_operand(&kp.tmA[i], g->a[i], BM, i ? "A1" : "A0");
@@ -593,7 +636,7 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
       kp.a_batched[i] = g->a[i].batched;
     }
     if (b_used[i]) {
-      int r = encode_operand(&kp.tmB[i], g->b[i], bn, i ? "B1" : "B0");
+      int r = encode_operand(&kp.tmB[i], g->b[i], bn / mc, i ? "B1" : "B0");
       if (r) return r;
       kp.b_batched[i] = g->b[i].batched;
     }
@@ -605,9 +648,10 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   kp.nz3 = g->nz3;
   kp.total_iters = (int)total;
   const long long nt = (g->N + bn - 1) / bn;
-  const long long tiles = mt * nt * zz;
+  const long long mtg = (mt + mc - 1) / mc;          // row-tile groups: one per cluster
+  const long long tiles = mtg * nt * zz;
   PT_REQUIRE(tiles * total < (1ll << 31), "pt_gemm: work space too large");
-  kp.mt = (int)mt;
+  kp.mt = (int)mtg;
   kp.nt = (int)nt;
   kp.tiles = (int)tiles;
   kp.work = (int)(tiles * total);
@@ -629,15 +673,15 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   PT_REQUIRE(kp.osn == 1 || g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: out_stride_n needs PT_OUT_F32_ATOMIC_ADD");
 
   // persistent grid: one CTA per SM for the wide tiles, two for the narrow ones (fewer when there is less work)
-  const long long slots = (long long)sms * (bn <= 128 ? 2 : 1);
+  const long long slots = (long long)sms * (bn <= 128 ? 2 : 1) / mc;     // clusters (or single CTAs) that can be resident
   long long G = streamk ? (kp.work / 4 > 0 ? kp.work / 4 : 1) : tiles;
   if (G > slots) G = slots;
-  dim3 grid((unsigned)G, 1, 1);
+  dim3 grid((unsigned)(G * mc), 1, 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 64: return launch<64>(kp, grid, st);
-    case 128: return launch<128>(kp, grid, st);
-    case 160: return launch<160>(kp, grid, st);
-    default: return launch<256>(kp, grid, st);
+    case 64: return launch<64, 1>(kp, grid, st);
+    case 128: return launch<128, 1>(kp, grid, st);
+    case 160: return launch<160, 1>(kp, grid, st);
+    default: return mc == 2 ? launch<256, 2>(kp, grid, st) : launch<256, 1>(kp, grid, st);
   }
 }
