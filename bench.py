@@ -247,6 +247,37 @@ def run_ours(args):
     ck = clocks.stop() if rank == 0 else None
     loss_val = float(loss_buf.item())
 
+    # The complete training step of train.py:100-120: the step above + clip_grad_norm_(1.0) + AdamW
+    # (two fused kernels over the flat buffers) + the bf16 re-pack of the updated weights, captured in one graph.
+    full_ms = None
+    if not args.no_full_step:
+        from prompt_tts_b200.optim import FusedClipAdamW
+        opt = FusedClipAdamW(stepper)
+        graph = None
+        for p in model.parameters():
+            p.grad = None
+        step()
+        opt.step()                          # builds the flat master buffer; parameters now alias it
+        torch.cuda.synchronize()
+        stepper.cache.epoch += 1            # stale packs at capture time => the re-pack kernels are part of the graph
+        full_graph = torch.cuda.CUDAGraph() if use_graph else None
+        if full_graph is not None:
+            with torch.cuda.graph(full_graph):
+                step()
+                opt.step()
+
+        def full_step():
+            if full_graph is not None:
+                full_graph.replay()
+            else:
+                step()
+                opt.step()
+        for _ in range(2):
+            full_step()
+        full_ms = timed(full_step, args.steps) / args.steps
+        full_loss = float(loss_buf.item())
+        full_graph = None
+
     if rank == 0:
         ms_step = ms / args.steps
         frames = BATCH * T_FRAMES * world
@@ -288,6 +319,10 @@ def run_ours(args):
                                        "bound": "MUFU (exp) + TMEM round trips, not the tensor pipe: see DESIGN.md section 3"},
                          "step_frac": (FLOP_PER_FRAME * BATCH * T_FRAMES / (ms_step / 1e3) / 1e12) / peak},
         }
+        if full_ms is not None:
+            line["train_step_full"] = {"ms_per_step": full_ms, "frames_per_s": frames / (full_ms / 1e3), "loss_after": full_loss,
+                                       "includes": "add_noise + fwd + MSE + bwd" + (" + NCCL gradient all-reduce" if world > 1 else "")
+                                                   + " + global-norm clip + AdamW (fused, flat buffers) + bf16 weight re-pack, one CUDA graph"}
         if world == 1 and not args.no_sampling:
             # secondary figure of BASELINE.json's metric (configs[3]): sampling real-time factor, denoiser only
             del graph
@@ -393,6 +428,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampling", action="store_true")
+    ap.add_argument("--no-full-step", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
