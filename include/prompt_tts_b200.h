@@ -49,6 +49,8 @@ int pt_version(void);
 const char* pt_last_error(void);
 /* 0 if device `dev` is sm_100 and the TMA driver entry point resolves */
 int pt_check_device(int dev);
+/* leave n SMs free of persistent (GEMM / attention) CTAs so that an overlapped collective can make progress (data-parallel runs) */
+int pt_set_sm_reserve(int n);
 /* cumulative number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long pt_launch_count(void);
 

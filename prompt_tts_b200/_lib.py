@@ -85,6 +85,7 @@ def call(name: str, *args) -> None:
 # ---------------------------------------------------------------------------------------------
 _SIGS = {
     "check_device": "i",
+    "set_sm_reserve": "i",
     "gemm": "pp",
     "attn_fwd": "pp",
     "attn_bwd": "pp",

@@ -6,6 +6,7 @@
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_pt_launches = 0;
+int g_pt_sm_reserve = 0;
 
 void pt_set_error(const char* fmt, ...) {
   va_list ap;
@@ -28,3 +29,12 @@ extern "C" int pt_check_device(int dev) {
 }
 
 extern "C" unsigned long long pt_launch_count(void) { return g_pt_launches; }
+
+// Persistent GEMM / attention grids claim every SM's shared memory; a concurrently running collective (NCCL's channel CTAs
+// during the overlapped gradient all-reduce) then cannot become resident and stalls until a kernel boundary.  Reserving a few
+// SMs keeps the exchange moving.  Takes effect for subsequent launches (CUDA-graph captures keep what they were captured with).
+extern "C" int pt_set_sm_reserve(int n) {
+  PT_REQUIRE(n >= 0 && n < 64, "pt_set_sm_reserve: n=%d", n);
+  g_pt_sm_reserve = n;
+  return PT_OK;
+}

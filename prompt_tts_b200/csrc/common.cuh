@@ -35,7 +35,8 @@ extern unsigned long long g_pt_launches;  // kernels launched by this library (a
     PT_CUDA_OK(cudaGetLastError());  \
   } while (0)
 
-static inline int pt_num_sms() {
+extern int g_pt_sm_reserve;  // SMs the persistent kernels leave free (api.cu: pt_set_sm_reserve)
+static inline int pt_num_sms_physical() {
   static int n = 0;
   if (!n) {
     int dev = 0;
@@ -44,6 +45,11 @@ static inline int pt_num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+// SM count the persistent grids (GEMM, attention) are sized for
+static inline int pt_num_sms() {
+  const int n = pt_num_sms_physical() - g_pt_sm_reserve;
+  return n > 1 ? n : 1;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
