@@ -97,7 +97,7 @@ typedef struct {
   int32_t M, N;            /* output tile space per (z2,z3) */
   int32_t nz2, nz3;        /* launch batch extents (grid.z = nz2*nz3*splitk) */
   int32_t splitk;          /* >1: contraction split over grid.z, requires PT_OUT_F32_ATOMIC_ADD */
-  int32_t block_n;         /* 0 = auto; else 64 / 128 / 160 / 256; bit 0 set (e.g. 257) = never pair CTAs into multicast clusters */
+  int32_t block_n;         /* 0 = auto; else 64 / 128 / 160 / 192 / 224 / 256; bit 0 set (e.g. 257) = never pair CTAs into multicast clusters */
   /* epilogue:  out = alpha * acc + bias[n] + bias_z2[z2, n] + residual[z2,z3,m,n] */
   void* out;
   int32_t out_dtype;

@@ -604,12 +604,14 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   const long long zz = (long long)g->nz2 * g->nz3;
   const int sms = pt_num_sms();
   if (bn == 0) {
-    const int cand[4] = {256, 128, 64, 160};
-    const double cyc[4] = {mt >= 2 && allow_cluster && !streamk ? 780.0 : 800.0, 430.0, 260.0, 640.0};   // paired 256-wide tiles share B (+1-3 %)
+    // 224 / 192 exist for wave quantisation: when a narrower tile keeps the number of waves, every wave gets shorter
+    const int cand[6] = {256, 224, 192, 128, 64, 160};
+    const double cyc[6] = {mt >= 2 && allow_cluster && !streamk ? 780.0 : 800.0, 730.0, 660.0, 430.0, 260.0, 640.0};
     double best = 1e300;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
       const int c = cand[i];
       if (c == 160 && !(g->N % 160 == 0 && g->N % 128 != 0 && g->N <= 640)) continue;   // only where it removes ragged waste
+      if ((c == 224 || c == 192) && streamk) continue;                                  // stream-K launches have no waves to quantise
       const long long tiles_c = mt * ((g->N + c - 1) / c) * zz;
       double cost;
       if (streamk) {
@@ -624,7 +626,7 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
       }
     }
   }
-  PT_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "pt_gemm: block_n=%d", bn);
+  PT_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 192 || bn == 224 || bn == 256, "pt_gemm: block_n=%d", bn);
 
   // clusters of two CTAs (TMA multicast of the B tile) for the 256-wide tiles whenever there are two row tiles to pair
   // (measured: +1-3 % on the large data-parallel shapes, -4 % on stream-K ones, so only the former use it)
@@ -682,6 +684,8 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
     case 64: return launch<64, 1>(kp, grid, st);
     case 128: return launch<128, 1>(kp, grid, st);
     case 160: return launch<160, 1>(kp, grid, st);
+    case 192: return launch<192, 1>(kp, grid, st);
+    case 224: return launch<224, 1>(kp, grid, st);
     default: return mc == 2 ? launch<256, 2>(kp, grid, st) : launch<256, 1>(kp, grid, st);
   }
 }

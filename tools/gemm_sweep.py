@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 seen = {}
 count = collections.Counter()
 orig = ops.gemm
-BNS = (0, 64, 128, 160, 256)
+BNS = (0, 64, 128, 160, 192, 224, 256, 257)
 
 def time_one(a, b, segs, M, N, out, kw):
     g = torch.cuda.CUDAGraph()
@@ -58,7 +58,7 @@ ops.gemm = orig
 tot_auto = sum(seen[k][0] * n for k, n in count.items())
 tot_best = sum(min(seen[k].values()) * n for k, n in count.items())
 print(f"auto {tot_auto/1e3:.2f} ms   per-shape best {tot_best/1e3:.2f} ms   ({len(seen)} shapes, {sum(count.values())} calls)")
-print("  n   auto    b64   b128   b160   b256  best  lost_us  (M, N, K, nz, nseg, a_kmajor, b_kmajor, out_mode, residual)")
+print("  n   auto    b64   b128   b160   b192   b224   b256 b256nc  best  lost_us  (M, N, K, nz, nseg, a_kmajor, b_kmajor, out_mode, residual)")
 rows = []
 for k, n in count.items():
     r = seen[k]
@@ -66,4 +66,4 @@ for k, n in count.items():
     rows.append(((r[0] - r[best]) * n, n, r, best, k))
 for lost, n, r, best, k in sorted(rows, key=lambda t: -t[1] * t[2][0])[:70]:
     fl = 2.0 * k[0] * k[1] * k[2] * k[3]
-    print(f"{n:3d} {r[0]:6.1f} {r[64]:6.1f} {r[128]:6.1f} {r[160]:6.1f} {r[256]:6.1f}  {best:4d} {lost:7.1f}  {fl/min(r.values())/1e6:5.0f}TF {k}")
+    print(f"{n:3d} {r[0]:6.1f} {r[64]:6.1f} {r[128]:6.1f} {r[160]:6.1f} {r[192]:6.1f} {r[224]:6.1f} {r[256]:6.1f} {r[257]:6.1f}  {best:4d} {lost:7.1f}  {fl/min(r.values())/1e6:5.0f}TF {k}")
