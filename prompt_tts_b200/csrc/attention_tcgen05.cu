@@ -2,7 +2,8 @@
 //
 // Replaces diffusers' AttnProcessor2_0 (F.scaled_dot_product_attention, no mask, no dropout) as the reference
 // uses it from tts/ldm/transformer_1d.py:258-265 and tts/models.py:95-100,117-119.  No [Lq, Lk] matrix ever
-// reaches HBM: logits live in TMEM, probabilities go registers -> shared memory -> tensor core.
+// reaches HBM: logits live in TMEM; probabilities (and dS) are written back into TMEM over the logits they came from and feed
+// the second MMA as its A operand from tensor memory -- they never touch shared memory either.
 //
 // One kernel template, three modes.  A CTA owns 128 "resident" rows and streams 64-row tiles of the other side:
 //
@@ -16,7 +17,7 @@
 // no accumulator rescaling), sweep 2 does the work.
 //
 // Warp roles (352 threads): warp 0 TMA producer, warp 1 stage-1 MMA issuer, warp 10 stage-2 MMA issuer, warps 2-5 and 6-9 two
-// transform groups that ping-pong over the streamed tiles (group g owns TMEM buffer X[g] and smem tile T[g]),
+// transform groups that ping-pong over the streamed tiles (group g owns TMEM buffer X[g]),
 // so the tensor core computes the logits of tile j+1 while the CUDA cores exponentiate tile j.
 // Every streamed tile is used twice from the same shared-memory bytes: K-major as the B operand of stage 1 and
 // MN-major as the B operand of stage 2 (only the UMMA descriptor differs).
@@ -57,15 +58,13 @@ struct ACfg {
   static constexpr int R_BYTES = BM * DP * 2;
   static constexpr int S_BYTES = BN * DP * 2;
   static constexpr int STAGE_BYTES = 2 * S_BYTES;
-  static constexpr int T_BYTES = BM * BN * 2;
-  static constexpr int FIXED = NX * R_BYTES + XBUF * NACC * T_BYTES;
+  static constexpr int FIXED = NX * R_BYTES;                 // the transformed tiles (P, dS) live in TMEM, over the logits they came from
   static constexpr int BUDGET = (MODE == MODE_DKV ? 205 : 221) * 1024;                  // of 227 KB: leaves room for alignment slack, barriers, statistics
   static constexpr int NSTAGE_FIT = (BUDGET - FIXED) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_FIT >= 8 ? 8 : NSTAGE_FIT;   // deep ring: bytes in flight must cover the TMA round trip
   static constexpr int LOOKAHEAD = XBUF == 2 ? (NSTAGE >= 3 ? 2 : (NSTAGE >= 2 ? 1 : 0)) : 0;   // stage-1 MMAs issued ahead of stage 2
   static constexpr int OFF_S = NX * R_BYTES;
-  static constexpr int OFF_T = OFF_S + NSTAGE * STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_T + XBUF * NACC * T_BYTES;
+  static constexpr int OFF_BAR = OFF_S + NSTAGE * STAGE_BYTES;
   static constexpr int OFF_STAT = OFF_BAR + 512;
   static constexpr int STAT_COLS = 2048;                     // DKV: query rows whose statistics fit in shared memory
   static constexpr int STAT_BYTES = (MODE == MODE_DKV ? 2 * STAT_COLS * 4 : 0) + 2 * BM * 4;   // DKV column stats [2][STAT_COLS] + row reduce [2][BM]
@@ -97,30 +96,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 
-// FWD sweep 2, 32 columns: P = exp2(x * c2 - mc) -> bf16 -> 4 swizzled 16-byte chunks of this thread's T row
+// FWD sweep 2, 32 columns: P = exp2(x * c2 - mc) -> bf16 pairs -> 16 TMEM columns of this thread's lane (A operand of stage 2)
 template <bool PARTIAL>
-__device__ __forceinline__ void fwd_chunk(const uint32_t* v, int c, int ncol, float c2, float mc, float& rsum, uint32_t tt, int rsw) {
-  float pv[32];
+__device__ __forceinline__ void fwd_chunk(const uint32_t* v, int c, int ncol, float c2, float mc, float& rsum, uint32_t tdst) {
+  uint32_t pk[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float e = ex2f(fmaf(__uint_as_float(v[i]), c2, -mc));
-    if (PARTIAL && c * 32 + i >= ncol) e = 0.f;
-    pv[i] = e;
-    rsum += e;
+  for (int i = 0; i < 32; i += 2) {
+    float e0 = ex2f(fmaf(__uint_as_float(v[i]), c2, -mc));
+    float e1 = ex2f(fmaf(__uint_as_float(v[i + 1]), c2, -mc));
+    if (PARTIAL && c * 32 + i >= ncol) e0 = 0.f;
+    if (PARTIAL && c * 32 + i + 1 >= ncol) e1 = 0.f;
+    rsum += e0 + e1;
+    pk[i >> 1] = pack2(e0, e1);
   }
-#pragma unroll
-  for (int u = 0; u < 4; ++u)
-    sts128(tt + (uint32_t)(((c * 4 + u) ^ rsw) << 4), pack2(pv[u * 8], pv[u * 8 + 1]), pack2(pv[u * 8 + 2], pv[u * 8 + 3]),
-           pack2(pv[u * 8 + 4], pv[u * 8 + 5]), pack2(pv[u * 8 + 6], pv[u * 8 + 7]));
+  tmem_st16(tdst + c * 16, pk);
 }
 
 template <int MODE, int DP>
@@ -130,19 +124,19 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t sR = sbase, sS = sbase + C::OFF_S, sT = sbase + C::OFF_T, bar0 = sbase + C::OFF_BAR;
+  const uint32_t sR = sbase, sS = sbase + C::OFF_S, bar0 = sbase + C::OFF_BAR;
   // barriers (every one of them is reused across work items with a running phase)
   const uint32_t r_full = bar0;
   auto s_full = [&](int s) { return bar0 + 8u * (1 + s); };
   auto s_empty = [&](int s) { return bar0 + 8u * (9 + s); };
   auto x_full = [&](int g, int slot) { return bar0 + 8u * (17 + g * 2 + slot); };
   auto x_empty = [&](int g, int slot) { return bar0 + 8u * (21 + g * 2 + slot); };
-  auto t_full = [&](int g) { return bar0 + 8u * (25 + g); };
-  auto t_empty = [&](int g) { return bar0 + 8u * (27 + g); };
-  const uint32_t acc_full = bar0 + 8u * 29;
-  const uint32_t acc_empty = bar0 + 8u * 30;
-  const uint32_t r_empty = bar0 + 8u * 31;
-  const uint32_t tmem_slot = bar0 + 8u * 32;
+  auto t_full = [&](int g) { return bar0 + 8u * (25 + g); };                       // P / dS of group g are in TMEM
+  auto p_empty = [&](int g, int slot) { return bar0 + 8u * (27 + g * 2 + slot); };  // stage 2 has consumed them: the X slot may be refilled
+  const uint32_t acc_full = bar0 + 8u * 31;
+  const uint32_t acc_empty = bar0 + 8u * 32;
+  const uint32_t r_empty = bar0 + 8u * 33;
+  const uint32_t tmem_slot = bar0 + 8u * 34;
   float* sstat = reinterpret_cast<float*>(sgen + C::OFF_STAT);          // DKV: [2][STAT_COLS] column statistics of the work item
   float* sred = sstat + (MODE == MODE_DKV ? 2 * C::STAT_COLS : 0);      // [2][BM]
 
@@ -174,9 +168,9 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       for (int u = 0; u < 2; ++u) {
         mbar_init(x_full(s, u), 1);
         mbar_init(x_empty(s, u), 128);
+        mbar_init(p_empty(s, u), 1);
       }
       mbar_init(t_full(s), 128);
-      mbar_init(t_empty(s), 1);
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 256);
@@ -189,12 +183,11 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 32);
+  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 34);
   // X buffers: FWD gives each group two 64-column slots (stage 1 runs a whole tile ahead of the group); the backward
   // modes need X1 | X2 per tile and have TMEM for one 128-column buffer per group only
   auto xcol = [&](int g, int slot_or_x) { return (uint32_t)(g * C::XW + slot_or_x * BN); };
   auto acccol = [&](int a) { return (uint32_t)(C::X_COLS + a * C::ACC_STRIDE); };
-  auto tT = [&](int g, int a) { return sT + (uint32_t)((g * NACC + a) * C::T_BYTES); };
   auto gsel = [&](int j) { return XBUF == 2 ? (j & 1) : 0; };
   // tiles of one sweep handled by group g
   const int per_g0 = XBUF == 2 ? (n_tiles + 1) >> 1 : n_tiles, per_g1 = XBUF == 2 ? n_tiles >> 1 : 0;
@@ -241,6 +234,22 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view
     int s1 = 0, ph1 = 0;   // ring position / parity of the next tile
     int kb0 = 0, kb1 = 0;  // X fills done by earlier work items, per group
+    // An X slot is released either by the transform threads (sweep-1 tile: the logits are in registers) or by the stage-2 commit
+    // (main tile: P / dS were written over the logits and have been consumed).  Per slot i = g*2+slot: what the last fill was
+    // (2 bits: 0 none, 1 sweep-1, 2 main) and the parity of the next phase of each of its two barriers.
+    uint32_t last_kind = 0, par_x = 0, par_p = 0;
+    auto wait_slot_free = [&](int g, int slot, uint32_t kind) {
+      const int i = g * 2 + slot;
+      const uint32_t prev = (last_kind >> (2 * i)) & 3u;
+      if (prev == 1u) {
+        mbar_wait(x_empty(g, slot), (par_x >> i) & 1u);
+        par_x ^= 1u << i;
+      } else if (prev == 2u) {
+        mbar_wait(p_empty(g, slot), (par_p >> i) & 1u);
+        par_p ^= 1u << i;
+      }
+      last_kind = (last_kind & ~(3u << (2 * i))) | (kind << (2 * i));
+    };
     int wi = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
       mbar_wait(r_full, wi & 1);
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
             const int slot = k & 1;
             const int half = sweep == 0 ? (j & 1) : 0;             // which K tile of the stage
             if (half == 0) mbar_wait(s_full(s1), ph1);
-            mbar_wait(x_empty(g, slot), ((k >> 1) & 1) ^ 1);
+            wait_slot_free(g, slot, sweep == 0 ? 1u : 2u);
             fence_after();
             if (leader) {
               const uint64_t b0 = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4) + half * (C::S_BYTES >> 4));
@@ -278,9 +287,8 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       } else {
         for (int j = 0; j < n_tiles; ++j) {
           const int g = gsel(j);
-          const int use = (g ? kb1 : kb0) + (XBUF == 2 ? (j >> 1) : j);
           mbar_wait(s_full(s1), ph1);
-          mbar_wait(x_empty(g, 0), (use & 1) ^ 1);
+          wait_slot_free(g, 0, 2u);
           fence_after();
           if (leader) {
             const uint64_t bS = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
@@ -306,13 +314,14 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       }
     }
   } else if (warp == 10) {
-    // ------------------------------------------------------------------ stage-2 MMA issuer: ACC += T[g] * S (MN-major view), frees the ring slot
+    // ------------------------------------------------------------------ stage-2 MMA issuer: ACC += P * S, A = P from TMEM (written by the
+    // transform over the logits), B = MN-major view of the streamed tile; frees the ring slot and the X slot
     const bool leader = elect_one();
     const uint32_t idesc2 = idesc_f16(0, 1, nd, BM);
     const uint64_t dSmn = umma_desc(sS, BN * 128, 1024);   // streamed tiles, MN-major view
-    const uint64_t dT = umma_desc(sT, 0, 1024);            // transformed tiles, K-major
     int s2 = 0;
-    int tu0 = 0, tu1 = 0;   // T fills done by earlier work items, per group
+    int tu0 = 0, tu1 = 0;   // t_full phases consumed so far, per group
+    int kf0 = 0, kf1 = 0;   // FWD: X fills of earlier work items, per group (slot = fill & 1)
     int wi = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
       if (MODE == MODE_FWD) s2 = (s2 + n_tiles1) % NSTAGE;   // sweep 1 used these ring stages (released by the stage-1 issuer)
@@ -321,6 +330,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       for (int j = 0; j < n_tiles; ++j) {
         const int g = gsel(j);
         const int use = (g ? tu1 : tu0) + (XBUF == 2 ? (j >> 1) : j);
+        const int slot = MODE == MODE_FWD ? (((g ? kf1 : kf0) + (g ? per_g1 : per_g0) + (j >> 1)) & 1) : 0;
         mbar_wait(t_full(g), use & 1);
         fence_after();
         if (leader) {
@@ -329,14 +339,15 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
           for (int a = 0; a < NACC; ++a) {
             // B operand: FWD -> V (S2); DQ -> K (S1); DKV: dV <- dO (S2), dK <- Q (S1)
             const int cs = MODE == MODE_FWD ? 1 : (MODE == MODE_DQ ? 0 : (a == 0 ? 1 : 0));
-            const uint64_t a0 = dT + (uint64_t)((g * NACC + a) * (C::T_BYTES >> 4));
+            // A operand in TMEM: FWD P in its X slot; DQ dS over X1; DKV P^T over X1 (-> dV), dS^T over X2 (-> dK)
+            const uint32_t acol = tmem + xcol(g, MODE == MODE_FWD ? slot : a);
             const uint64_t b0 = bS + (uint64_t)(cs * (C::S_BYTES >> 4));
             const uint32_t dcol = tmem + acccol(a);
 #pragma unroll
             for (int k = 0; k < BN / 16; ++k)
-              umma_f16(dcol, a0 + (uint64_t)(k * 2), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (j == 0 && k == 0) ? 0u : 1u);
+              umma_f16_ts(dcol, acol + (uint32_t)(k * 8), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (j == 0 && k == 0) ? 0u : 1u);
           }
-          umma_commit(t_empty(g));
+          umma_commit(p_empty(g, slot));
           umma_commit(s_empty(s2));
           if (j == n_tiles - 1) umma_commit(acc_full);
         }
@@ -345,6 +356,8 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       }
       tu0 += per_g0;
       tu1 += per_g1;
+      kf0 += 2 * per_g0;
+      kf1 += 2 * per_g1;
     }
   } else {
     // ------------------------------------------------------------------ transform groups (warps 2-5, 6-9)
@@ -356,9 +369,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     const bool active = XBUF == 2 || g == 0;      // with one X buffer only group 0 transforms (group 1 helps in the epilogue)
     const int jstep = XBUF == 2 ? 2 : 1;
     const float c2 = p.scale * 1.4426950408889634f;
-    const uint32_t trow = (uint32_t)(row * 128);
-    const int rsw = row & 7;
-    int kx = 0, kt = 0;   // running X / T use counts of this group (across work items)
+    int kx = 0;           // running X use count of this group (across work items)
     uint32_t v1[32], v2[32];
     int wi = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
@@ -397,26 +408,24 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
         const float mc = m * c2;
         // ---- sweep 2: P = exp(s - m) -> T[g] (bf16, K-major, SWIZZLE_128B) ; partial row sums
         float rsum = 0.f;
-        for (int j = g; j < n_tiles; j += 2, ++kx, ++kt) {
+        for (int j = g; j < n_tiles; j += 2, ++kx) {
           const int slot = kx & 1;
           mbar_wait(x_full(g, slot), (kx >> 1) & 1);
           fence_after();
           tmem_ld32(tl + xcol(g, slot), v1);
           tmem_ld32(tl + xcol(g, slot) + 32, v2);
           tmem_wait_ld();
-          fence_before();
-          mbar_arrive(x_empty(g, slot));
-          mbar_wait(t_empty(g), (kt & 1) ^ 1);
           const int ncol = min(BN, p.Ls - j * BN);
-          const uint32_t tt = tT(g, 0) + trow;
+          const uint32_t tdst = tl + xcol(g, slot);      // P overwrites the logits of this slot (32 of its 64 columns)
           if (ncol == BN) {
-            fwd_chunk<false>(v1, 0, ncol, c2, mc, rsum, tt, rsw);
-            fwd_chunk<false>(v2, 1, ncol, c2, mc, rsum, tt, rsw);
+            fwd_chunk<false>(v1, 0, ncol, c2, mc, rsum, tdst);
+            fwd_chunk<false>(v2, 1, ncol, c2, mc, rsum, tdst);
           } else {
-            fwd_chunk<true>(v1, 0, ncol, c2, mc, rsum, tt, rsw);
-            fwd_chunk<true>(v2, 1, ncol, c2, mc, rsum, tt, rsw);
+            fwd_chunk<true>(v1, 0, ncol, c2, mc, rsum, tdst);
+            fwd_chunk<true>(v2, 1, ncol, c2, mc, rsum, tdst);
           }
-          fence_async_smem();
+          tmem_wait_st();
+          fence_before();
           mbar_arrive(t_full(g));
         }
         sred[g * BM + row] = rsum;
@@ -471,23 +480,16 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
           asm volatile("bar.sync 2, 256;" ::: "memory");
         }
         if (active)
-          for (int j = g; j < n_tiles; j += jstep, ++kx, ++kt) {
+          for (int j = g; j < n_tiles; j += jstep, ++kx) {
             const float4* cst = reinterpret_cast<const float4*>(sstat + j * BN);
             const float4* cdl = reinterpret_cast<const float4*>(sstat + C::STAT_COLS + j * BN);
             mbar_wait(x_full(g, 0), kx & 1);
             fence_after();
-            const uint32_t tt0 = tT(g, 0) + trow;
-            const uint32_t tt1 = tT(g, NACC - 1) + trow;
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
               tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
               tmem_ld32(tl + xcol(g, 1) + c * 32, v2);
               tmem_wait_ld();
-              if (c == BN / 32 - 1) {
-                fence_before();
-                mbar_arrive(x_empty(g, 0));
-              }
-              if (c == 0) mbar_wait(t_empty(g), (kt & 1) ^ 1);
               uint32_t pp[16], dd[16];
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
@@ -509,14 +511,16 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
                 dd[i >> 1] = pack2(de[0], de[1]);
                 dd[(i >> 1) + 1] = pack2(de[2], de[3]);
               }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint32_t off = (uint32_t)(((c * 4 + u) ^ rsw) << 4);
-                if (MODE == MODE_DKV) sts128(tt0 + off, pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
-                sts128(tt1 + off, dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
+              // in place over the logits already consumed: DQ: dS over X1; DKV: P^T over X1, dS^T over X2 (16 columns per 32 logits)
+              if (MODE == MODE_DKV) {
+                tmem_st16(tl + xcol(g, 0) + c * 16, pp);
+                tmem_st16(tl + xcol(g, 1) + c * 16, dd);
+              } else {
+                tmem_st16(tl + xcol(g, 0) + c * 16, dd);
               }
             }
-            fence_async_smem();
+            tmem_wait_st();
+            fence_before();
             mbar_arrive(t_full(g));
           }
         // ---- epilogue: accumulators -> bf16 rows
