@@ -134,7 +134,7 @@ def run_reference(args):
             "data": "synthetic", "config": {"workload": f"{CFG} denoiser train step on host cores, batch 2 x {T_FRAMES} frames x 550 text tokens"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -338,7 +338,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_step_time(2, 1)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # Tear down without destroy_process_group(): with NCCL work captured in a live CUDA graph it can block forever.
         # Everything measured is already printed; leave through a barrier and a hard exit (exit code 0).
@@ -464,6 +464,24 @@ def gemm_profile(step, model, ops, torch):
     return fl, ms, afl, ams
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """stdout carries exactly one JSON line.  Native libraries (NCCL's version banner, for one) write to fd 1 directly, so fd 1 is
+    pointed at stderr for the whole run and the JSON line goes to a saved duplicate of the original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -476,6 +494,7 @@ def main():
     ap.add_argument("--no-full-step", action="store_true")
     ap.add_argument("--no-rvq", action="store_true")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
