@@ -164,7 +164,7 @@ def run_ours(args):
     grad_sync = None
     if world > 1:
         from prompt_tts_b200.dp import GradSync
-        grad_sync = GradSync(model, world_size=world)
+        grad_sync = GradSync(model, world_size=world, bucket_mb=float(os.environ.get("PT_BUCKET_MB", "128")))
     stepper = DenoiserTrainStep(model, grad_sync=grad_sync)
     inp = synth(cfg, BATCH, T_FRAMES, 1000 + rank, dev)
     host = {k: v.cpu().pin_memory() for k, v in inp.items()}

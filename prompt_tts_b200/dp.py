@@ -20,7 +20,7 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, model, world_size: Optional[int] = None, bucket_mb: float = 64.0, group=None):
+    def __init__(self, model, world_size: Optional[int] = None, bucket_mb: float = 128.0, group=None):
         self.group = group
         self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
