@@ -95,8 +95,8 @@ typedef struct {
   pt_segment_t seg[8];
   int32_t nseg;
   int32_t M, N;            /* output tile space per (z2,z3) */
-  int32_t nz2, nz3;        /* launch batch extents (grid.z = nz2*nz3*splitk) */
-  int32_t splitk;          /* >1: contraction split over grid.z, requires PT_OUT_F32_ATOMIC_ADD */
+  int32_t nz2, nz3;        /* batch extents of the output tile space */
+  int32_t splitk;          /* ignored (kept for ABI stability): PT_OUT_F32_ATOMIC_ADD outputs are scheduled stream-K by the library */
   int32_t block_n;         /* 0 = auto; else 64 / 128 / 160 / 192 / 224 / 256; bit 0 set (e.g. 257) = never pair CTAs into multicast clusters */
   /* epilogue:  out = alpha * acc + bias[n] + bias_z2[z2, n] + residual[z2,z3,m,n] */
   void* out;

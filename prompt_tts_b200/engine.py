@@ -136,16 +136,10 @@ def accum(v: Var, g: torch.Tensor, owned: bool = True) -> None:
         v.owned = True
 
 
-def _splitk(tiles: int, iters: int) -> int:
-    """Split the contraction so that the launch fills ~2 waves, keeping >= 8 k-iterations per split."""
-    want = max(1, (2 * _NUM_SMS) // max(1, tiles))
-    return max(1, min(want, iters // 8 if iters >= 16 else 1))
-
-
-def _wgrad_gemm(dy2d_op, x2d_op, seg, N: int, K: int, out: torch.Tensor, out_stride_m: int, iters: int) -> None:
-    tiles = ((N + 127) // 128) * ((K + 127) // 128)
-    ops.gemm([dy2d_op], [x2d_op], [seg], N, K, out, out_strides=(out_stride_m, 0, 0), out_mode=OUT_F32_ATOMIC_ADD,
-             splitk=_splitk(tiles, iters))
+def _wgrad_gemm(dy2d_op, x2d_op, seg, N: int, K: int, out: torch.Tensor, out_stride_m: int) -> None:
+    """dW[N, K] += dy^T x: fp32 atomic-accumulate output, scheduled stream-K by the library (the few-tile / long-K weight
+    gradients load every SM evenly whatever the tile count)."""
+    ops.gemm([dy2d_op], [x2d_op], [seg], N, K, out, out_strides=(out_stride_m, 0, 0), out_mode=OUT_F32_ATOMIC_ADD)
 
 
 # ------------------------------------------------------------------------------------------------ linear / 1x1 conv
@@ -175,7 +169,7 @@ def linear(tape: Tape, x: Var, wparams: Sequence[torch.Tensor], bias: Optional[S
         if bias is not None:
             ops.colsum(dy2, tape.pgrad_cat(bias) if len(bias) > 1 else tape.pgrad(bias[0]))
         gw = tape.pgrad_cat(wparams) if len(wparams) > 1 else tape.pgrad(wparams[0]).view(N, K)
-        _wgrad_gemm(ops.operand(dy2, False), ops.operand(x2, False), ops.segment(M), N, K, gw, K, (M + 63) // 64)
+        _wgrad_gemm(ops.operand(dy2, False), ops.operand(x2, False), ops.segment(M), N, K, gw, K)
         if x.needs_grad:
             dx = torch.empty_like(x2) if (x.grad is None or not x.owned) else x.grad.reshape(M, K)
             prev = x.grad.reshape(M, K) if x.grad is not None else None
