@@ -335,17 +335,62 @@ __global__ void text_embed_fwd_kernel(const int32_t* __restrict__ ids, const flo
     store8(y + r * D + v * 8, f);
   }
 }
-__global__ void text_embed_bwd_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ dy, float* __restrict__ dE, long long BL, int D) {
+// dE[v, :] += sum over positions p with ids[p] == v of dy[p, :].  The vocabulary is tiny (150 rows) and the padding id takes ~40 % of
+// the positions, so scattering with atomics serialises on a handful of addresses.  Instead: CTA (v, chunk) scans its chunk of the
+// ids, gathers the matching rows into registers (thread t owns 16-byte vectors t, t + blockDim, ...) and flushes once.
+constexpr int EMB_MAXV = 4;      // vectors per thread: D <= 8 * EMB_MAXV * 256
+__global__ void __launch_bounds__(256) text_embed_bwd_kernel(const int32_t* __restrict__ ids, const bf16* __restrict__ dy, float* __restrict__ dE,
+                                                             long long BL, int D, int per_chunk) {
+  const int v = blockIdx.x;
+  const long long p0 = (long long)blockIdx.y * per_chunk, p1 = min(BL, p0 + per_chunk);
   const int nv = D >> 3;
-  const long long total = BL * nv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / nv;
-    const int v = (int)(i % nv);
-    float f[8];
-    load8(dy + r * D + v * 8, f);
-    float* d = dE + (long long)ids[r] * D + v * 8;
+  float acc[EMB_MAXV][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(d + j, f[j]);
+  for (int k = 0; k < EMB_MAXV; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  __shared__ int hits[256];
+  __shared__ int nhit;
+  bool any = false;
+  for (long long base = p0; base < p1; base += blockDim.x) {
+    if (threadIdx.x == 0) nhit = 0;
+    __syncthreads();
+    const long long pp = base + threadIdx.x;
+    if (pp < p1 && ids[pp] == v) hits[atomicAdd(&nhit, 1)] = (int)(pp - base);   // order within a batch of 256 positions does not matter
+    __syncthreads();
+    const int n = nhit;
+    for (int hh = 0; hh < n; hh += 4) {       // four independent row gathers in flight
+      const bf16* row[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) row[u] = dy + (base + hits[min(hh + u, n - 1)]) * D;
+#pragma unroll
+      for (int k = 0; k < EMB_MAXV; ++k) {
+        const int vec = threadIdx.x + k * blockDim.x;
+        if (vec < nv) {
+          float f[4][8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) load8(row[u] + vec * 8, f[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (hh + u < n) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[k][j] += f[u][j];
+            }
+        }
+      }
+    }
+    any |= n > 0;
+    __syncthreads();
+  }
+  if (!any) return;
+#pragma unroll
+  for (int k = 0; k < EMB_MAXV; ++k) {
+    const int vec = threadIdx.x + k * blockDim.x;
+    if (vec < nv) {
+      float* d = dE + (long long)v * D + vec * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(d + j, acc[k][j]);
+    }
   }
 }
 
@@ -570,7 +615,13 @@ extern "C" int pt_text_embed_fwd(const int32_t* ids, const float* E, const float
 }
 extern "C" int pt_text_embed_bwd(const int32_t* ids, const void* dy, float* dE, int B, int L, int D, int V, void* stream) {
   PT_REQUIRE(B > 0 && L > 0 && D % 8 == 0 && V > 0, "text_embed_bwd: D=%d", D);
-  text_embed_bwd_kernel<<<grid_for((long long)B * L * (D / 8), 256), 256, 0, ST>>>(ids, (const bf16*)dy, dE, (long long)B * L, D);
+  PT_REQUIRE(D <= 8 * EMB_MAXV * 256 && V <= 65535, "text_embed_bwd: D=%d V=%d", D, V);
+  const long long BL = (long long)B * L;
+  int chunks = (int)((BL + 511) / 512);              // ~512 positions per CTA: the padding id's rows are spread over many CTAs
+  if (chunks > 256) chunks = 256;
+  const int per_chunk = (int)((BL + chunks - 1) / chunks);
+  const int threads = (D / 8) >= 256 ? 256 : (((D / 8) + 31) / 32 * 32);
+  text_embed_bwd_kernel<<<dim3(V, chunks), threads, 0, ST>>>(ids, (const bf16*)dy, dE, BL, D, per_chunk);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
