@@ -1,0 +1,80 @@
+"""GPU: pt_gemm (persistent tcgen05 GEMM family) against fp32 torch contractions, through the C ABI.
+
+The case list is tools/gemm_probe.py's: every operand majorness (NT / NN / TN / TT), ragged M / N / K, every tile width,
+Conv1d k=3 forward (bias + time shift + residual epilogue), its data gradient and weight gradient (stream-K atomic
+accumulate), the batched head-strided contractions -- plus the paths added later: cluster multicast on / off must agree,
+and the three conv taps of a weight gradient in ONE launch (tap = z2) must equal three launches."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import ROOT, rel
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+pytestmark = pytest.mark.gpu
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def test_probe_cases_match_fp32(cuda):
+    import gemm_probe
+    cs = gemm_probe.cases()
+    worst = {}
+    for name, fn in cs.items():
+        e = fn()
+        worst[name] = e
+        tol = 1e-5 if ("f32" in name or name.startswith("tn_") or "conv3_dw" in name or "attn_qk" in name) else 4e-3
+        assert e < tol, (name, e)
+    assert len(worst) >= 25
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 960), (1000, 1280, 320), (257, 256, 64)])
+def test_cluster_multicast_agrees_with_single_cta(cuda, M, N, K):
+    """block_n = 256 pairs CTAs into clusters that share the B tile by TMA multicast; 257 forbids it.  Odd numbers of row tiles
+    leave the second CTA of the last pair with a fully out-of-bounds tile."""
+    from prompt_tts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A, B = bf(torch.randn(M, K, device=cuda, generator=g)), bf(torch.randn(N, K, device=cuda, generator=g))
+    outs = []
+    for bn in (256, 257):
+        o = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
+        ops.gemm([ops.operand(A, True)], [ops.operand(B, True)], [ops.segment(K)], M, N, o, block_n=bn)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    assert rel(outs[0], A.float() @ B.float().t()) < 4e-3
+
+
+@pytest.mark.parametrize("bn", [64, 128, 160, 192, 224, 256])
+def test_every_tile_width(cuda, bn):
+    from prompt_tts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(bn)
+    M, N, K = 520, 960, 200          # ragged in M (4.06 tiles), N for every width, and K (3.125 k-blocks)
+    A, B = bf(torch.randn(M, K, device=cuda, generator=g)), bf(torch.randn(K, N, device=cuda, generator=g))
+    bias = torch.randn(N, device=cuda, generator=g)
+    res = bf(torch.randn(M, N, device=cuda, generator=g))
+    o = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
+    ops.gemm([ops.operand(A, True)], [ops.operand(B, False)], [ops.segment(K)], M, N, o, bias=bias, residual=res, block_n=bn)
+    torch.cuda.synchronize()
+    assert rel(o, A.float() @ B.float() + bias + res.float()) < 4e-3
+
+
+def test_conv_weight_gradient_three_taps_one_launch(cuda):
+    from prompt_tts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Bn, L, Ci, Co = 3, 94, 64, 128
+    dy, x = bf(torch.randn(Bn, L, Co, device=cuda, generator=g)), bf(torch.randn(Bn, L, Ci, device=cuda, generator=g))
+    dw = torch.zeros(Co, Ci, 3, device=cuda)
+    seg = ops.segment(L, b_k0=-1, b_k0_z2=1, nrep=Bn, rep_is_batch=True)
+    ops.gemm([ops.operand(dy, False, batched=True)], [ops.operand(x, False, batched=True)], [seg], Co, Ci, dw.view(Co, Ci * 3),
+             out_strides=(3 * Ci, 1, 0), nz2=3, out_mode=ops.OUT_F32_ATOMIC_ADD, out_stride_n=3)
+    torch.cuda.synchronize()
+    xx = x.float().transpose(1, 2).requires_grad_(True)
+    w = torch.zeros(Co, Ci, 3, device=cuda, requires_grad=True)
+    F.conv1d(xx, w, padding=1).backward(dy.float().transpose(1, 2))
+    assert rel(dw, w.grad) < 1e-5
