@@ -52,6 +52,21 @@ def test_product_fails_loudly_without_gpu():
         m(x, 3, torch.zeros(1, 24, dtype=torch.int32), None)
 
 
+def test_sampler_and_optimizer_fail_loudly():
+    from prompt_tts_b200 import _lib
+    from prompt_tts_b200.models import TTSSingleSpeaker
+    from prompt_tts_b200.optim import FusedClipAdamW
+    from prompt_tts_b200.sample import DDPMSampler
+    from prompt_tts_b200.train import DenoiserTrainStep
+    m = TTSSingleSpeaker(load_cfg("tiny"))
+    with pytest.raises(_lib.PtError):                      # CPU tensors: there is no CPU fallback
+        DDPMSampler(m, n_infer=2).sample(torch.zeros(1, 24, dtype=torch.int32), 16)
+    with pytest.raises(_lib.PtError):                      # the flat gradient layout is defined by the first train step
+        FusedClipAdamW(DenoiserTrainStep(m)).step()
+    smp = DDPMSampler(m, n_infer=100)
+    assert smp.timesteps[0] == 990 and smp.timesteps[-1] == 0 and len(smp.timesteps) == 100     # set_timesteps(100) over 1000
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "prompt_tts_b200")
     for dp, _, files in os.walk(pkg):
