@@ -119,10 +119,10 @@ int pt_groupnorm_stats(const void* x, float* stats, int B, int L, int C, int G, 
 /* y = act(gn(x) * gamma + beta); act: 0 none, 1 SiLU */
 int pt_groupnorm_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
                        int B, int L, int C, int G, int act, void* stream);
-/* backward of apply+stats: dx bf16; dgamma/dbeta fp32 [C] are ACCUMULATED (atomic add).
- * scratch: fp32 [B, G, 2], zero-filled by the callee. */
+/* backward of apply+stats: dx bf16 (+ dx_add if not NULL: fused accumulation of the gradient that reached x through another
+ * branch; dx may alias dx_add); dgamma/dbeta fp32 [C] are ACCUMULATED (atomic add).  scratch: fp32 [B, G, 2], zero-filled by the callee. */
 int pt_groupnorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,
-                     void* dx, float* dgamma, float* dbeta, float* scratch,
+                     const void* dx_add, void* dx, float* dgamma, float* dbeta, float* scratch,
                      int B, int L, int C, int G, int act, void* stream);
 
 /* LayerNorm over rows x[M, C] bf16, eps; rowstats[M,2] = (mean, rstd) */

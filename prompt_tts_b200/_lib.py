@@ -91,7 +91,7 @@ _SIGS = {
     "attn_bwd": "pp",
     "groupnorm_stats": "ppiiiifp",
     "groupnorm_apply": "pppppiiiiip",
-    "groupnorm_bwd": "pppppppppiiiiip",
+    "groupnorm_bwd": "ppppppppppiiiiip",
     "layernorm_fwd": "ppppplifp",
     "layernorm_bwd": "pppppppplip",
     "softmax_fwd": "pplillp",

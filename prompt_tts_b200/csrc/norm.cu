@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(320) gn_bwd_reduce_kernel(const bf16* __restri
 // backward pass 2: dx = rstd * (dz*gamma - s1/n - xhat * s2/n)  =  dz * a1 + x * c2 + c3   (per-channel coefficients in registers)
 __global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ scratch, bf16* __restrict__ dx, int L, int C, int G,
-                                                           int rows_per_cta, int act) {
+                                                           const float* __restrict__ scratch, const bf16* __restrict__ dx_add, bf16* dx, int L,
+                                                           int C, int G, int rows_per_cta, int act) {
   const GnMap m = gn_map(C);
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(L, r0 + rows_per_cta);
@@ -277,6 +277,12 @@ __global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restric
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       body(fx[u], fd[u]);
+      if (dx_add) {   // fused accumulation of the gradient that reached x through the other branch (dx may alias dx_add)
+        float t[8];
+        load8(dx_add + base + (long long)(r + u * m.rpp) * C, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fd[u][j] += t[j];
+      }
       store8(dx + base + (long long)(r + u * m.rpp) * C, fd[u]);
     }
   }
@@ -285,6 +291,12 @@ __global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restric
     load8(x + base + (long long)r * C, fx);
     load8(dy + base + (long long)r * C, fd);
     body(fx, fd);
+    if (dx_add) {
+      float t[8];
+      load8(dx_add + base + (long long)r * C, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fd[j] += t[j];
+    }
     store8(dx + base + (long long)r * C, fd);
   }
 }
@@ -487,8 +499,8 @@ extern "C" int pt_groupnorm_apply(const void* x, const float* stats, const float
   return PT_OK;
 }
 
-extern "C" int pt_groupnorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, void* dx,
-                                float* dgamma, float* dbeta, float* scratch, int B, int L, int C, int G, int act, void* stream) {
+extern "C" int pt_groupnorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, const void* dx_add,
+                                void* dx, float* dgamma, float* dbeta, float* scratch, int B, int L, int C, int G, int act, void* stream) {
   PT_REQUIRE(B > 0 && L > 0 && G > 0 && C % G == 0, "groupnorm_bwd: B=%d L=%d C=%d G=%d", B, L, C, G);
   GnGeom g;
   if (int r = gn_geom(B, L, C, &g)) return r;
@@ -497,8 +509,8 @@ extern "C" int pt_groupnorm_bwd(const void* dy, const void* x, const float* stat
   gn_bwd_reduce_kernel<<<dim3(g.chunks_red, B), g.threads, g.threads * 16 * sizeof(float), st>>>(
       (const bf16*)dy, (const bf16*)x, stats, gamma, beta, dgamma, dbeta, scratch, L, C, G, g.rows_red, act);
   PT_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<<<dim3(g.chunks_apply, B), g.threads, 0, st>>>((const bf16*)dy, (const bf16*)x, stats, gamma, beta, scratch, (bf16*)dx, L,
-                                                                     C, G, g.rows_apply, act);
+  gn_bwd_apply_kernel<<<dim3(g.chunks_apply, B), g.threads, 0, st>>>((const bf16*)dy, (const bf16*)x, stats, gamma, beta, scratch,
+                                                                     (const bf16*)dx_add, (bf16*)dx, L, C, G, g.rows_apply, act);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }

@@ -270,8 +270,14 @@ def groupnorm(tape: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor, eps: 
     def bwd():
         if y.grad is None:
             return
-        dx = ops.groupnorm_bwd(y.grad, x.data, stats, gamma.detach(), beta.detach(), tape.pgrad(gamma), tape.pgrad(beta), groups, act)
-        accum(x, dx, owned=True)
+        if not x.needs_grad:
+            ops.groupnorm_bwd(y.grad, x.data, stats, gamma.detach(), beta.detach(), tape.pgrad(gamma), tape.pgrad(beta), groups, act)
+            return
+        # the residual branch usually reached x first: fold that gradient into this pass instead of a separate add kernel
+        prev = x.grad
+        dx = ops.groupnorm_bwd(y.grad, x.data, stats, gamma.detach(), beta.detach(), tape.pgrad(gamma), tape.pgrad(beta), groups, act,
+                               dx_add=prev, out=prev if (prev is not None and x.owned) else None)
+        x.grad, x.owned = dx, True
 
     tape.record(bwd)
     return y

@@ -117,11 +117,12 @@ def groupnorm_apply(x, stats, gamma, beta, G: int, act: bool) -> torch.Tensor:
     return y
 
 
-def groupnorm_bwd(dy, x, stats, gamma, beta, dgamma, dbeta, G: int, act: bool) -> torch.Tensor:
+def groupnorm_bwd(dy, x, stats, gamma, beta, dgamma, dbeta, G: int, act: bool, dx_add=None, out=None) -> torch.Tensor:
+    """dx (+ dx_add: the gradient that already reached x through another branch, fused into the same pass; `out` may be dx_add)."""
     B, L, Cc = x.shape
-    dx = torch.empty_like(x)
+    dx = torch.empty_like(x) if out is None else out
     scratch = torch.empty(B, G, 2, dtype=F32, device=x.device)
-    call("groupnorm_bwd", _p(dy), _p(x), _p(stats), _p(gamma), _p(beta), _p(dx), _p(dgamma), _p(dbeta), _p(scratch),
+    call("groupnorm_bwd", _p(dy), _p(x), _p(stats), _p(gamma), _p(beta), _p(dx_add), _p(dx), _p(dgamma), _p(dbeta), _p(scratch),
          B, L, Cc, G, 1 if act else 0, _stream())
     return dx
 

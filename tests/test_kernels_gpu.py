@@ -40,6 +40,12 @@ def test_groupnorm_fwd_bwd(cuda, B, L, C, act):
     dx = ops.groupnorm_bwd(dy, x, stats, gamma, beta, dgam, dbet, 32, act)
     assert rel(dx.float().transpose(1, 2), xr.grad) < 8e-3
     assert rel(dgam, gr.grad) < 2e-3 and rel(dbet, br.grad) < 2e-3
+    # fused accumulation of a gradient that reached x through another branch, in place
+    prev = bf(torch.randn(B, L, C, device=cuda, generator=g))
+    acc = prev.clone()
+    out = ops.groupnorm_bwd(dy, x, stats, gamma, beta, torch.zeros_like(dgam), torch.zeros_like(dbet), 32, act, dx_add=acc, out=acc)
+    assert out.data_ptr() == acc.data_ptr()
+    assert rel(acc.float().transpose(1, 2), xr.grad + prev.float().transpose(1, 2)) < 8e-3
 
 
 @pytest.mark.parametrize("M,C", [(100, 64), (4099, 320), (777, 768), (513, 1280)])
