@@ -539,9 +539,11 @@ extern "C" int pt_layernorm_bwd(const void* dy, const void* x, const float* rows
   PT_REQUIRE(M > 0 && C % 8 == 0 && C / 8 <= 32 * LN_MAXV, "layernorm_bwd: M=%lld C=%d", (long long)M, C);
   const int wpb = 8;
   long long blocks = (M + wpb - 1) / wpb;
-  const long long cap = 2ll * pt_num_sms();
-  if (blocks > cap) blocks = cap;
   const int nv = (C / 8 + 31) / 32;
+  // every CTA ends with a 2C-value flush (shared-memory fold + global atomics): wide rows get one CTA per SM so that a warp
+  // sees enough rows to amortise it, narrow rows two (measured: 1 / 2 / 4 per SM at C = 768 -> 65 / 44 / 48 us)
+  const long long cap = (nv >= 4 ? 1ll : 2ll) * pt_num_sms();
+  if (blocks > cap) blocks = cap;
   const size_t smem = (size_t)wpb * 2 * C * sizeof(float);
 #define LN_BWD(NV_)                                                                                                            \
   case NV_: {                                                                                                                  \
