@@ -51,10 +51,13 @@ class DDPMSampler:
     @torch.no_grad()
     def sample(self, ids: torch.Tensor, T: int, x_T: Optional[torch.Tensor] = None, noises: Optional[torch.Tensor] = None,
                prompt: Optional[torch.Tensor] = None, prompt_noise: Optional[torch.Tensor] = None, seed: int = 0,
-               return_codes: bool = False) -> torch.Tensor:
+               return_codes: bool = False, prompt_tokens: Optional[torch.Tensor] = None) -> torch.Tensor:
         """ids int32 [B, Lt]; returns x_0 fp32 [B, C, T] (or int64 codes in [0, 1023] with return_codes).
         x_T / noises[n_infer, B, C, T] / prompt_noise may be given for reproducibility against an oracle; otherwise they are
-        drawn from a generator seeded with `seed`.  prompt fp32 [B, C, P]: clean prompt frames in-painted at every step."""
+        drawn from a generator seeded with `seed`.  prompt fp32 [B, C, P]: clean prompt frames in-painted at every step.
+        prompt_tokens float [B, P, cross_attention_dim] (optional, default off): a speech-prompt encoding appended to the text
+        encoding as extra cross-attention tokens -- `Unet1DConditionModel.forward` takes `encoder_hidden_states` of any length
+        (unet_1d_condition.py:557); with None the conditioning is exactly the reference's."""
         if not ids.is_cuda:
             raise ops._lib.PtError("DDPMSampler: inputs must be CUDA tensors; there is no CPU fallback")
         dev = ids.device
@@ -65,6 +68,10 @@ class DDPMSampler:
         # text encoder once; K/V of every cross-attention layer are filled in by the first denoiser call and then reused
         tape = E.Tape(self.cache, recording=False)
         self._enc = self.model.text_encoder._fwd(tape, ids.to(torch.int32).contiguous())
+        if prompt_tokens is not None:
+            if prompt_tokens.shape[0] != B or prompt_tokens.shape[2] != self._enc.data.shape[2]:
+                raise ops._lib.PtError(f"prompt_tokens must be [B, P, {self._enc.data.shape[2]}], got {tuple(prompt_tokens.shape)}")
+            self._enc = E.Var(torch.cat([self._enc.data, ops.cast_bf16(prompt_tokens.float().contiguous())], dim=1), needs_grad=False)
         self._kv: Dict[int, E.Var] = {}
         self._static = {"x": x, "t": torch.zeros(B, dtype=torch.int64, device=dev), "eps": torch.empty_like(x)}
         self._graph = None

@@ -73,3 +73,33 @@ def test_sampler_prompt_inpainting_and_codes(cuda):
     ref = torch.clamp(torch.round((x + 1) * 511.5), 0, 1023).to(torch.int64)
     assert torch.equal(codes, ref)
     assert torch.equal(codes[..., :P], torch.round((prompt + 1) * 511.5).to(torch.int64))     # prompt codes round-trip exactly
+
+
+def test_sampler_prompt_tokens_extend_the_cross_attention_context(cuda):
+    """Optional speech-prompt tokens appended to the text encoding (SURVEY 8 row N2 hook, default off): the run with tokens equals
+    the oracle loop whose encoder_hidden_states is [text encoding | tokens], and differs from the run without them."""
+    import ref_model
+    from prompt_tts_b200.models import TTSSingleSpeaker
+    from prompt_tts_b200.sample import DDPMSampler
+    cfg = load_cfg("tiny")
+    torch.manual_seed(0)
+    model = TTSSingleSpeaker(cfg).to(cuda).eval()
+    B, T, n_infer, P = 2, 16, 3, 9
+    inp = synth_inputs(cfg, B, T, seed=8, device=cuda)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x_T = torch.randn(B, cfg["in_channels"], T, device=cuda, generator=g)
+    noises = torch.randn(n_infer, B, cfg["in_channels"], T, device=cuda, generator=g)
+    toks = torch.randn(B, P, cfg["cross_attention_dim"], device=cuda, generator=g)
+    smp = DDPMSampler(model, n_infer=n_infer)
+    with_t = smp.sample(inp["ids"], T, x_T=x_T, noises=noises, prompt_tokens=toks)
+    without = smp.sample(inp["ids"], T, x_T=x_T, noises=noises)
+    assert rel(with_t, without) > 1e-3
+    sd = {k: v.detach().float() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        enc = torch.cat([ref_model.text_encoder(sd, cfg, inp["ids"]), toks], dim=1)
+        x = x_T.clone()
+        stride = 1000 // n_infer
+        for i, t in enumerate([k * stride for k in range(n_infer)][::-1]):
+            eps = ref_model.unet(sd, cfg, x, torch.full((B,), t, device=cuda, dtype=torch.int64), enc)
+            x = ref_model.ddpm_step(eps, t, x, noises[i], acp=ref_model.ddpm_alphas_cumprod().to(cuda), n_infer=n_infer)
+    assert rel(with_t, x) < 4e-2
