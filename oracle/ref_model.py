@@ -228,6 +228,21 @@ def codes_to_x0(codes_int):
     return (codes_int.float() / 1023 - 0.5) / 0.5
 
 
+def collate(codes_list, cmu_sequences, max_seq_length):
+    """TTS_SingleSpkr_Collate_Fn.__call__ (tts/dataloader.py:145-188) + SingleSpeakerDataset's `code = npy / 1023` (:64,77) on
+    plain arrays: returns (code fp32 [B, 8, T], cmu_sequence_id int32 [B, max_len], attention_mask int32 [B, max_len])."""
+    import numpy as np
+    code = torch.FloatTensor(np.array([np.asarray(c) / 1023 for c in codes_list]))
+    code = (code - 0.5) / 0.5                                   # torchvision Normalize([0.5], [0.5])
+    ids = torch.zeros(len(cmu_sequences), max_seq_length, dtype=torch.int64).tolist()
+    mask = torch.zeros(len(cmu_sequences), max_seq_length, dtype=torch.int64).tolist()
+    for i, ex in enumerate(cmu_sequences):                      # _collate_batch_helpler, dataloader.py:123-137 (pad token 0)
+        k = min(len(ex), max_seq_length)
+        ids[i][:k] = list(ex[:k])
+        mask[i][:k] = [1] * k
+    return code, torch.IntTensor(ids), torch.IntTensor(mask)
+
+
 # ----------------------------------------------------------------------------------------------
 # parameter table: reference-format names and shapes, built without the reference
 # ----------------------------------------------------------------------------------------------
