@@ -13,8 +13,9 @@
 //   DKV   K, V              Q, dO             X1 = K Q^T,  X2 = V dO^T      P^T, dS^T                    dV += P^T dO ; dK += dS^T Q
 //
 // with P = exp(X1*s - lse) in the backward modes (lse saved by FWD, D = rowsum(dO * O) from a small pre-pass).
-// FWD makes two sweeps over the streamed side: sweep 1 only takes the row maximum of the logits (exact softmax,
-// no accumulator rescaling), sweep 2 does the work.
+// FWD is a single-sweep online softmax: each transform group keeps its own running row maximum, row sum and accumulator; the
+// reference maximum only moves when a row's maximum grows by more than 2^8 (then that group's accumulator is rescaled in TMEM,
+// which is rare), and the two groups are merged exactly in the epilogue.
 //
 // Warp roles (352 threads): warp 0 TMA producer, warp 1 stage-1 MMA issuer, warp 10 stage-2 MMA issuer, warps 2-5 and 6-9 two
 // transform groups that ping-pong over the streamed tiles (group g owns TMEM buffer X[g]),
@@ -50,7 +51,9 @@ struct alignas(64) AParams {
 template <int MODE, int DP>
 struct ACfg {
   static constexpr int NX = MODE == MODE_FWD ? 1 : 2;       // stage-1 products per tile
-  static constexpr int NACC = MODE == MODE_DKV ? 2 : 1;     // stage-2 accumulators
+  static constexpr int NACC = MODE == MODE_DKV ? 2 : 1;     // stage-2 accumulators written per tile
+  static constexpr int NACC_T = MODE == MODE_FWD ? 2 : NACC; // accumulators held in TMEM (FWD: one per transform group, merged in the epilogue)
+  static constexpr int XSLOTS = MODE == MODE_FWD ? (DP > 128 ? 1 : 2) : 1;   // FWD: X slots per group (TMEM permitting), so stage 1 runs a tile ahead
   // one X buffer / one transform group: DKV at DP = 192 for TMEM (2*128 + 2*192 > 512); DQ at DP = 192 so that shared memory
   // holds two ring stages (a single stage serialises the TMA round trip with every tile)
   static constexpr int XBUF = (MODE != MODE_FWD && DP > 128) ? 1 : 2;
@@ -67,12 +70,12 @@ struct ACfg {
   static constexpr int OFF_BAR = OFF_S + NSTAGE * STAGE_BYTES;
   static constexpr int OFF_STAT = OFF_BAR + 512;
   static constexpr int STAT_COLS = 2048;                     // DKV: query rows whose statistics fit in shared memory
-  static constexpr int STAT_BYTES = (MODE == MODE_DKV ? 2 * STAT_COLS * 4 : 0) + 2 * BM * 4;   // DKV column stats [2][STAT_COLS] + row reduce [2][BM]
+  static constexpr int STAT_BYTES = (MODE == MODE_DKV ? 2 * STAT_COLS * 4 : 0) + 4 * BM * 4;   // DKV column stats [2][STAT_COLS] + row reduce [2][BM]
   static constexpr int SMEM_BYTES = 1024 + OFF_STAT + STAT_BYTES;
   static constexpr int XW = 128;                             // TMEM columns per X buffer (two 64-column products)
-  static constexpr int X_COLS = XBUF * XW;
+  static constexpr int X_COLS = MODE == MODE_FWD ? 2 * XSLOTS * BN : XBUF * XW;
   static constexpr int ACC_STRIDE = DP;
-  static constexpr int TMEM_USED = X_COLS + NACC * ACC_STRIDE;
+  static constexpr int TMEM_USED = X_COLS + NACC_T * ACC_STRIDE;
   static constexpr int TMEM_COLS = TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512));
   static_assert(NSTAGE >= 1, "smem budget");
   static_assert(TMEM_USED <= 512, "TMEM budget");
@@ -101,7 +104,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// FWD sweep 2, 32 columns: P = exp2(x * c2 - mc) -> bf16 pairs -> 16 TMEM columns of this thread's lane (A operand of stage 2)
+// FWD, 32 columns: P = exp2(x * c2 - mc) -> bf16 pairs -> 16 TMEM columns of this thread's lane (A operand of stage 2)
 template <bool PARTIAL>
 __device__ __forceinline__ void fwd_chunk(const uint32_t* v, int c, int ncol, float c2, float mc, float& rsum, uint32_t tdst) {
   uint32_t pk[16];
@@ -120,7 +123,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t* v, int c, int ncol, fl
 template <int MODE, int DP>
 __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AParams p) {
   using C = ACfg<MODE, DP>;
-  constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE;
+  constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE, XSLOTS = C::XSLOTS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -142,7 +145,6 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.Ls + BN - 1) / BN;
-  const int n_tiles1 = (n_tiles + 1) >> 1;    // FWD sweep 1: ring stages (two K tiles each)
   const int ks1 = (p.D + 15) >> 4;            // stage-1 k-steps (head dim, zero padded to a multiple of 16)
   const int nd = ks1 << 4;                    // stage-2 N
   // persistent CTA: work item w -> (resident row block, head, batch), row block fastest (neighbouring CTAs share K/V in L2)
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 34);
   // X buffers: FWD gives each group two 64-column slots (stage 1 runs a whole tile ahead of the group); the backward
   // modes need X1 | X2 per tile and have TMEM for one 128-column buffer per group only
-  auto xcol = [&](int g, int slot_or_x) { return (uint32_t)(g * C::XW + slot_or_x * BN); };
+  auto xcol = [&](int g, int slot_or_x) { return (uint32_t)(MODE == MODE_FWD ? (g * XSLOTS + slot_or_x) * BN : g * C::XW + slot_or_x * BN); };
   auto acccol = [&](int a) { return (uint32_t)(C::X_COLS + a * C::ACC_STRIDE); };
   auto gsel = [&](int j) { return XBUF == 2 ? (j & 1) : 0; };
   // tiles of one sweep handled by group g
@@ -220,8 +222,6 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
         }
         if (++s == NSTAGE) s = 0, ph ^= 1;
       };
-      if (MODE == MODE_FWD)   // sweep 1: both slots of a stage hold consecutive 64-row tiles of K
-        for (int j = 0; j < n_tiles1; ++j) load_tile(&p.tmS[0], &p.tmS[0], 2 * j * BN, (2 * j + 1) * BN);
       for (int j = 0; j < n_tiles; ++j) load_tile(&p.tmS[0], &p.tmS[1], j * BN, j * BN);
     }
   } else if (warp == 1) {
@@ -234,9 +234,9 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view
     int s1 = 0, ph1 = 0;   // ring position / parity of the next tile
     int kb0 = 0, kb1 = 0;  // X fills done by earlier work items, per group
-    // An X slot is released either by the transform threads (sweep-1 tile: the logits are in registers) or by the stage-2 commit
-    // (main tile: P / dS were written over the logits and have been consumed).  Per slot i = g*2+slot: what the last fill was
-    // (2 bits: 0 none, 1 sweep-1, 2 main) and the parity of the next phase of each of its two barriers.
+    // An X slot is released by the stage-2 commit (P / dS were written over the logits and have been consumed); the x_empty path
+    // (release by the transform threads) is kept for tiles whose logits are only read.  Per slot i = g*2+slot: what the last fill was
+    // (2 bits: 0 none, 1 read-only, 2 main) and the parity of the next phase of each of its two barriers.
     uint32_t last_kind = 0, par_x = 0, par_p = 0;
     auto wait_slot_free = [&](int g, int slot, uint32_t kind) {
       const int i = g * 2 + slot;
@@ -254,36 +254,30 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
       mbar_wait(r_full, wi & 1);
       if (MODE == MODE_FWD) {
-        // tile t (64 streamed rows) of either sweep goes to group t & 1; that group's k-th tile overall uses slot k & 1.
-        // Sweep 1 (row maxima) reads only K: a ring stage holds two consecutive K tiles; sweep 2 stages hold (K, V).
-        for (int sweep = 0; sweep < 2; ++sweep) {
-          for (int j = 0; j < n_tiles; ++j) {
-            const int g = j & 1;
-            const int k = (g ? kb1 : kb0) + (sweep ? (g ? per_g1 : per_g0) : 0) + (j >> 1);
-            const int slot = k & 1;
-            const int half = sweep == 0 ? (j & 1) : 0;             // which K tile of the stage
-            if (half == 0) mbar_wait(s_full(s1), ph1);
-            wait_slot_free(g, slot, sweep == 0 ? 1u : 2u);
-            fence_after();
-            if (leader) {
-              const uint64_t b0 = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4) + half * (C::S_BYTES >> 4));
-              const uint32_t dcol = tmem + xcol(g, slot);
+        // tile j (64 streamed rows) goes to group j & 1; that group's k-th tile overall uses X slot k % XSLOTS
+        for (int j = 0; j < n_tiles; ++j) {
+          const int g = j & 1;
+          const int k = (g ? kb1 : kb0) + (j >> 1);
+          const int slot = XSLOTS == 2 ? (k & 1) : 0;
+          mbar_wait(s_full(s1), ph1);
+          wait_slot_free(g, slot, 2u);
+          fence_after();
+          if (leader) {
+            const uint64_t b0 = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
+            const uint32_t dcol = tmem + xcol(g, slot);
 #pragma unroll
-              for (int kk = 0; kk < DP / 16; ++kk)
-                if (kk < ks1)
-                  umma_f16(dcol, dR + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2),
-                           b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2), idesc1, kk > 0 ? 1u : 0u);
-              umma_commit(x_full(g, slot));
-              if (sweep == 0 && (half == 1 || j == n_tiles - 1)) umma_commit(s_empty(s1));
-              if (sweep == 1 && j == n_tiles - 1) umma_commit(r_empty);
-            }
-            __syncwarp();
-            if (sweep == 1 || half == 1 || j == n_tiles - 1)
-              if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
+            for (int kk = 0; kk < DP / 16; ++kk)
+              if (kk < ks1)
+                umma_f16(dcol, dR + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2),
+                         b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2), idesc1, kk > 0 ? 1u : 0u);
+            umma_commit(x_full(g, slot));
+            if (j == n_tiles - 1) umma_commit(r_empty);
           }
+          __syncwarp();
+          if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
         }
-        kb0 += 2 * per_g0;
-        kb1 += 2 * per_g1;
+        kb0 += per_g0;
+        kb1 += per_g1;
       } else {
         for (int j = 0; j < n_tiles; ++j) {
           const int g = gsel(j);
@@ -324,13 +318,12 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     int kf0 = 0, kf1 = 0;   // FWD: X fills of earlier work items, per group (slot = fill & 1)
     int wi = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
-      if (MODE == MODE_FWD) s2 = (s2 + n_tiles1) % NSTAGE;   // sweep 1 used these ring stages (released by the stage-1 issuer)
       mbar_wait(acc_empty, (wi & 1) ^ 1);                    // the epilogue of the previous work item has drained the accumulators
       fence_after();
       for (int j = 0; j < n_tiles; ++j) {
         const int g = gsel(j);
         const int use = (g ? tu1 : tu0) + (XBUF == 2 ? (j >> 1) : j);
-        const int slot = MODE == MODE_FWD ? (((g ? kf1 : kf0) + (g ? per_g1 : per_g0) + (j >> 1)) & 1) : 0;
+        const int slot = (MODE == MODE_FWD && XSLOTS == 2) ? (((g ? kf1 : kf0) + (j >> 1)) & 1) : 0;
         mbar_wait(t_full(g), use & 1);
         fence_after();
         if (leader) {
@@ -342,10 +335,11 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
             // A operand in TMEM: FWD P in its X slot; DQ dS over X1; DKV P^T over X1 (-> dV), dS^T over X2 (-> dK)
             const uint32_t acol = tmem + xcol(g, MODE == MODE_FWD ? slot : a);
             const uint64_t b0 = bS + (uint64_t)(cs * (C::S_BYTES >> 4));
-            const uint32_t dcol = tmem + acccol(a);
+            const uint32_t dcol = tmem + acccol(MODE == MODE_FWD ? g : a);     // FWD: each group accumulates into its own O
+            const bool first = MODE == MODE_FWD ? j < 2 : j == 0;
 #pragma unroll
             for (int k = 0; k < BN / 16; ++k)
-              umma_f16_ts(dcol, acol + (uint32_t)(k * 8), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (j == 0 && k == 0) ? 0u : 1u);
+              umma_f16_ts(dcol, acol + (uint32_t)(k * 8), b0 + (uint64_t)(k * (2048 >> 4)), idesc2, (first && k == 0) ? 0u : 1u);
           }
           umma_commit(p_empty(g, slot));
           umma_commit(s_empty(s2));
@@ -356,8 +350,8 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       }
       tu0 += per_g0;
       tu1 += per_g1;
-      kf0 += 2 * per_g0;
-      kf1 += 2 * per_g1;
+      kf0 += per_g0;
+      kf1 += per_g1;
     }
   } else {
     // ------------------------------------------------------------------ transform groups (warps 2-5, 6-9)
@@ -378,83 +372,106 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       const int r = r0 + row;
 
       if (MODE == MODE_FWD) {
-        // ---- sweep 1: exact row maximum of the raw logits.  This group's k-th tile (of both sweeps, all work items) sits in X slot k & 1.
-        float m = -INFINITY;
-        for (int j = g; j < n_tiles; j += 2, ++kx) {
-          const int slot = kx & 1;
-          mbar_wait(x_full(g, slot), (kx >> 1) & 1);
+        // ---- online softmax: this group keeps its own running maximum m (raw logit units), row sum l and accumulator O_g.
+        // The reference point m only moves when a row's maximum grows by more than 2^8 (then O_g and l are rescaled), so
+        // p = exp2((x - m) c) <= 256 and the rescale is rare; the two groups are merged exactly in the epilogue.
+        float m = -INFINITY, l = 0.f;
+        int kw = 0;                                      // tiles of this group in this work item so far
+        for (int j = g; j < n_tiles; j += 2, ++kx, ++kw) {
+          const int slot = XSLOTS == 2 ? (kx & 1) : 0;
+          mbar_wait(x_full(g, slot), (XSLOTS == 2 ? (kx >> 1) : kx) & 1);
           fence_after();
           tmem_ld32(tl + xcol(g, slot), v1);
           tmem_ld32(tl + xcol(g, slot) + 32, v2);
           tmem_wait_ld();
-          fence_before();
-          mbar_arrive(x_empty(g, slot));
           const int ncol = min(BN, p.Ls - j * BN);
+          float mt = -INFINITY;
           if (ncol == BN) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
+            for (int i = 0; i < 32; ++i) mt = fmaxf(mt, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              if (i < ncol) m = fmaxf(m, __uint_as_float(v1[i]));
-              if (32 + i < ncol) m = fmaxf(m, __uint_as_float(v2[i]));
+              if (i < ncol) mt = fmaxf(mt, __uint_as_float(v1[i]));
+              if (32 + i < ncol) mt = fmaxf(mt, __uint_as_float(v2[i]));
             }
           }
-        }
-        sred[g * BM + row] = m;
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        m = fmaxf(sred[row], sred[BM + row]);
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        const float mc = m * c2;
-        // ---- sweep 2: P = exp(s - m) -> T[g] (bf16, K-major, SWIZZLE_128B) ; partial row sums
-        float rsum = 0.f;
-        for (int j = g; j < n_tiles; j += 2, ++kx) {
-          const int slot = kx & 1;
-          mbar_wait(x_full(g, slot), (kx >> 1) & 1);
-          fence_after();
-          tmem_ld32(tl + xcol(g, slot), v1);
-          tmem_ld32(tl + xcol(g, slot) + 32, v2);
-          tmem_wait_ld();
-          const int ncol = min(BN, p.Ls - j * BN);
+          const float m_new = fmaxf(m, mt);
+          if (kw == 0) {
+            m = m_new;                                   // nothing accumulated yet (stage 2 of this tile overwrites O_g)
+          } else {
+            const bool grow = (m_new - m) * c2 > 8.f;
+            if (__any_sync(0xffffffffu, grow)) {         // warp-collective: tcgen05.ld / st need the whole warp
+              const float alpha = grow ? ex2f((m - m_new) * c2) : 1.f;
+              if (grow) m = m_new;
+              l *= alpha;
+              // stage 2 of this group's previous tile must have retired before O_g is touched
+              const int kp = kx - 1;
+              mbar_wait(p_empty(g, XSLOTS == 2 ? (kp & 1) : 0), (XSLOTS == 2 ? (kp >> 1) : kp) & 1);
+              fence_after();
+              for (int cc = 0; cc * 16 < p.D; ++cc) {
+                uint32_t t[16];
+                tmem_ld16(tl + acccol(g) + cc * 16, t);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+                tmem_st16(tl + acccol(g) + cc * 16, t);
+              }
+              tmem_wait_st();
+            }
+          }
+          const float mc = m * c2;
           const uint32_t tdst = tl + xcol(g, slot);      // P overwrites the logits of this slot (32 of its 64 columns)
           if (ncol == BN) {
-            fwd_chunk<false>(v1, 0, ncol, c2, mc, rsum, tdst);
-            fwd_chunk<false>(v2, 1, ncol, c2, mc, rsum, tdst);
+            fwd_chunk<false>(v1, 0, ncol, c2, mc, l, tdst);
+            fwd_chunk<false>(v2, 1, ncol, c2, mc, l, tdst);
           } else {
-            fwd_chunk<true>(v1, 0, ncol, c2, mc, rsum, tdst);
-            fwd_chunk<true>(v2, 1, ncol, c2, mc, rsum, tdst);
+            fwd_chunk<true>(v1, 0, ncol, c2, mc, l, tdst);
+            fwd_chunk<true>(v2, 1, ncol, c2, mc, l, tdst);
           }
           tmem_wait_st();
           fence_before();
           mbar_arrive(t_full(g));
         }
-        sred[g * BM + row] = rsum;
+        // ---- merge the two groups: M = max(m_0, m_1), w_g = exp2((m_g - M) c), L = sum w_g l_g, O = sum w_g O_g / L
+        sred[(g * BM + row) * 2] = m;
+        sred[(g * BM + row) * 2 + 1] = l;
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        rsum = sred[row] + sred[BM + row];
-        // ---- epilogue: O = ACC / rowsum ; lse = m * scale + ln(rowsum)
+        const float m0 = sred[row * 2], l0 = sred[row * 2 + 1], m1 = sred[(BM + row) * 2], l1 = sred[(BM + row) * 2 + 1];
+        const float mm = fmaxf(m0, m1);
+        const float w0 = ex2f((m0 - mm) * c2), w1 = n_tiles > 1 ? ex2f((m1 - mm) * c2) : 0.f;    // a group without tiles has m = -inf, l = 0
+        const float lsum = w0 * l0 + w1 * l1;
         mbar_wait(acc_full, wi & 1);
         fence_after();
-        const float inv = 1.f / rsum;
+        const float f0 = w0 / lsum, f1 = w1 / lsum;
         bf16* orow = p.out0 + (long long)b * p.o_bs + (long long)r * p.o_rs + (long long)h * p.D;
         for (int cc = g; cc * 16 < p.D; cc += 2) {
           tmem_ld16(tl + acccol(0) + cc * 16, v1);
+          if (n_tiles > 1) tmem_ld16(tl + acccol(1) + cc * 16, v2);
           tmem_wait_ld();
           if (r < p.Lr) {
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(v1[i]) * f0;
+            if (n_tiles > 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = fmaf(__uint_as_float(v2[i]), f1, o[i]);
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u)
               if (cc * 16 + u * 8 < p.D) {
                 uint4 wv;
-                wv.x = pack2(__uint_as_float(v1[u * 8]) * inv, __uint_as_float(v1[u * 8 + 1]) * inv);
-                wv.y = pack2(__uint_as_float(v1[u * 8 + 2]) * inv, __uint_as_float(v1[u * 8 + 3]) * inv);
-                wv.z = pack2(__uint_as_float(v1[u * 8 + 4]) * inv, __uint_as_float(v1[u * 8 + 5]) * inv);
-                wv.w = pack2(__uint_as_float(v1[u * 8 + 6]) * inv, __uint_as_float(v1[u * 8 + 7]) * inv);
+                wv.x = pack2(o[u * 8], o[u * 8 + 1]);
+                wv.y = pack2(o[u * 8 + 2], o[u * 8 + 3]);
+                wv.z = pack2(o[u * 8 + 4], o[u * 8 + 5]);
+                wv.w = pack2(o[u * 8 + 6], o[u * 8 + 7]);
                 *reinterpret_cast<uint4*>(orow + cc * 16 + u * 8) = wv;
               }
           }
         }
         fence_before();
         mbar_arrive(acc_empty);
-        if (g == 0 && r < p.Lr) p.lse[((long long)b * p.H + h) * p.Lr + r] = m * p.scale + __logf(rsum);
+        if (g == 0 && r < p.Lr) p.lse[((long long)b * p.H + h) * p.Lr + r] = mm * p.scale + __logf(lsum);
         asm volatile("bar.sync 2, 256;" ::: "memory");   // sred is rewritten by the next work item
       } else {
         // ---- backward modes
