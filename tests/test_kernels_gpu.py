@@ -137,6 +137,39 @@ def test_fused_attention_fwd_bwd(cuda, B, H, Lq, Lk, d, fused):
     assert torch.isfinite(o.float()).all() and torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all() and torch.isfinite(dv.float()).all()
 
 
+@pytest.mark.parametrize("Lq,Lk,d", [(200, 330, 40), (130, 752, 64), (94, 550, 160)])
+def test_fused_attention_rescale_path(cuda, Lq, Lk, d):
+    """The forward is an online softmax that rescales a group's accumulator only when a row maximum grows by more than 2^8.  Random
+    logits never do that, so force it: key norms ramp up along the sequence (every later 64-key tile raises the maximum by far more
+    than the threshold, for both transform groups) and a few rows get the opposite sign (their maximum sits in the FIRST tile)."""
+    from prompt_tts_b200 import ops
+    g = gen(21)
+    B, H = 2, 4
+    C = H * d
+    scale = d ** -0.5
+    q = bf(torch.randn(B, Lq, C, device=cuda, generator=g))
+    ramp = torch.linspace(0.05, 6.0, Lk, device=cuda)[None, :, None]
+    kv = torch.randn(B, Lk, 2 * C, device=cuda, generator=g)
+    kv[:, :, :C] = q[:, :1, :].float().sign() * kv[:, :, :C].abs() * ramp      # aligned with row 0 of q: logits grow with the key index
+    kv = bf(kv)
+    q = q.clone()
+    q[:, 1::7] = -q[:, 1::7].abs() * q[:, :1, :].sign()                          # some rows see decreasing logits instead
+    k, v = kv[:, :, :C], kv[:, :, C:]
+    o = torch.full((B, Lq, C), float("nan"), device=cuda, dtype=torch.bfloat16)
+    lse = torch.full((B, H, Lq), float("nan"), device=cuda)
+    ops.attn_fwd(q, k, v, o, lse, H, d, scale)
+    qh = q.float().view(B, Lq, H, d).transpose(1, 2)
+    kh = k.float().view(B, Lk, H, d).transpose(1, 2)
+    vh = v.float().view(B, Lk, H, d).transpose(1, 2)
+    sc = (qh @ kh.transpose(-1, -2)) * scale
+    spread = (sc.max(-1).values - sc[..., :64].max(-1).values).max().item()
+    assert spread * 1.4427 > 8 * 3, f"the test must cross the rescale threshold several times (spread {spread})"
+    ref = (torch.softmax(sc, -1) @ vh).transpose(1, 2).reshape(B, Lq, C)
+    assert torch.isfinite(o.float()).all()
+    assert rel(o, ref) < 4e-3, rel(o, ref)
+    assert rel(lse, torch.logsumexp(sc, -1)) < 1e-5
+
+
 def test_fused_attention_properties_full_size(cuda):
     """Size-independent properties at the bench shape (32 x 8 heads x 752 x 752, d = 40), where a dense reference would
     need 2.3 GB per [B, H, Lq, Lk] matrix: rows of softmax sum to one (V = 1 -> O = 1), O is linear in V, and permuting the
