@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpt_b200.so")
+LIB_PATH = os.environ.get("PT_B200_LIB") or os.path.join(_HERE, "libpt_b200.so")   # the override is for A/B runs of two builds
 
 
 class Operand(C.Structure):

@@ -76,6 +76,28 @@ __device__ __forceinline__ void load8(const bf16* p, float* f) {
     f[2 * i + 1] = t.y;
   }
 }
+// the same in two steps: issue the 16-byte load now (4 registers), convert when the value is needed -- lets a thread keep many
+// loads in flight without holding 8 fp32 registers per vector
+__device__ __forceinline__ bf16x8 load8raw(const bf16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+__device__ __forceinline__ void unpack8(const bf16x8& r, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(r.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+// same values, but the compiler cannot see that (the words pass through a volatile mov): a kernel that converts the same raw
+// vector in several phases re-converts it each time instead of keeping the 8 fp32 results alive in registers across phases
+__device__ __forceinline__ void unpack8_again(const bf16x8& r, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t w;
+    asm volatile("mov.b32 %0, %1;" : "=r"(w) : "r"(*reinterpret_cast<const uint32_t*>(&r.v[i])));
+    f[2 * i] = __uint_as_float(w << 16);
+    f[2 * i + 1] = __uint_as_float(w & 0xffff0000u);
+  }
+}
 __device__ __forceinline__ void store8(bf16* p, const float* f) {
   bf16x8 r;
 #pragma unroll

@@ -31,23 +31,52 @@ __device__ __forceinline__ GnMap gn_map(int C) {
   return m;
 }
 
-// per-channel (a, b) with  gn(x) * gamma + beta = x * a + b  for this thread's 8 channels
+// per-channel (a, b) with  gn(x) * gamma + beta = x * a + b  for this thread's 8 channels.
+// fast (host-checked: gamma/beta 16-byte aligned, C/G >= 8 so the 8 channels span at most two groups): six vector loads
+// instead of 32 scalar ones -- this prologue is on the critical path of every CTA.
+template <bool FAST>
 __device__ __forceinline__ void gn_coeffs(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta, int b,
                                           int c0, int cpg, int G, float* a1, float* b1, float* rs, float* ms) {
+  float gm[8], bt[8], mean[8], rstd[8];
+  if constexpr (FAST) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), e1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const int ga = c0 / cpg, gb = (c0 + 7) / cpg;
+    const float2 sa = __ldg(reinterpret_cast<const float2*>(stats) + (long long)b * G + ga);
+    const float2 sb = __ldg(reinterpret_cast<const float2*>(stats) + (long long)b * G + gb);
+    const int nb = (ga + 1) * cpg - c0;   // channels of this vector that belong to the first group
+    gm[0] = g0.x, gm[1] = g0.y, gm[2] = g0.z, gm[3] = g0.w, gm[4] = g1.x, gm[5] = g1.y, gm[6] = g1.z, gm[7] = g1.w;
+    bt[0] = e0.x, bt[1] = e0.y, bt[2] = e0.z, bt[3] = e0.w, bt[4] = e1.x, bt[5] = e1.y, bt[6] = e1.z, bt[7] = e1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = j < nb ? sa.x : sb.x;
+      rstd[j] = j < nb ? sa.y : sb.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      mean[j] = stats[((long long)b * G + g) * 2];
+      rstd[j] = stats[((long long)b * G + g) * 2 + 1];
+      gm[j] = gamma[c0 + j];
+      bt[j] = beta[c0 + j];
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cpg;
-    const float mean = stats[((long long)b * G + g) * 2], rstd = stats[((long long)b * G + g) * 2 + 1];
-    const float gm = gamma[c0 + j];
-    a1[j] = rstd * gm;
-    b1[j] = beta[c0 + j] - mean * rstd * gm;
+    a1[j] = rstd[j] * gm[j];
+    b1[j] = bt[j] - mean[j] * rstd[j] * gm[j];
     if (rs) {
-      rs[j] = rstd;
-      ms[j] = -mean * rstd;
+      rs[j] = rstd[j];
+      ms[j] = -mean[j] * rstd[j];
     }
   }
 }
 
+// All four kernels stream rows in batches of U per thread: the 16-byte loads of a batch are issued back to back as raw bf16
+// (4 registers each, converted when consumed) and the per-channel coefficients are fetched after the first batch is already in
+// flight; several CTAs per SM cover each other's round trips.  A whole tensor here is only 100-600 KB per SM, i.e. a few memory round
+// trips: what matters is that every round trip carries as many bytes as possible and that nothing serialises in front of it.
 __global__ void __launch_bounds__(320) gn_stats_kernel(const bf16* __restrict__ x, float* __restrict__ sums, int L, int C, int G, int rows_per_cta) {
   extern __shared__ float sh[];  // [threads][16] partials, reused as [C][2]
   const GnMap m = gn_map(C);
@@ -118,45 +147,51 @@ __global__ void gn_finalize_kernel(float* __restrict__ stats, int n, float inv_c
   }
 }
 
-// y = act(x * a[c] + b[c]) with a = rstd*gamma, b = beta - mean*a
+// y = act(x * a[c] + b[c]) with a = rstd*gamma, b = beta - mean*a.  Rows are streamed in batches of U per thread: the 16-byte
+// loads of a batch are issued back to back as raw bf16 (4 registers each, converted when consumed) and the per-channel
+// coefficients are fetched after the first batch is already in flight -- a tensor here is only 100-600 KB per SM, a few memory
+// round trips, so what matters is that each round trip carries many bytes and nothing serialises in front of it (9.2 vs 12.3 us
+// at 32 x 752 x 320).  The same restructuring made the three reducing kernels slower (their flush dominates) and was not kept.
+template <int U, bool FAST>
 __global__ void __launch_bounds__(320) gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, bf16* __restrict__ y, int L, int C, int G, int rows_per_cta,
                                                        int act) {
   const GnMap m = gn_map(C);
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(L, r0 + rows_per_cta);
-  float a1[8], b1[8];
-  gn_coeffs(stats, gamma, beta, b, m.v * 8, C / G, G, a1, b1, nullptr, nullptr);
   const long long base = ((long long)b * L) * C + m.v * 8;
+  const int step = U * m.rpp;
   int r = r0 + m.rsub;
-  for (; r + 3 * m.rpp < r1; r += 4 * m.rpp) {
-    float f[4][8];
+  bf16x8 cur[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load8(x + base + (long long)(r + u * m.rpp) * C, f[u]);
+  for (int u = 0; u < U; ++u)
+    if (r + u * m.rpp < r1) cur[u] = load8raw(x + base + (long long)(r + u * m.rpp) * C);
+  float a1[8], b1[8];
+  gn_coeffs<FAST>(stats, gamma, beta, b, m.v * 8, C / G, G, a1, b1, nullptr, nullptr);
+  while (r < r1) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
+      if (r + u * m.rpp < r1) {
+        float f[8];
+        unpack8(cur[u], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(f[u][j], a1[j], b1[j]);
-        f[u][j] = act ? z * sigmoid_fast(z) : z;
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(f[j], a1[j], b1[j]);
+          f[j] = act ? z * sigmoid_fast(z) : z;
+        }
+        store8(y + base + (long long)(r + u * m.rpp) * C, f);
       }
-      store8(y + base + (long long)(r + u * m.rpp) * C, f[u]);
     }
-  }
-  for (; r < r1; r += m.rpp) {
-    float f[8];
-    load8(x + base + (long long)r * C, f);
+    r += step;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(f[j], a1[j], b1[j]);
-      f[j] = act ? z * sigmoid_fast(z) : z;
-    }
-    store8(y + base + (long long)r * C, f);
+    for (int u = 0; u < U; ++u)
+      if (r + u * m.rpp < r1) cur[u] = load8raw(x + base + (long long)(r + u * m.rpp) * C);
   }
 }
 
 // backward pass 1: per-channel sum(dz), sum(dz*xhat) -> dgamma/dbeta (global atomics) and
 // per-(b,g) s1 = sum(dz*gamma), s2 = sum(dz*gamma*xhat) -> scratch.
+template <bool FAST>
 __global__ void __launch_bounds__(320) gn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ scratch,
@@ -167,7 +202,7 @@ __global__ void __launch_bounds__(320) gn_bwd_reduce_kernel(const bf16* __restri
   const int r0 = blockIdx.x * rows_per_cta, r1 = min(L, r0 + rows_per_cta);
   const int cpg = C / G;
   float a1[8], b1[8], rs[8], ms[8], sdz[8], sdzx[8];
-  gn_coeffs(stats, gamma, beta, b, m.v * 8, cpg, G, a1, b1, rs, ms);
+  gn_coeffs<FAST>(stats, gamma, beta, b, m.v * 8, cpg, G, a1, b1, rs, ms);
 #pragma unroll
   for (int j = 0; j < 8; ++j) sdz[j] = sdzx[j] = 0.f;
   const long long base = ((long long)b * L) * C + m.v * 8;
@@ -232,6 +267,7 @@ __global__ void __launch_bounds__(320) gn_bwd_reduce_kernel(const bf16* __restri
 }
 
 // backward pass 2: dx = rstd * (dz*gamma - s1/n - xhat * s2/n)  =  dz * a1 + x * c2 + c3   (per-channel coefficients in registers)
+template <bool FAST>
 __global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ scratch, const bf16* __restrict__ dx_add, bf16* dx, int L,
@@ -244,7 +280,7 @@ __global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restric
   float a1[8], b1[8], c2[8], c3[8];
   {
     float rs[8], ms[8];
-    gn_coeffs(stats, gamma, beta, b, m.v * 8, cpg, G, a1, b1, rs, ms);
+    gn_coeffs<FAST>(stats, gamma, beta, b, m.v * 8, cpg, G, a1, b1, rs, ms);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (m.v * 8 + j) / cpg;
@@ -269,17 +305,22 @@ __global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restric
   int r = r0 + m.rsub;
   for (; r + m.rpp < r1; r += 2 * m.rpp) {
     float fx[2][8], fd[2][8];
+    bf16x8 ta[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       load8(x + base + (long long)(r + u * m.rpp) * C, fx[u]);
       load8(dy + base + (long long)(r + u * m.rpp) * C, fd[u]);
+      // fused accumulation of the gradient that reached x through the other branch.  dx may alias dx_add, so these loads must be
+      // issued here, with the others and before any store of this iteration (each element is read and written by the same
+      // thread): left next to their use they cannot be hoisted above the previous row's store and cost a second round trip
+      if (dx_add) ta[u] = load8raw(dx_add + base + (long long)(r + u * m.rpp) * C);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       body(fx[u], fd[u]);
-      if (dx_add) {   // fused accumulation of the gradient that reached x through the other branch (dx may alias dx_add)
+      if (dx_add) {
         float t[8];
-        load8(dx_add + base + (long long)(r + u * m.rpp) * C, t);
+        unpack8(ta[u], t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) fd[u][j] += t[j];
       }
@@ -288,12 +329,14 @@ __global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restric
   }
   for (; r < r1; r += m.rpp) {
     float fx[8], fd[8];
+    bf16x8 ta;
     load8(x + base + (long long)r * C, fx);
     load8(dy + base + (long long)r * C, fd);
+    if (dx_add) ta = load8raw(dx_add + base + (long long)r * C);
     body(fx, fd);
     if (dx_add) {
       float t[8];
-      load8(dx_add + base + (long long)r * C, t);
+      unpack8(ta, t);
 #pragma unroll
       for (int j = 0; j < 8; ++j) fd[j] += t[j];
     }
@@ -301,9 +344,12 @@ __global__ void __launch_bounds__(320) gn_bwd_apply_kernel(const bf16* __restric
   }
 }
 
+constexpr int GN_U_APPLY = 8;
+
 struct GnGeom {
   int threads, rpp;
-  int rows_apply, chunks_apply;   // elementwise passes: grid (chunks, B)
+  int rows_apply, chunks_apply;   // forward apply: one batch of GN_U_APPLY rows per thread
+  int rows_bapply, chunks_bapply; // backward apply
   int rows_red, chunks_red;       // reduction passes (fewer CTAs: each flushes 2C + 2G atomics)
 };
 int gn_geom(int B, int L, int C, GnGeom* g) {
@@ -320,9 +366,15 @@ int gn_geom(int B, int L, int C, GnGeom* g) {
     *rows = r;
     *chunks = (L + r - 1) / r;
   };
-  pick(6 * pt_num_sms(), 4, &g->rows_apply, &g->chunks_apply);
+  pick(16 * pt_num_sms(), GN_U_APPLY, &g->rows_apply, &g->chunks_apply);
+  pick(6 * pt_num_sms(), 4, &g->rows_bapply, &g->chunks_bapply);
   pick(3 * pt_num_sms(), 8, &g->rows_red, &g->chunks_red);
   return PT_OK;
+}
+// the vectorised coefficient fetch needs 16-byte aligned gamma / beta, 8-byte aligned stats and groups of at least 8 channels
+int gn_fast(const float* stats, const float* gamma, const float* beta, int C, int G) {
+  return ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0 &&
+         C / G >= 8;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -331,71 +383,96 @@ int gn_geom(int B, int L, int C, GnGeom* g) {
 constexpr int LN_MAXV = 8;
 
 template <int NV, int ROWS>
-__global__ void ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                               bf16* __restrict__ y, float* __restrict__ rowstats, long long M, int C, float eps) {
-  // one warp per ROWS consecutive rows, all of them in flight at once (small C: one row is too few bytes per warp)
+  // one warp per ROWS consecutive rows, all of them requested at once as raw bf16 (4 registers per 16-byte vector, converted
+  // each time they are used): many rows in flight per warp at a register cost that still leaves three CTAs per SM
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
   if (row0 >= M) return;
   const int nvec = C >> 3;
-  float f[ROWS][NV][8];
-  float s[ROWS];
+  bf16x8 raw[ROWS][NV];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
-    s[r] = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
-      if (v < nvec && row0 + r < M) load8(x + (row0 + r) * C + v * 8, f[r][i]);
+      if (v < nvec && row0 + r < M) raw[r][i] = load8raw(x + (row0 + r) * C + v * 8);
     }
   }
+  const float inv_c = 1.f / (float)C;
+  float mean[ROWS], rstd[ROWS];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
-    if (row0 + r >= M) break;
+    float s = 0.f;
+    if (row0 + r < M) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
+      for (int i = 0; i < NV; ++i) {
+        if (lane + i * 32 < nvec) {
+          float f[8];
+          unpack8(raw[r][i], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[r] += f[r][i][j];
-      }
-    }
-    const float mean = warp_sum(s[r]) / (float)C;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = f[r][i][j] - mean;
-          q = fmaf(d, d, q);
+          for (int j = 0; j < 8; ++j) s += f[j];
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    mean[r] = s;
+  }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float o[8];
+  for (int r = 0; r < ROWS; ++r) mean[r] = warp_sum(mean[r]) * inv_c;   // ROWS independent shuffle chains
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf((f[r][i][j] - mean) * rstd, gm[j], bt[j]);
-        store8(y + (row0 + r) * C + v * 8, o);
+  for (int r = 0; r < ROWS; ++r) {
+    float q = 0.f;
+    if (row0 + r < M) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane + i * 32 < nvec) {
+          float f[8];
+          unpack8_again(raw[r][i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = f[j] - mean[r];
+            q = fmaf(d, d, q);
+          }
+        }
       }
     }
-    if (lane == 0) {
-      rowstats[2 * (row0 + r)] = mean;
-      rowstats[2 * (row0 + r) + 1] = rstd;
+    rstd[r] = q;
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) rstd[r] = rsqrtf(warp_sum(rstd[r]) * inv_c + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if (row0 + r < M) {
+          float f[8], o[8];
+          unpack8_again(raw[r][i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf((f[j] - mean[r]) * rstd[r], gm[j], bt[j]);
+          store8(y + (row0 + r) * C + v * 8, o);
+        }
+      }
     }
+  }
+  if (lane < ROWS && row0 + lane < M) {
+    float mu = mean[0], rs = rstd[0];
+#pragma unroll
+    for (int r = 1; r < ROWS; ++r)
+      if (lane == r) mu = mean[r], rs = rstd[r];
+    *reinterpret_cast<float2*>(rowstats + 2 * (row0 + lane)) = make_float2(mu, rs);
   }
 }
 
-// Each warp walks rows w, w + nwarps_total, ...; per-lane dgamma/dbeta partials stay in registers and are
-// flushed once through shared memory + global atomics.
+// Each warp walks rows w, w + nwarps_total, ...; per-lane dgamma/dbeta partials stay in registers and are flushed once through
+// shared memory + global atomics.  A row is held as raw bf16 (x, dy, dx_add: 12 registers per 8 channels) and the NEXT row of the
+// warp is requested before the current one is reduced, so the two warp-wide reductions and the arithmetic of a row overlap the
+// memory round trip of the following one.
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ rowstats,
                               const float* __restrict__ gamma, const bf16* __restrict__ dx_add, bf16* __restrict__ dx,
@@ -404,52 +481,89 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
   const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  const float inv_c = 1.f / (float)C;
   float ag[NV][8], ab[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
   }
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += wstride) {
-    const float mean = rowstats[2 * row], rstd = rowstats[2 * row + 1];
-    float xh[NV][8], dg[NV][8];
+  bf16x8 cx[NV], cd[NV], ca[NV];
+  float2 cst = make_float2(0.f, 0.f);
+  auto fetch = [&](long long row, bf16x8* px, bf16x8* pd, bf16x8* pa, float2& st) {
+    if (row < M) {
+      st = __ldg(reinterpret_cast<const float2*>(rowstats + 2 * row));
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) {
+          px[i] = load8raw(x + row * C + v * 8);
+          pd[i] = load8raw(dy + row * C + v * 8);
+          if (dx_add) pa[i] = load8raw(dx_add + row * C + v * 8);
+        }
+      }
+    }
+  };
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  fetch(row, cx, cd, ca, cst);
+  for (; row < M; row += wstride) {
+    bf16x8 nx[NV], nd[NV], na[NV];
+    float2 nst = make_float2(0.f, 0.f);
+    fetch(row + wstride, nx, nd, na, nst);
+    const float mean = cst.x, rstd = cst.y;
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
         float fx[8], fd[8];
-        load8(x + row * C + v * 8, fx);
-        load8(dy + row * C + v * 8, fd);
+        unpack8(cx[i], fx);
+        unpack8(cd[i], fd);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (fx[j] - mean) * rstd;
-          ag[i][j] += fd[j] * xh[i][j];
+          const float xh = (fx[j] - mean) * rstd;
+          ag[i][j] = fmaf(fd[j], xh, ag[i][j]);
           ab[i][j] += fd[j];
-          dg[i][j] = fd[j] * __ldg(gamma + v * 8 + j);
-          c1 += dg[i][j];
-          c2 += dg[i][j] * xh[i][j];
+          const float dg = fd[j] * gm[j];
+          c1 += dg;
+          c2 = fmaf(dg, xh, c2);
         }
       }
     }
-    c1 = warp_sum(c1) / (float)C;
-    c2 = warp_sum(c2) / (float)C;
+    c1 = warp_sum(c1) * inv_c;
+    c2 = warp_sum(c2) * inv_c;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        float o[8];
+        float fx[8], fd[8], o[8];
+        unpack8_again(cx[i], fx);
+        unpack8_again(cd[i], fd);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (dg[i][j] - c1 - xh[i][j] * c2);
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (fx[j] - mean) * rstd;
+          o[j] = rstd * (fd[j] * gm[j] - c1 - xh * c2);
+        }
         if (dx_add) {
           float t[8];
-          load8(dx_add + row * C + v * 8, t);
+          unpack8(ca[i], t);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += t[j];
         }
         store8(dx + row * C + v * 8, o);
       }
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      cx[i] = nx[i];
+      cd[i] = nd[i];
+      ca[i] = na[i];
+    }
+    cst = nst;
   }
   float* slot = sh + (threadIdx.x >> 5) * 2 * C;
 #pragma unroll
@@ -493,8 +607,12 @@ extern "C" int pt_groupnorm_apply(const void* x, const float* stats, const float
   PT_REQUIRE(B > 0 && L > 0 && G > 0 && C % G == 0, "groupnorm_apply: B=%d L=%d C=%d G=%d", B, L, C, G);
   GnGeom g;
   if (int r = gn_geom(B, L, C, &g)) return r;
-  gn_apply_kernel<<<dim3(g.chunks_apply, B), g.threads, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, L, C, G,
-                                                                                  g.rows_apply, act);
+  if (gn_fast(stats, gamma, beta, C, G))
+    gn_apply_kernel<GN_U_APPLY, true><<<dim3(g.chunks_apply, B), g.threads, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, gamma, beta,
+                                                                                                      (bf16*)y, L, C, G, g.rows_apply, act);
+  else
+    gn_apply_kernel<GN_U_APPLY, false><<<dim3(g.chunks_apply, B), g.threads, 0, (cudaStream_t)stream>>>((const bf16*)x, stats, gamma, beta,
+                                                                                                       (bf16*)y, L, C, G, g.rows_apply, act);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
@@ -505,12 +623,20 @@ extern "C" int pt_groupnorm_bwd(const void* dy, const void* x, const float* stat
   GnGeom g;
   if (int r = gn_geom(B, L, C, &g)) return r;
   cudaStream_t st = (cudaStream_t)stream;
+  const int fast = gn_fast(stats, gamma, beta, C, G);
   PT_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * G, st));
-  gn_bwd_reduce_kernel<<<dim3(g.chunks_red, B), g.threads, g.threads * 16 * sizeof(float), st>>>(
-      (const bf16*)dy, (const bf16*)x, stats, gamma, beta, dgamma, dbeta, scratch, L, C, G, g.rows_red, act);
-  PT_LAUNCH_CHECK();
-  gn_bwd_apply_kernel<<<dim3(g.chunks_apply, B), g.threads, 0, st>>>((const bf16*)dy, (const bf16*)x, stats, gamma, beta, scratch,
-                                                                     (const bf16*)dx_add, (bf16*)dx, L, C, G, g.rows_apply, act);
+  const dim3 gr(g.chunks_red, B), ga(g.chunks_bapply, B);
+  const size_t smem = g.threads * 16 * sizeof(float);
+  const bf16 *dyp = (const bf16*)dy, *xp = (const bf16*)x, *addp = (const bf16*)dx_add;
+  if (fast) {
+    gn_bwd_reduce_kernel<true><<<gr, g.threads, smem, st>>>(dyp, xp, stats, gamma, beta, dgamma, dbeta, scratch, L, C, G, g.rows_red, act);
+    PT_LAUNCH_CHECK();
+    gn_bwd_apply_kernel<true><<<ga, g.threads, 0, st>>>(dyp, xp, stats, gamma, beta, scratch, addp, (bf16*)dx, L, C, G, g.rows_bapply, act);
+  } else {
+    gn_bwd_reduce_kernel<false><<<gr, g.threads, smem, st>>>(dyp, xp, stats, gamma, beta, dgamma, dbeta, scratch, L, C, G, g.rows_red, act);
+    PT_LAUNCH_CHECK();
+    gn_bwd_apply_kernel<false><<<ga, g.threads, 0, st>>>(dyp, xp, stats, gamma, beta, scratch, addp, (bf16*)dx, L, C, G, g.rows_bapply, act);
+  }
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
@@ -527,7 +653,7 @@ extern "C" int pt_layernorm_fwd(const void* x, const float* gamma, const float* 
                                                                                                               (bf16*)y, rowstats, M, C, eps); \
     break;
   switch (nv) {
-    LN_FWD(1, 4) LN_FWD(2, 4) LN_FWD(3, 2) LN_FWD(4, 2) LN_FWD(5, 2) LN_FWD(6, 1) LN_FWD(7, 1) LN_FWD(8, 1)
+    LN_FWD(1, 8) LN_FWD(2, 8) LN_FWD(3, 4) LN_FWD(4, 4) LN_FWD(5, 2) LN_FWD(6, 2) LN_FWD(7, 2) LN_FWD(8, 2)
   }
 #undef LN_FWD
   PT_LAUNCH_CHECK();
@@ -537,21 +663,25 @@ extern "C" int pt_layernorm_fwd(const void* x, const float* gamma, const float* 
 extern "C" int pt_layernorm_bwd(const void* dy, const void* x, const float* rowstats, const float* gamma, const void* dx_add, void* dx,
                                 float* dgamma, float* dbeta, int64_t M, int C, void* stream) {
   PT_REQUIRE(M > 0 && C % 8 == 0 && C / 8 <= 32 * LN_MAXV, "layernorm_bwd: M=%lld C=%d", (long long)M, C);
+  PT_REQUIRE((reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(rowstats) & 7) == 0,
+             "layernorm_bwd: gamma must be 16-byte aligned, rowstats 8-byte aligned");
   const int wpb = 8;
   long long blocks = (M + wpb - 1) / wpb;
   const int nv = (C / 8 + 31) / 32;
-  // every CTA ends with a 2C-value flush (shared-memory fold + global atomics): wide rows get one CTA per SM so that a warp
-  // sees enough rows to amortise it, narrow rows two (measured: 1 / 2 / 4 per SM at C = 768 -> 65 / 44 / 48 us)
-  const long long cap = (nv >= 4 ? 1ll : 2ll) * pt_num_sms();
-  if (blocks > cap) blocks = cap;
+  // every CTA ends with a 2C-value flush (shared-memory fold + global atomics), so the grid is exactly one resident wave: as
+  // many CTAs as fit at once (register-limited: two per SM up to C = 512, one above), each warp walking many rows
   const size_t smem = (size_t)wpb * 2 * C * sizeof(float);
 #define LN_BWD(NV_)                                                                                                            \
   case NV_: {                                                                                                                  \
-    static bool attr_set = false;                                                                                              \
-    if (!attr_set) {                                                                                                           \
+    static int occ = 0;                                                                                                        \
+    if (!occ) {                                                                                                                \
       PT_CUDA_OK(cudaFuncSetAttribute(ln_bwd_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * NV_ * 256 * 4)); \
-      attr_set = true;                                                                                                         \
+      int o = 0;                                                                                                               \
+      PT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ln_bwd_kernel<NV_>, wpb * 32, 8 * 2 * NV_ * 256 * 4));       \
+      occ = o < 1 ? 1 : (o > 2 ? 2 : o);                                                                                       \
     }                                                                                                                          \
+    const long long cap = (long long)occ * pt_num_sms();                                                                       \
+    if (blocks > cap) blocks = cap;                                                                                            \
     ln_bwd_kernel<NV_><<<(unsigned)blocks, wpb * 32, smem, (cudaStream_t)stream>>>(                                             \
         (const bf16*)dy, (const bf16*)x, rowstats, gamma, (const bf16*)dx_add, (bf16*)dx, dgamma, dbeta, M, C);                \
   } break;
