@@ -3,6 +3,7 @@ UNet1DConditionOutput (:28-35).  conv_in -> time embedding -> down blocks -> mid
 GroupNorm + SiLU + conv_out, executed as one tape over channels-last bf16 activations."""
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, Optional, Tuple, Union
 
 import torch
@@ -19,6 +20,10 @@ from .unet_blocks import UNetMidBlock1DCrossAttn, get_down_block, get_up_block
 class UNet1DConditionOutput(BaseOutput):
     """`.sample`: [B, out_channels, L] (unet_1d_condition.py:28-35)."""
     sample: torch.FloatTensor
+
+
+# measurement switch: the direct (CUDA-core) conv_in / conv_out kernels instead of the implicit-GEMM path
+_DIRECT_CONV_IO = os.environ.get("PT_DIRECT_CONV_IO", "0") == "1"
 
 
 class Unet1DConditionModel(nn.Module):
@@ -158,16 +163,21 @@ class Unet1DConditionModel(nn.Module):
             si += k
             return r
 
-        # conv_in (:654)
+        # conv_in (:654).  With a channel count that is a multiple of 8 (16-byte rows: a valid TMA operand) it runs on the same
+        # implicit-GEMM path as every other k=3 convolution -- the 8-wide contraction is zero-filled up to one 64-deep stage, which
+        # wastes tensor-core work that is not missed (8 us against 220 us for the direct kernel, `profiles/r01_bw_probe_v8.txt`).
         w, bia = self.conv_in.weight, self.conv_in.bias
-        h0 = torch.empty(B, L, C0, dtype=E.BF16, device=sample_ncl.device)
-        ops.call("conv_in_fwd", ops._p(sample_ncl), ops._p(w.detach()), ops._p(bia.detach()), ops._p(h0), B, Cin, L, C0, ops._stream())
-        h_in = E.Var(h0)      # NB: a distinct name -- the closure below must not see later rebinding of `h`
+        if Cin % 8 == 0 and not _DIRECT_CONV_IO:
+            h_in = E.conv3(tape, E.Var(ops.ncl_to_nlc(sample_ncl), needs_grad=False), w, bia)
+        else:
+            h0 = torch.empty(B, L, C0, dtype=E.BF16, device=sample_ncl.device)
+            ops.call("conv_in_fwd", ops._p(sample_ncl), ops._p(w.detach()), ops._p(bia.detach()), ops._p(h0), B, Cin, L, C0, ops._stream())
+            h_in = E.Var(h0)      # NB: a distinct name -- the closure below must not see later rebinding of `h`
 
-        def conv_in_bwd():
-            if h_in.grad is not None:
-                ops.call("conv_in_bwd", ops._p(h_in.grad), ops._p(sample_ncl), ops._p(tape.pgrad(w)), ops._p(tape.pgrad(bia)), B, Cin, L, C0, ops._stream())
-        tape.record(conv_in_bwd)
+            def conv_in_bwd():
+                if h_in.grad is not None:
+                    ops.call("conv_in_bwd", ops._p(h_in.grad), ops._p(sample_ncl), ops._p(tape.pgrad(w)), ops._p(tape.pgrad(bia)), B, Cin, L, C0, ops._stream())
+            tape.record(conv_in_bwd)
         h = h_in
 
         skips = [h]
@@ -187,6 +197,14 @@ class Unet1DConditionModel(nn.Module):
         hn = E.groupnorm(tape, h, self.conv_norm_out.weight, self.conv_norm_out.bias, self._norm_eps, True, self._groups)
         wo, bo = self.conv_out.weight, self.conv_out.bias
         Cout = wo.shape[0]
+        if Cout % 8 == 0 and not _DIRECT_CONV_IO:
+            # same implicit-GEMM path (N = 8 of a 64-wide tile); the layout change back to fp32 [B, C, L] is a separate small kernel
+            y_cl = E.conv3(tape, hn, wo, bo)
+
+            def seed_gemm(gouts):
+                y_cl.grad, y_cl.owned = ops.ncl_to_nlc(gouts[0].float().contiguous()), True
+
+            return ops.nlc_to_ncl(y_cl.data), seed_gemm
         y = torch.empty(B, Cout, L, dtype=E.F32, device=sample_ncl.device)
         ops.call("conv_out_fwd", ops._p(hn.data), ops._p(wo.detach()), ops._p(bo.detach()), ops._p(y), B, C0, L, Cout, ops._stream())
 
