@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
 
 // delta[b, h, q] = sum_j dO[b, q, h*d + j] * O[b, q, h*d + j].  A CTA takes DELTA_ROWS rows; consecutive threads read consecutive
 // 16-byte vectors of a row (coalesced), each vector lies inside one head (d % 8 == 0), partial dots meet in shared memory.
-constexpr int DELTA_ROWS = 32;
+constexpr int DELTA_ROWS = 8;
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long o_rs, long long o_bs, const bf16* __restrict__ d_o,
                                                          long long do_rs, long long do_bs, float* __restrict__ delta, int B, int H, int L, int D) {
   __shared__ float acc[DELTA_ROWS * 64];   // [row][head], H <= 64
@@ -590,43 +590,27 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   const int nvec = (H * D) >> 3, vph = D >> 3;
   for (int i = threadIdx.x; i < DELTA_ROWS * H; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
-  const int total = DELTA_ROWS * nvec;
-  constexpr int U = 4;   // vectors in flight per thread (a thread has only a handful: without this the kernel is latency-bound)
-  for (int i0 = threadIdx.x; i0 < total; i0 += U * 256) {
-    float a[U][8], c[U][8];
-    int slot[U];
+  for (int i = threadIdx.x; i < DELTA_ROWS * nvec; i += blockDim.x) {
+    const int rl = i / nvec, v = i - rl * nvec;
+    const long long row = row0 + rl;
+    if (row < nrows) {
+      const int bb = (int)(row / L), l = (int)(row - (long long)bb * L);
+      float a[8], c[8];
+      load8(o + (long long)bb * o_bs + (long long)l * o_rs + v * 8, a);
+      load8(d_o + (long long)bb * do_bs + (long long)l * do_rs + v * 8, c);
+      float t = 0.f;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * 256;
-      slot[u] = -1;
-      if (i < total) {
-        const int rl = i / nvec, v = i - rl * nvec;
-        const long long row = row0 + rl;
-        if (row < nrows) {
-          const int bb = (int)(row / L), l = (int)(row - (long long)bb * L);
-          load8(o + (long long)bb * o_bs + (long long)l * o_rs + v * 8, a[u]);
-          load8(d_o + (long long)bb * do_bs + (long long)l * do_rs + v * 8, c[u]);
-          slot[u] = rl * H + v / vph;
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (slot[u] >= 0) {
-        float t = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t = fmaf(a[u][j], c[u][j], t);
-        atomicAdd(&acc[slot[u]], t);
-      }
+      for (int u = 0; u < 8; ++u) t = fmaf(a[u], c[u], t);
+      atomicAdd(&acc[rl * H + v / vph], t);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < DELTA_ROWS * H; i += blockDim.x) {
-    const int hh = i / DELTA_ROWS, rl = i - hh * DELTA_ROWS;   // consecutive threads -> consecutive rows of one head: contiguous stores
+    const int rl = i / H, hh = i - rl * H;
     const long long row = row0 + rl;
     if (row < nrows) {
       const int bb = (int)(row / L), l = (int)(row - (long long)bb * L);
-      delta[((long long)bb * H + hh) * L + l] = acc[rl * H + hh];
+      delta[((long long)bb * H + hh) * L + l] = acc[i];
     }
   }
 }
