@@ -63,26 +63,32 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// 8 x bf16 <-> 8 x float through one 16-byte access
+// 8 x bf16 <-> 8 x float through ONE 16-byte access.  The carrier is four plain 32-bit words moved as a uint4: a struct of
+// __nv_bfloat162 members is copied member-wise by the compiler (the type is not trivially copyable), which turns every
+// "16-byte" access into four 4-byte ones with a 16-byte stride -- four times the load/store instructions and, for stores,
+// four partial writes per sector (found with cuobjdump: STG.E x4 instead of STG.E.128 in every kernel using it).
 struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
+  uint32_t w[4];
 };
-__device__ __forceinline__ void load8(const bf16* p, float* f) {
-  bf16x8 r = *reinterpret_cast<const bf16x8*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(r.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+__device__ __forceinline__ bf16x8 ld16(const void* p) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  bf16x8 r;
+  r.w[0] = t.x, r.w[1] = t.y, r.w[2] = t.z, r.w[3] = t.w;
+  return r;
 }
-// the same in two steps: issue the 16-byte load now (4 registers), convert when the value is needed -- lets a thread keep many
-// loads in flight without holding 8 fp32 registers per vector
-__device__ __forceinline__ bf16x8 load8raw(const bf16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+__device__ __forceinline__ void st16(void* p, const bf16x8& r) { *reinterpret_cast<uint4*>(p) = make_uint4(r.w[0], r.w[1], r.w[2], r.w[3]); }
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t f2_to_bf2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+// issue the 16-byte load now (4 registers), convert when the value is needed -- lets a thread keep many loads in flight without
+// holding 8 fp32 registers per vector
+__device__ __forceinline__ bf16x8 load8raw(const bf16* p) { return ld16(p); }
 __device__ __forceinline__ void unpack8(const bf16x8& r, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(r.v[i]);
+    const float2 t = bf2_to_f2(r.w[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -93,16 +99,18 @@ __device__ __forceinline__ void unpack8_again(const bf16x8& r, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     uint32_t w;
-    asm volatile("mov.b32 %0, %1;" : "=r"(w) : "r"(*reinterpret_cast<const uint32_t*>(&r.v[i])));
-    f[2 * i] = __uint_as_float(w << 16);
-    f[2 * i + 1] = __uint_as_float(w & 0xffff0000u);
+    asm volatile("mov.b32 %0, %1;" : "=r"(w) : "r"(r.w[i]));
+    const float2 t = bf2_to_f2(w);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
   }
 }
+__device__ __forceinline__ void load8(const bf16* p, float* f) { unpack8(ld16(p), f); }
 __device__ __forceinline__ void store8(bf16* p, const float* f) {
   bf16x8 r;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  *reinterpret_cast<bf16x8*>(p) = r;
+  for (int i = 0; i < 4; ++i) r.w[i] = f2_to_bf2(f[2 * i], f[2 * i + 1]);
+  st16(p, r);
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }

@@ -196,7 +196,7 @@ __global__ void copy2d_kernel(const bf16* __restrict__ src, long long ld_src, bf
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / nvec;
     const int v = (int)(i % nvec);
-    *reinterpret_cast<bf16x8*>(dst + r * ld_dst + v * 8) = *reinterpret_cast<const bf16x8*>(src + r * ld_src + v * 8);
+    st16(dst + r * ld_dst + v * 8, ld16(src + r * ld_src + v * 8));
   }
 }
 
@@ -205,9 +205,9 @@ __global__ void upsample2_fwd_kernel(const bf16* __restrict__ x, bf16* __restric
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / nvec;  // b*L + l
     const int v = (int)(i % nvec);
-    const bf16x8 t = *reinterpret_cast<const bf16x8*>(x + (r * nvec + v) * 8);
-    *reinterpret_cast<bf16x8*>(y + ((2 * r) * nvec + v) * 8) = t;
-    *reinterpret_cast<bf16x8*>(y + ((2 * r + 1) * nvec + v) * 8) = t;
+    const bf16x8 t = ld16(x + (r * nvec + v) * 8);
+    st16(y + ((2 * r) * nvec + v) * 8, t);
+    st16(y + ((2 * r + 1) * nvec + v) * 8, t);
   }
 }
 __global__ void upsample2_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, long long rows_in, int nvec) {

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
 #pragma unroll
           for (int i = 0; i < NIT; ++i) {
             const int m = mw + crow + i * RPI;
-            if (m < p.M && nb < p.N) dst[i] = *reinterpret_cast<const bf16x8*>(p.res + zoff_r + (long long)m * p.rsm + nb);
+            if (m < p.M && nb < p.N) dst[i] = ld16(p.res + zoff_r + (long long)m * p.rsm + nb);
           }
         };
         if (has_res) load_res(0, rr[0]);
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
             }
             if (has_res) {
 #pragma unroll
-              for (int i = 0; i < NIT; ++i) *reinterpret_cast<bf16x8*>(stg + (crow + i * RPI) * PITCH + cvec * 16) = rr[c & 1][i];
+              for (int i = 0; i < NIT; ++i) st16(stg + (crow + i * RPI) * PITCH + cvec * 16, rr[c & 1][i]);
               __syncwarp();
             }
 #pragma unroll
@@ -375,20 +375,20 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][g * 8 + j]), p.alpha, sbias[c * CH + g * 8 + j]);
-              bf16x8* cell = reinterpret_cast<bf16x8*>(stg + lane * PITCH + g * 16);   // this thread's row, vector g
+              uint8_t* cell = stg + lane * PITCH + g * 16;   // this thread's row, vector g
               if (has_res) {
-                const bf16x8 t = *cell;
+                const bf16x8 t = ld16(cell);
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
-                  const float2 u = __bfloat1622float2(t.v[h]);
+                  const float2 u = bf2_to_f2(t.w[h]);
                   f[2 * h] += u.x;
                   f[2 * h + 1] += u.y;
                 }
               }
               bf16x8 t;
 #pragma unroll
-              for (int h = 0; h < 4; ++h) t.v[h] = __floats2bfloat162_rn(f[2 * h], f[2 * h + 1]);
-              *cell = t;
+              for (int h = 0; h < 4; ++h) t.w[h] = f2_to_bf2(f[2 * h], f[2 * h + 1]);
+              st16(cell, t);
             }
             __syncwarp();
             const int ncol = nb + cvec * 8;
@@ -396,8 +396,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
             for (int i = 0; i < NIT; ++i) {
               const int m = mw + crow + i * RPI;
               if (m < p.M && ncol < p.N)
-                *reinterpret_cast<bf16x8*>(outp + zoff_o + (long long)m * p.osm + ncol) =
-                    *reinterpret_cast<const bf16x8*>(stg + (crow + i * RPI) * PITCH + cvec * 16);
+                st16(outp + zoff_o + (long long)m * p.osm + ncol, ld16(stg + (crow + i * RPI) * PITCH + cvec * 16));
             }
           }
         }

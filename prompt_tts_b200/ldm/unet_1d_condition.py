@@ -165,7 +165,7 @@ class Unet1DConditionModel(nn.Module):
 
         # conv_in (:654).  With a channel count that is a multiple of 8 (16-byte rows: a valid TMA operand) it runs on the same
         # implicit-GEMM path as every other k=3 convolution -- the 8-wide contraction is zero-filled up to one 64-deep stage, which
-        # wastes tensor-core work that is not missed (8 us against 220 us for the direct kernel, `profiles/r01_bw_probe_v8.txt`).
+        # wastes tensor-core work that is not missed (8 us against 220 us for the direct kernel, `profiles/r01_bw_probe_v9.txt`).
         w, bia = self.conv_in.weight, self.conv_in.bias
         if Cin % 8 == 0 and not _DIRECT_CONV_IO:
             h_in = E.conv3(tape, E.Var(ops.ncl_to_nlc(sample_ncl), needs_grad=False), w, bia)

@@ -78,3 +78,30 @@ def test_conv_weight_gradient_three_taps_one_launch(cuda):
     w = torch.zeros(Co, Ci, 3, device=cuda, requires_grad=True)
     F.conv1d(xx, w, padding=1).backward(dy.float().transpose(1, 2))
     assert rel(dw, w.grad) < 1e-5
+
+
+@pytest.mark.parametrize("Ci,Co", [(8, 320), (320, 8), (16, 64)])
+def test_thin_conv_on_the_gemm_path(cuda, Ci, Co):
+    """conv_in (8 -> C) and conv_out (C -> 8) of the reference model (unet_1d_condition.py:193,734) run on the implicit-GEMM conv
+    path with the 8-wide side zero-filled to one tile: forward, bias, weight and data gradients against F.conv1d in fp32."""
+    from prompt_tts_b200 import engine as E
+    g = torch.Generator(device="cuda").manual_seed(7)
+    Bn, L = 3, 94
+    x = bf(torch.randn(Bn, L, Ci, device=cuda, generator=g))
+    w = (torch.randn(Co, Ci, 3, device=cuda, generator=g) * 0.2).requires_grad_(True)
+    b = torch.randn(Co, device=cuda, generator=g).requires_grad_(True)
+    dy = bf(torch.randn(Bn, L, Co, device=cuda, generator=g))
+    tape = E.Tape(E.PackCache())
+    xv = E.Var(x)
+    y = E.conv3(tape, xv, w, b)
+    y.grad, y.owned = dy, True
+    tape.backward()
+    torch.cuda.synchronize()
+    xr = x.float().transpose(1, 2).requires_grad_(True)
+    wr = bf(w.detach()).float().requires_grad_(True)      # the path contracts bf16 copies of the weights
+    br = b.detach().clone().requires_grad_(True)
+    yr = F.conv1d(xr, wr, br, padding=1)
+    yr.backward(dy.float().transpose(1, 2))
+    assert rel(y.data.float().transpose(1, 2), yr) < 5e-3
+    assert rel(tape.pgrads[id(w)], wr.grad) < 1e-4 and rel(tape.pgrads[id(b)], br.grad) < 1e-4
+    assert rel(xv.grad.float().transpose(1, 2), xr.grad) < 5e-3
