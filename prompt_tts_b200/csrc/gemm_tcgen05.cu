@@ -2,10 +2,10 @@
 //
 //   out[z, m, n] = alpha * sum_seg sum_k A_seg[m + shift, k] * B_seg[n, k]  (+ bias, + per-batch bias, + residual)
 //
-// One CTA per 128 x BN output tile.  Warp roles (192 threads):
+// One CTA per 128 x BN output tile.  Warp roles (192 threads for tiles <= 128 wide, 320 above):
 //   warp 0   TMA producer: cp.async.bulk.tensor.4d into a ring of SWIZZLE_128B stages
 //   warp 1   MMA issuer:   one thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32 in TMEM)
-//   warp 2-5 epilogue:     tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+//   warp 2.. epilogue:     tcgen05.ld 32x32b -> registers -> fused epilogue -> global; one or two warps per TMEM lane quarter
 // Operands may be K-major or MN-major (UMMA descriptors handle the transposed case), so the same kernel
 // serves forward (K-major x K-major), data-gradient (K-major x MN-major) and weight-gradient
 // (MN-major x MN-major, contraction over rows and batch) GEMMs, k=3 convolutions as three shifted
@@ -63,11 +63,18 @@ struct Cfg {
   static constexpr int B_STAGE_BYTES = BN_S * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int CTAS_PER_SM = BN <= 128 ? 2 : 1;  // narrow tiles: two persistent CTAs per SM hide each other's issue latency
-  static constexpr int EPI_COLS = (BN % 64 == 0 && CTAS_PER_SM == 1) ? 64 : 32;   // columns per epilogue pass
-  static constexpr int EPI_BF16_BYTES = 4 * 32 * (EPI_COLS * 2 + 16);
-  static constexpr int EPI_F32_BYTES = CTAS_PER_SM == 1 ? 4 * 32 * 33 * 4 : 4 * 32 * 17 * 4;   // fp32 transpose tile per warp: 32 x 32 (+1) or 32 x 16 (+1)
+  // Epilogue warps.  One warp per TMEM lane quarter is a single dependent instruction stream per SM sub-partition: ~1700
+  // instructions per 128 x 256 tile at an IPC of ~0.13 = 13k clocks, more than the mainloop of any K < 1000 (ncu on
+  // 24064 x 2560 x 320: same 87 us with K = 64 as with K = 320).  Wide tiles (one CTA per SM) therefore get TWO warps per
+  // quarter, each taking every other 32-column pass; narrow tiles already have two CTAs = eight epilogue warps per SM.
+  static constexpr int EPI_WARPS = CTAS_PER_SM == 1 ? 8 : 4;
+  static constexpr int EPI_SPLIT = EPI_WARPS / 4;        // warps sharing one lane quarter
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int EPI_COLS = 32;                     // columns per epilogue pass
+  static constexpr int EPI_BF16_BYTES = EPI_WARPS * 32 * (EPI_COLS * 2 + 16);
+  static constexpr int EPI_F32_BYTES = EPI_WARPS * 32 * 17 * 4;   // fp32 transpose tile per warp: 32 x 16 (+1)
   static constexpr int EPI_BYTES = EPI_BF16_BYTES > EPI_F32_BYTES ? EPI_BF16_BYTES : EPI_F32_BYTES;
-  static constexpr int F32_COLS = CTAS_PER_SM == 1 ? 32 : 16;   // columns per transpose pass of the atomic epilogue
+  static constexpr int F32_COLS = 16;   // columns per transpose pass of the atomic epilogue
   static constexpr int BAR_BYTES = 256;
   static constexpr int BIAS_BYTES = 1024;
   static constexpr int AUX_BYTES = 1024 /*align slack*/ + BAR_BYTES + BIAS_BYTES + EPI_BYTES;
@@ -120,7 +127,7 @@ struct Sched {
 // each loads its own A tile and HALF of the B tile, multicast into both CTAs' shared memory, which halves the B traffic from L2
 // (operand delivery, ~64 B/clk/SM, is what limits the 256-wide tiles).  A stage is reusable when BOTH CTAs' MMAs have retired.
 template <int BN, int MC>
-__global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const __grid_constant__ KParams p) {
   using C = Cfg<BN>;
   const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 128);
+      mbar_init(tmem_empty_bar(a), 32 * C::EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -288,8 +295,12 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
       ++segi;
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5), overlapped with the next segment's mainloop
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    // ------------------------------------------------------------ epilogue (warps 2..), overlapped with the next segment's mainloop
+    const int q = warp & 3;              // TMEM lane quarter this warp may touch
+    const int ew = warp - 2;             // epilogue warp index: private staging tile
+    const int half = ew >> 2;            // which of the EPI_SPLIT warps of this quarter: takes passes half, half + EPI_SPLIT, ...
+    constexpr int ES = C::EPI_SPLIT;
+    constexpr int ET = 32 * C::EPI_WARPS;
     const int et = threadIdx.x - 64;
     int segi = 0;
     int staged_n0 = -1, staged_z2 = -1;
@@ -300,9 +311,9 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
       // stage the per-column additive term (bias + per-batch time shift) in shared memory -- only when the column block (or the
       // batch element of a time shift) differs from what is already there: tiles are walked m-fastest, so this is rare
       if (n0 != staged_n0 || (p.bias_z2 != nullptr && z2 != staged_z2)) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone is done with the previous contents
+        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");   // everyone is done with the previous contents
         const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.bz2_stride : nullptr;
-        for (int j = et; j < BN; j += 128) {
+        for (int j = et; j < BN; j += ET) {
           const int n = n0 + j;
           float bsum = 0.f;
           if (n < p.N) {
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
           }
           sbias[j] = bsum;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
         staged_n0 = n0;
         staged_z2 = z2;
       }
@@ -321,13 +332,14 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
         // ---- bf16 output (+ optional bf16 residual): every global access is a full 64/128-byte row segment.
         // Accumulator rows live one per thread; a warp-private padded smem tile transposes between "thread = row"
         // and "8 (or 4) lanes = one contiguous row segment".
-        constexpr int CH = C::EPI_COLS;            // columns per pass (64 or 32)
+        constexpr int CH = C::EPI_COLS;            // columns per pass
         constexpr int NPASS = BN / CH;
+        constexpr int NPH = (NPASS + ES - 1) / ES; // passes per warp
         constexpr int VPR = CH / 8;                // 16-byte vectors per row segment
         constexpr int RPI = 32 / VPR;              // rows covered by one warp-wide access
         constexpr int NIT = 32 / RPI;              // accesses per pass
         constexpr int PITCH = CH * 2 + 16;         // bytes, padded: conflict-free for both access patterns
-        uint8_t* stg = sepi + q * (32 * PITCH);
+        uint8_t* stg = sepi + ew * (32 * PITCH);
         const int mw = m0 + q * 32;                // first row of this warp
         const int crow = lane / VPR, cvec = lane % VPR;
         const long long zoff_o = (long long)z2 * p.osz2 + (long long)z3 * p.osz3;
@@ -335,6 +347,7 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
         bf16* outp = reinterpret_cast<bf16*>(p.out);
         const bool has_res = p.res != nullptr;
         const int last_c = min(NPASS, (p.N - n0 + CH - 1) / CH) - 1;   // last pass with columns inside N
+        const int last_k = last_c >= half ? (last_c - half) / ES : -1;  // this warp's last pass (pass index = half + k * ES)
         uint32_t v[2][CH];
         bf16x8 rr[2][NIT];
         auto load_res = [&](int pass, bf16x8* dst) {
@@ -345,21 +358,25 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
             if (m < p.M && nb < p.N) dst[i] = ld16(p.res + zoff_r + (long long)m * p.rsm + nb);
           }
         };
-        if (has_res) load_res(0, rr[0]);
+        if (has_res && last_k >= 0) load_res(half, rr[0]);
         mbar_wait(tmem_full_bar(acc), full_parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (last_k < 0) {   // no column of this warp's passes is inside N: nothing to read, hand the buffer back
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(tmem_empty_bar(acc));
+        } else {
+          tmem_ld32(tbase + (uint32_t)(half * CH), v[0]);
+        }
 #pragma unroll
-        for (int h = 0; h < CH / 32; ++h) tmem_ld32(tbase + h * 32, v[0] + h * 32);
-#pragma unroll
-        for (int c = 0; c < NPASS; ++c) {
+        for (int k = 0; k < NPH; ++k) {
+          const int c = half + k * ES;             // pass index (warp-uniform)
           const int nb = n0 + c * CH;
-          if (c <= last_c) {  // warp-uniform
+          if (k <= last_k) {  // warp-uniform
             __syncwarp();
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c < last_c) {
-#pragma unroll
-              for (int h = 0; h < CH / 32; ++h) tmem_ld32(tbase + (uint32_t)((c + 1) * CH + h * 32), v[(c + 1) & 1] + h * 32);
-              if (has_res) load_res(c + 1, rr[(c + 1) & 1]);
+            if (k < last_k) {
+              tmem_ld32(tbase + (uint32_t)((c + ES) * CH), v[(k + 1) & 1]);
+              if (has_res) load_res(c + ES, rr[(k + 1) & 1]);
             } else {
               // the accumulator is in registers: hand the TMEM buffer back to the MMA warp
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -367,14 +384,17 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
             }
             if (has_res) {
 #pragma unroll
-              for (int i = 0; i < NIT; ++i) st16(stg + (crow + i * RPI) * PITCH + cvec * 16, rr[c & 1][i]);
+              for (int i = 0; i < NIT; ++i) st16(stg + (crow + i * RPI) * PITCH + cvec * 16, rr[k & 1][i]);
               __syncwarp();
             }
+            const float* sb = sbias + c * CH;
 #pragma unroll
             for (int g = 0; g < VPR; ++g) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sb + g * 8), b1 = *reinterpret_cast<const float4*>(sb + g * 8 + 4);
+              const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float f[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][g * 8 + j]), p.alpha, sbias[c * CH + g * 8 + j]);
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[k & 1][g * 8 + j]), p.alpha, bs[j]);
               uint8_t* cell = stg + lane * PITCH + g * 16;   // this thread's row, vector g
               if (has_res) {
                 const bf16x8 t = ld16(cell);
@@ -401,36 +421,48 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
           }
         }
       } else {
-        // ---- fp32 store / fp32 atomic accumulate (tiny MLP outputs, weight gradients): one row per thread
+        // ---- fp32 store / fp32 atomic accumulate (tiny MLP outputs, weight gradients): one row per thread, 16 columns per pass
         const int m = m0 + q * 32 + lane;
         const bool m_ok = m < p.M;
         const long long out_off = (long long)z2 * p.osz2 + (long long)z3 * p.osz3 + (long long)m * p.osm;
-        constexpr int NCH = BN / 32;
-        const int last_c = min(NCH, (p.N - n0 + 31) / 32) - 1;
-        uint32_t v[2][32];
+        constexpr int FC = C::F32_COLS;            // 16
+        constexpr int NCH = BN / FC;
+        constexpr int NPH = (NCH + ES - 1) / ES;   // chunks per warp
+        const int last_c = min(NCH, (p.N - n0 + FC - 1) / FC) - 1;
+        const int last_k = last_c >= half ? (last_c - half) / ES : -1;   // this warp's last chunk (chunk index = half + k * ES)
+        uint32_t v[2][FC];
         mbar_wait(tmem_full_bar(acc), full_parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tmem_ld32(tbase, v[0]);
+        if (last_k < 0) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(tmem_empty_bar(acc));
+        } else {
+          tmem_ld16(tbase + (uint32_t)(half * FC), v[0]);
+        }
+        float* tile = reinterpret_cast<float*>(sepi) + ew * (32 * (FC + 1));
+        const int mrow0 = m0 + q * 32;
+        const long long zoff = (long long)z2 * p.osz2 + (long long)z3 * p.osz3;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int nb = n0 + c * 32;
-          if (c <= last_c) {  // warp-uniform
+        for (int k = 0; k < NPH; ++k) {
+          const int c = half + k * ES;
+          const int nb = n0 + c * FC;
+          if (k <= last_k) {  // warp-uniform
             __syncwarp();
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c < last_c) {
-              tmem_ld32(tbase + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
+            if (k < last_k) {
+              tmem_ld16(tbase + (uint32_t)((c + ES) * FC), v[(k + 1) & 1]);
             } else {
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
               mbar_arrive(tmem_empty_bar(acc));
             }
-            float f[32];
+            float f[FC];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[c & 1][j]), p.alpha, sbias[c * 32 + j]);
-            if (m_ok) {
-              if (p.out_dtype == PT_OUT_F32) {
+            for (int j = 0; j < FC; ++j) f[j] = fmaf(__uint_as_float(v[k & 1][j]), p.alpha, sbias[c * FC + j]);
+            if (p.out_dtype == PT_OUT_F32) {
+              if (m_ok) {
                 float* o = reinterpret_cast<float*>(p.out) + out_off + nb;
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
+                for (int g = 0; g < FC / 4; ++g) {
                   if (nb + g * 4 + 4 <= p.N) {
                     *reinterpret_cast<float4*>(o + g * 4) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
                   } else {
@@ -440,28 +472,19 @@ __global__ void __launch_bounds__(192, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const _
                   }
                 }
               }
-            }
-            if (p.out_dtype == PT_OUT_F32_ATOMIC_ADD) {
-              // transpose through a warp-private tile so that one warp-wide RED covers consecutive columns of one row
-              // (8 floats per 32-byte L2 sector instead of 1)
-              constexpr int FC = C::F32_COLS;
-              float* tile = reinterpret_cast<float*>(sepi) + q * (32 * (FC + 1));
-              const int mrow0 = m0 + q * 32;
-              const long long zoff = (long long)z2 * p.osz2 + (long long)z3 * p.osz3;
+            } else {
+              // PT_OUT_F32_ATOMIC_ADD: transpose through a warp-private tile so that one warp-wide RED covers consecutive columns of
+              // two rows (8 floats per 32-byte L2 sector instead of 1)
 #pragma unroll
-              for (int hh = 0; hh < 32 / FC; ++hh) {
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < FC; ++j) tile[lane * (FC + 1) + j] = f[hh * FC + j];
-                __syncwarp();
-                const int col = lane % FC, rsub = lane / FC;          // FC == 32: one row per instruction; FC == 16: two rows
-                const int n = nb + hh * FC + col;
-                if (n < p.N) {
-                  float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)n * p.osn;
+              for (int j = 0; j < FC; ++j) tile[lane * (FC + 1) + j] = f[j];
+              __syncwarp();
+              const int col = lane % FC, rsub = lane / FC;
+              const int n = nb + col;
+              if (n < p.N) {
+                float* o = reinterpret_cast<float*>(p.out) + zoff + (long long)n * p.osn;
 #pragma unroll 8
-                  for (int r = rsub; r < 32; r += 32 / FC) {
-                    if (mrow0 + r < p.M) atomicAdd(o + (long long)(mrow0 + r) * p.osm, tile[r * (FC + 1) + col]);
-                  }
+                for (int r = rsub; r < 32; r += 32 / FC) {
+                  if (mrow0 + r < p.M) atomicAdd(o + (long long)(mrow0 + r) * p.osm, tile[r * (FC + 1) + col]);
                 }
               }
             }
@@ -523,11 +546,11 @@ int launch(const KParams& kp, dim3 grid, cudaStream_t st) {
     attr_set = true;
   }
   if (MC == 1) {
-    gemm_kernel<BN, MC><<<grid, 192, Cfg<BN>::SMEM_BYTES, st>>>(kp);
+    gemm_kernel<BN, MC><<<grid, Cfg<BN>::THREADS, Cfg<BN>::SMEM_BYTES, st>>>(kp);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(192, 1, 1);
+    cfg.blockDim = dim3(Cfg<BN>::THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
