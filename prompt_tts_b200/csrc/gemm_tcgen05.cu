@@ -10,6 +10,8 @@
 // serves forward (K-major x K-major), data-gradient (K-major x MN-major) and weight-gradient
 // (MN-major x MN-major, contraction over rows and batch) GEMMs, k=3 convolutions as three shifted
 // segments (TMA out-of-bounds zero fill = conv padding), and the batched attention contractions.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -560,6 +562,21 @@ int launch(const KParams& kp, dim3 grid, cudaStream_t st) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // the schedule strides by the number of clusters launched, so never launch more than can be resident at once (a GPC whose SM
+    // count is not a multiple of the cluster size leaves SMs unused)
+    static int max_clusters = 0;
+    if (!max_clusters) {
+      int n = 0;
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3((unsigned)(pt_num_sms_physical() / MC * MC), 1, 1);
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, MC>, &q) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = pt_num_sms_physical() / MC;
+      }
+      max_clusters = n;
+      if (getenv("PT_GEMM_DEBUG")) fprintf(stderr, "[pt_gemm] BN=%d cluster=%d: %d clusters resident at once\n", BN, MC, n);
+    }
+    if ((int)grid.x / MC > max_clusters) cfg.gridDim = dim3((unsigned)(max_clusters * MC), 1, 1);
     PT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, MC>, kp));
   }
   PT_LAUNCH_CHECK();
@@ -613,10 +630,11 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
     if (b_used[i]) PT_REQUIRE(g->b[i].kmajor == kp.b_kmajor, "pt_gemm: B operands must share one majorness");
   }
 
-  // tile width: cost model fitted to tools/gemm_sweep.py on B200 (profiles/r01_gemm_sweep.txt).  One k-iteration (BK = 64) of a
-  // 128 x bn tile costs ~800 / 640 / 430 / 260 cycles for bn = 256 / 160 / 128 / 64 (operand delivery from L2 dominates,
-  // which favours wide tiles).  Data-parallel launches are paced by the busiest SM (ceil(tiles / SMs) tiles); stream-K
-  // launches are balanced but pay one atomic flush of a tile per segment (~0.65 cycles per flushed column-row).
+  // tile width: cost model fitted to tools/gemm_sweep.py on B200 (profiles/r01_gemm_sweep_v3.txt).  One k-iteration (BK = 64) of a
+  // 128 x bn tile costs ~800 / 730 / 660 / 640 / 430 / 260 cycles for bn = 256 / 224 / 192 / 160 / 128 / 64 (each SM ingests
+  // operands at ~64 B/clk, which favours wide tiles).  Data-parallel launches are paced by the busiest SM (ceil(tiles / SMs)
+  // tiles); stream-K launches are balanced but pay one atomic flush of a tile per segment (~0.65 cycles per flushed column-row),
+  // and their 64-wide tiles (MN-major operands, two CTAs per SM sharing the flush path) run ~1.6x slower than that table.
   const bool streamk = g->out_dtype == PT_OUT_F32_ATOMIC_ADD;
   PT_REQUIRE(!streamk || (g->bias == nullptr && g->bias_z2 == nullptr && g->residual == nullptr),
              "pt_gemm: PT_OUT_F32_ATOMIC_ADD outputs are scheduled stream-K and take no bias/residual");
@@ -628,19 +646,17 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   if (bn == 0) {
     // 224 / 192 exist for wave quantisation: when a narrower tile keeps the number of waves, every wave gets shorter
     const int cand[6] = {256, 224, 192, 128, 64, 160};
-    const double cyc[6] = {mt >= 2 && allow_cluster && !streamk ? 780.0 : 800.0, 730.0, 660.0, 430.0, 260.0, 640.0};
+    const double cyc[6] = {mt >= 2 && allow_cluster && !streamk ? 780.0 : 800.0, 730.0, 660.0, 430.0, streamk ? 416.0 : 260.0, 640.0};
     double best = 1e300;
     for (int i = 0; i < 6; ++i) {
       const int c = cand[i];
-      if (c == 160 && !(g->N % 160 == 0 && g->N % 128 != 0 && g->N <= 640)) continue;   // only where it removes ragged waste
-      if ((c == 224 || c == 192) && streamk) continue;                                  // stream-K launches have no waves to quantise
       const long long tiles_c = mt * ((g->N + c - 1) / c) * zz;
       double cost;
       if (streamk) {
         const double slots_c = (double)sms * (c <= 128 ? 2 : 1);
         cost = (double)tiles_c * (double)total * cyc[i] / sms + 0.65 * ((double)tiles_c + slots_c) * c;
       } else {
-        cost = (double)((tiles_c + sms - 1) / sms) * ((double)total * cyc[i] + 1500.0);
+        cost = (double)((tiles_c + sms - 1) / sms) * ((double)total * cyc[i] + 500.0);
       }
       if (cost < best * 0.97) {   // ties go to the earlier (wider) candidate
         best = cost;
@@ -652,6 +668,8 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
 
   // clusters of two CTAs (TMA multicast of the B tile) for the 256-wide tiles whenever there are two row tiles to pair
   // (measured: +1-3 % on the large data-parallel shapes, -4 % on stream-K ones, so only the former use it)
+  // (a cluster of four sharing B in quarters was measured too: 24064 x 2560 x 320 67 -> 74 us, 6016 x 3840 x 1280 57 -> 64 us --
+  // what limits the mainloop is each SM's own ingest rate, ~64 B/clk, which multicast does not change)
   const int mc = (bn == 256 && mt >= 2 && allow_cluster && !streamk) ? 2 : 1;
   for (int i = 0; i < 2; ++i) {
     if (a_used[i]) {
