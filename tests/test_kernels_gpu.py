@@ -209,6 +209,14 @@ def test_geglu_add_upsample_copy(cuda):
     yr = a * F.gelu(gt)
     yr.backward(dy.float())
     assert rel(y, yr) < 5e-3 and rel(ops.geglu_bwd(dy, u), ur.grad) < 6e-3
+    for (Mg, Fg) in [(20011, 1280), (70, 8)]:   # more items than one grid sweep (two items per thread in flight) and a tiny one
+        ub = bf(torch.randn(Mg, 2 * Fg, device=cuda, generator=g))
+        dyb = bf(torch.randn(Mg, Fg, device=cuda, generator=g))
+        ubr = ub.float().requires_grad_(True)
+        ab, gb = ubr.chunk(2, -1)
+        ybr = ab * F.gelu(gb)
+        ybr.backward(dyb.float())
+        assert rel(ops.geglu_fwd(ub), ybr) < 5e-3 and rel(ops.geglu_bwd(dyb, ub), ubr.grad) < 6e-3
     a2, b2 = bf(torch.randn(64, 320, device=cuda, generator=g)), bf(torch.randn(64, 320, device=cuda, generator=g))
     assert rel(ops.add_(a2, b2), a2.float() + b2.float()) < 5e-3
     x = bf(torch.randn(2, 47, 64, device=cuda, generator=g))
