@@ -40,6 +40,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 struct alignas(64) KParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB[2];
+  CUtensorMap tmO;      // bf16 output as (N, M, z2, z3), box 32 x 32, SWIZZLE_64B: the epilogue stores through TMA
   pt_segment_t seg[8];
   int nseg;
   int a_kmajor, b_kmajor;
@@ -73,11 +74,11 @@ struct Cfg {
   static constexpr int EPI_SPLIT = EPI_WARPS / 4;        // warps sharing one lane quarter
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int EPI_COLS = 32;                     // columns per epilogue pass
-  static constexpr int EPI_BF16_BYTES = EPI_WARPS * 32 * (EPI_COLS * 2 + 16);
+  static constexpr int EPI_BF16_BYTES = EPI_WARPS * 32 * EPI_COLS * 2;   // one dense 32 x 32 bf16 store tile per warp
   static constexpr int EPI_F32_BYTES = EPI_WARPS * 32 * 17 * 4;   // fp32 transpose tile per warp: 32 x 16 (+1)
   static constexpr int EPI_BYTES = EPI_BF16_BYTES > EPI_F32_BYTES ? EPI_BF16_BYTES : EPI_F32_BYTES;
   static constexpr int F32_COLS = 16;   // columns per transpose pass of the atomic epilogue
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;     // keeps the epilogue staging 512-byte aligned (period of the 64-byte swizzle)
   static constexpr int BIAS_BYTES = 1024;
   static constexpr int AUX_BYTES = 1024 /*align slack*/ + BAR_BYTES + BIAS_BYTES + EPI_BYTES;
   static constexpr int STAGES_FIT = (227 * 1024 / CTAS_PER_SM - AUX_BYTES) / STAGE_BYTES;
@@ -334,19 +335,21 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
         // ---- bf16 output (+ optional bf16 residual): every global access is a full 64/128-byte row segment.
         // Accumulator rows live one per thread; a warp-private padded smem tile transposes between "thread = row"
         // and "8 (or 4) lanes = one contiguous row segment".
-        constexpr int CH = C::EPI_COLS;            // columns per pass
+        constexpr int CH = C::EPI_COLS;            // columns per pass (32: one 64-byte row segment)
         constexpr int NPASS = BN / CH;
         constexpr int NPH = (NPASS + ES - 1) / ES; // passes per warp
-        constexpr int VPR = CH / 8;                // 16-byte vectors per row segment
-        constexpr int RPI = 32 / VPR;              // rows covered by one warp-wide access
-        constexpr int NIT = 32 / RPI;              // accesses per pass
-        constexpr int PITCH = CH * 2 + 16;         // bytes, padded: conflict-free for both access patterns
-        uint8_t* stg = sepi + ew * (32 * PITCH);
+        constexpr int VPR = CH / 8;                // 16-byte vectors per row segment (4)
+        constexpr int RPI = 32 / VPR;              // rows covered by one warp-wide residual load
+        constexpr int NIT = 32 / RPI;              // residual loads per pass
+        // Store tile of this warp: 32 rows x 64 bytes, dense, in the SWIZZLE_64B pattern of the output tensor map (16-byte chunk
+        // index ^= address bits 7-8), which also makes the row-per-thread writes below bank-conflict free.  One elected lane hands
+        // the tile to TMA: no LDS / STG / 64-bit address arithmetic / tail predicates in the epilogue (tails are clipped by TMA).
+        uint8_t* stg = sepi + ew * (32 * CH * 2);
+        const uint32_t stg_u32 = smem_u32(stg);
+        auto cell = [&](int row, int chunk) { return stg + row * (CH * 2) + ((chunk ^ ((row >> 1) & 3)) << 4); };
         const int mw = m0 + q * 32;                // first row of this warp
         const int crow = lane / VPR, cvec = lane % VPR;
-        const long long zoff_o = (long long)z2 * p.osz2 + (long long)z3 * p.osz3;
         const long long zoff_r = (long long)z2 * p.rsz2 + (long long)z3 * p.rsz3;
-        bf16* outp = reinterpret_cast<bf16*>(p.out);
         const bool has_res = p.res != nullptr;
         const int last_c = min(NPASS, (p.N - n0 + CH - 1) / CH) - 1;   // last pass with columns inside N
         const int last_k = last_c >= half ? (last_c - half) / ES : -1;  // this warp's last pass (pass index = half + k * ES)
@@ -384,9 +387,11 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
               mbar_arrive(tmem_empty_bar(acc));
             }
-            if (has_res) {
+            if (lane == 0) tma_store_wait_read();   // the previous store of this warp has finished reading the tile
+            __syncwarp();
+            if (has_res) {   // residual rows arrive coalesced (8 rows x 64 bytes per access) and are re-read row-per-thread
 #pragma unroll
-              for (int i = 0; i < NIT; ++i) st16(stg + (crow + i * RPI) * PITCH + cvec * 16, rr[k & 1][i]);
+              for (int i = 0; i < NIT; ++i) st16(cell(crow + i * RPI, cvec), rr[k & 1][i]);
               __syncwarp();
             }
             const float* sb = sbias + c * CH;
@@ -397,9 +402,9 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
               float f[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(v[k & 1][g * 8 + j]), p.alpha, bs[j]);
-              uint8_t* cell = stg + lane * PITCH + g * 16;   // this thread's row, vector g
+              uint8_t* mine = cell(lane, g);       // this thread's row, vector g
               if (has_res) {
-                const bf16x8 t = ld16(cell);
+                const bf16x8 t = ld16(mine);
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                   const float2 u = bf2_to_f2(t.w[h]);
@@ -410,15 +415,13 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
               bf16x8 t;
 #pragma unroll
               for (int h = 0; h < 4; ++h) t.w[h] = f2_to_bf2(f[2 * h], f[2 * h + 1]);
-              st16(cell, t);
+              st16(mine, t);
             }
+            fence_proxy_async_smem();
             __syncwarp();
-            const int ncol = nb + cvec * 8;
-#pragma unroll
-            for (int i = 0; i < NIT; ++i) {
-              const int m = mw + crow + i * RPI;
-              if (m < p.M && ncol < p.N)
-                st16(outp + zoff_o + (long long)m * p.osm + ncol, ld16(stg + (crow + i * RPI) * PITCH + cvec * 16));
+            if (lane == 0) {
+              tma_store_4d(&p.tmO, stg_u32, nb, mw, z2, z3);
+              tma_store_commit();
             }
           }
         }
@@ -495,6 +498,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
       }
       ++segi;
     }
+    if (lane == 0) tma_store_wait_all();   // this warp's output tiles have left shared memory and are written
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -535,6 +539,35 @@ int encode_operand(CUtensorMap* tm, const pt_operand_t& op, int box_rows_kmajor,
     pt_set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d (dims %lld,%lld,%lld,%lld strides %lld,%lld,%lld box %u,%u)", name, (int)r,
                  (long long)dims[0], (long long)dims[1], (long long)dims[2], (long long)dims[3], (long long)strides[0],
                  (long long)strides[1], (long long)strides[2], box[0], box[1]);
+    return PT_ECUDA;
+  }
+  return PT_OK;
+}
+
+// bf16 output as a rank-4 tensor (N, M, z2, z3) for the epilogue's TMA stores: box 32 x 32, SWIZZLE_64B
+int encode_output(CUtensorMap* tm, const pt_gemm_t* g) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    pt_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return PT_ECUDA;
+  }
+  PT_REQUIRE((reinterpret_cast<uintptr_t>(g->out) & 15) == 0, "pt_gemm: bf16 output base not 16-byte aligned");
+  const long long ext[4] = {g->N, g->M, g->nz2, g->nz3};
+  const long long str[4] = {1, g->out_stride_m, g->out_stride_z2, g->out_stride_z3};
+  cuuint64_t dims[4], strides[3];
+  for (int i = 0; i < 4; ++i) dims[i] = (cuuint64_t)ext[i];
+  for (int i = 1; i < 4; ++i) {
+    long long st = str[i];
+    if (ext[i] == 1 && (st <= 0 || (st % 8) != 0)) st = 8;  // irrelevant axis, keep the encoder happy
+    PT_REQUIRE(st > 0 && st % 8 == 0, "pt_gemm: bf16 output stride[%d]=%lld must be a positive multiple of 8 elements", i, st);
+    strides[i - 1] = (cuuint64_t)st * 2;
+  }
+  cuuint32_t box[4] = {32, 32, 1, 1}, estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, g->out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    pt_set_error("cuTensorMapEncodeTiled(out) failed: CUresult %d (dims %lld,%lld,%lld,%lld strides %lld,%lld,%lld)", (int)r, ext[0], ext[1],
+                 ext[2], ext[3], (long long)strides[0], (long long)strides[1], (long long)strides[2]);
     return PT_ECUDA;
   }
   return PT_OK;
@@ -682,6 +715,9 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
       if (r) return r;
       kp.b_batched[i] = g->b[i].batched;
     }
+  }
+  if (g->out_dtype == PT_OUT_BF16) {
+    if (int r = encode_output(&kp.tmO, g)) return r;
   }
   kp.nseg = g->nseg;
   kp.M = g->M;
