@@ -101,7 +101,9 @@ typedef struct {
   /* epilogue:  out = alpha * acc + bias[n] + bias_z2[z2, n] + residual[z2,z3,m,n] */
   void* out;
   int32_t out_dtype;
-  int64_t out_stride_m, out_stride_z2, out_stride_z3; /* elements */
+  int64_t out_stride_m, out_stride_z2, out_stride_z3; /* elements.  PT_OUT_BF16: `out` 16-byte aligned, N and the strides multiples
+                                                        * of 8 -- the tiles are written by TMA stores through a rank-4 tensor map
+                                                        * (N, M, nz2, nz3); `residual` may alias `out` (in-place accumulation) */
   float alpha;
   const float* bias;       /* [N] fp32 or NULL */
   const float* bias_z2;    /* [nz2, >=N] fp32 rows of stride bias_z2_stride, or NULL (time-embedding shift) */
