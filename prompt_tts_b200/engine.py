@@ -17,7 +17,6 @@ import torch
 from . import ops
 from .ops import BF16, F32, OUT_BF16, OUT_F32, OUT_F32_ATOMIC_ADD
 
-_NUM_SMS = 148
 
 
 class Var:

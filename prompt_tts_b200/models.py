@@ -4,7 +4,6 @@ config dict, has the same forward signature and the same 740 state_dict entries,
 unchanged; one forward = one tape over hand-written sm_100a kernels."""
 from __future__ import annotations
 
-import math
 from typing import Any, Dict, Optional, Union
 
 import numpy as np

@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import torch
 
-from . import engine as E
 from . import ops
 
 
