@@ -128,3 +128,16 @@ def test_reference_arm_prints_one_json_line():
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_flop_count_matches_the_survey():
+    """tools/count_flops.py walks the module tree of the full config: the roofline denominators of SURVEY 8(d)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import count_flops
+    from prompt_tts_b200.models import TTSSingleSpeaker
+    model = TTSSingleSpeaker(load_cfg("1d_config"))
+    text, unet = count_flops.forward_flops(model, 752, 550)
+    assert abs(text / 1e9 - 45.2) < 0.1 and abs(unet / 1e9 - 218.2) < 0.1          # 263.4 GFLOP forward per sample
+    assert abs(3 * (text + unet) * 32 / 1e12 - 25.29) < 0.01                       # one train step at batch 32
+    text2, unet2 = count_flops.forward_flops(model, 1504, 550)
+    assert abs(unet2 / 1e9 - 428.0) < 0.1 and abs((text2 + 100 * unet2) / 1e12 - 42.84) < 0.01   # sampling, per utterance
