@@ -337,6 +337,10 @@ def run_ours(args):
             line["sampling"] = sampling_rtf(model, cfg, dev, torch, peak)
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_step_time(2, 1)
+            try:
+                cb["rvq"] = cpu_rvq_baseline()
+            except Exception as e:   # a baseline figure must never take the bench line down
+                cb["rvq"] = {"unavailable": str(e)[:120]}
             line["cpu_baseline"] = cb
         emit(line)
     if world > 1:
@@ -374,6 +378,26 @@ def sampling_rtf(model, cfg, dev, torch, peak_tflops):
             "tflops": flop / sec / 1e12, "frac_of_tensor_roofline": flop / sec / 1e12 / peak_tflops,
             "finite": bool(torch.isfinite(x).all().item()),
             "note": "includes the one eager warm-up forward and the graph capture of the loop (first two of the 100 steps)"}
+
+
+def cpu_rvq_baseline(n_clips=2, T=900):
+    """the RVQ oracle (oracle/rvq_oracle.c: scalar exact-fp32 restatement of encodec's quantiser, one host core) on a
+    bounded sample of config 5 -- a reported baseline, only ever run from the cpu_baseline leg."""
+    import time
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import rvq_oracle
+    rs = np.random.RandomState(0)
+    cb = rs.standard_normal((8, 1024, 128)).astype(np.float32)
+    lat = rs.standard_normal((n_clips, 128, T)).astype(np.float32)
+    t0 = time.perf_counter()
+    codes = rvq_oracle.encode(lat, cb)
+    t1 = time.perf_counter()
+    for _ in range(20):
+        rvq_oracle.decode(codes, cb)
+    t2 = time.perf_counter()
+    return {"encode_frames_per_s": n_clips * T / (t1 - t0), "decode_frames_per_s": 20 * n_clips * T / (t2 - t1), "cores": 1, "kind": "port",
+            "sample": f"{n_clips} clips x {T} frames, 8 x 1024 x 128 codebooks; oracle/rvq_oracle.c"}
 
 
 def rvq_throughput(dev, torch, ops, hbm_gbs):
