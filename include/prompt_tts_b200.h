@@ -237,6 +237,22 @@ int pt_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
 int pt_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   float wd, int step, const float* gnorm_sq, float max_norm, float gscale, void* stream);
 
+
+/* Graph-safe variant: everything that changes between steps lives in device memory, so a captured step replays correctly.
+ * `state` = PT_OPT_STATE_FLOATS fp32 words.  The host writes the hyper-parameter slots (an LR scheduler may rewrite PT_OPT_LR at any
+ * time, outside the graph); pt_adamw_prepare increments the step counter (an int32 stored in slot PT_OPT_STEP), evaluates the bias
+ * corrections in double precision and the clip factor min(1, max_norm / (sqrt(*gnorm_sq) * gscale + 1e-6)) * gscale, and leaves
+ * them in the coefficient slots that pt_adamw_step_dev reads.  `g` is fp32, or bf16 when g_is_bf16 (gradients all-reduced in
+ * bf16).  `w_bf16` (optional) receives bf16(p) in the same flat layout: the GEMM weight operands are views of it (no re-pack). */
+enum {
+  PT_OPT_LR = 0, PT_OPT_BETA1, PT_OPT_BETA2, PT_OPT_EPS, PT_OPT_WD, PT_OPT_MAX_NORM, PT_OPT_GSCALE, PT_OPT_STEP,
+  PT_OPT_CLIP, PT_OPT_STEP_SIZE, PT_OPT_INV_SQRT_BC2, PT_OPT_DECAY, PT_OPT_GNORM, PT_OPT_STATE_FLOATS = 16
+};
+int pt_sumsq_bf16(const void* x, int64_t n, float* out, void* stream);
+int pt_adamw_prepare(float* state, const float* gnorm_sq, void* stream);
+int pt_adamw_step_dev(float* p, const void* g, int g_is_bf16, float* m, float* v, void* w_bf16, int64_t n, const float* state,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

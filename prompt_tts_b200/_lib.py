@@ -130,6 +130,9 @@ _SIGS = {
     "codes_affine_inv": "pplp",
     "sumsq_f32": "plpp",
     "adamw_step": "pppplfffffipffp",
+    "sumsq_bf16": "plpp",
+    "adamw_prepare": "ppp",
+    "adamw_step_dev": "ppippplpp",
 }
 _CT = {"p": C.c_void_p, "i": C.c_int, "l": C.c_int64, "f": C.c_float}
 EXPORTS = ["pt_version", "pt_last_error", "pt_launch_count"] + ["pt_" + k for k in _SIGS]

@@ -134,12 +134,18 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   auto s_empty = [&](int s) { return bar0 + 8u * (9 + s); };
   auto x_full = [&](int g, int slot) { return bar0 + 8u * (17 + g * 2 + slot); };
   auto x_empty = [&](int g, int slot) { return bar0 + 8u * (21 + g * 2 + slot); };
-  auto t_full = [&](int g) { return bar0 + 8u * (25 + g); };                       // P / dS of group g are in TMEM
-  auto p_empty = [&](int g, int slot) { return bar0 + 8u * (27 + g * 2 + slot); };  // stage 2 has consumed them: the X slot may be refilled
-  const uint32_t acc_full = bar0 + 8u * 31;
-  const uint32_t acc_empty = bar0 + 8u * 32;
-  const uint32_t r_empty = bar0 + 8u * 33;
-  const uint32_t tmem_slot = bar0 + 8u * 34;
+  // P / dS of group g, X slot `slot`, are in TMEM.  One barrier PER SLOT: with two X slots the warps of a group may be a tile apart
+  // (a warp that takes the rescale path waits on p_empty and does a TMEM round trip while the other three go on to the next tile,
+  // whose logits are already in the other slot); on a single per-group barrier the fast warps' arrivals for tile k+1 completed the
+  // phase of tile k, and stage 2 consumed P rows the slow warp had not written yet (round-1 `full_d40_self` NaN: always the 32 rows
+  // of one warp, only with inputs that trigger rescales).  Per slot, a warp cannot arrive for tile k+2 before stage 2 of tile k.
+  auto t_full = [&](int g, int slot) { return bar0 + 8u * (25 + g * 2 + slot); };
+  auto p_empty = [&](int g, int slot) { return bar0 + 8u * (29 + g * 2 + slot); };  // stage 2 has consumed them: the X slot may be refilled
+  const uint32_t acc_full = bar0 + 8u * 33;
+  const uint32_t acc_empty = bar0 + 8u * 34;
+  const uint32_t r_empty = bar0 + 8u * 35;
+  constexpr int TMEM_SLOT_IDX = 36;
+  const uint32_t tmem_slot = bar0 + 8u * TMEM_SLOT_IDX;
   float* sstat = reinterpret_cast<float*>(sgen + C::OFF_STAT);          // DKV: [2][STAT_COLS] column statistics of the work item
   float* sred = sstat + (MODE == MODE_DKV ? 2 * C::STAT_COLS : 0);      // [2][BM]
 
@@ -171,8 +177,8 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
         mbar_init(x_full(s, u), 1);
         mbar_init(x_empty(s, u), 128);
         mbar_init(p_empty(s, u), 1);
+        mbar_init(t_full(s, u), 128);
       }
-      mbar_init(t_full(s), 128);
     }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 256);
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * 34);
+  const uint32_t tmem = *reinterpret_cast<uint32_t*>(sgen + C::OFF_BAR + 8 * TMEM_SLOT_IDX);
   // X buffers: FWD gives each group two 64-column slots (stage 1 runs a whole tile ahead of the group); the backward
   // modes need X1 | X2 per tile and have TMEM for one 128-column buffer per group only
   auto xcol = [&](int g, int slot_or_x) { return (uint32_t)(MODE == MODE_FWD ? (g * XSLOTS + slot_or_x) * BN : g * C::XW + slot_or_x * BN); };
@@ -315,16 +321,15 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     const uint64_t dSmn = umma_desc(sS, BN * 128, 1024);   // streamed tiles, MN-major view
     int s2 = 0;
     int tu0 = 0, tu1 = 0;   // t_full phases consumed so far, per group
-    int kf0 = 0, kf1 = 0;   // FWD: X fills of earlier work items, per group (slot = fill & 1)
     int wi = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
       mbar_wait(acc_empty, (wi & 1) ^ 1);                    // the epilogue of the previous work item has drained the accumulators
       fence_after();
       for (int j = 0; j < n_tiles; ++j) {
         const int g = gsel(j);
-        const int use = (g ? tu1 : tu0) + (XBUF == 2 ? (j >> 1) : j);
-        const int slot = (MODE == MODE_FWD && XSLOTS == 2) ? (((g ? kf1 : kf0) + (j >> 1)) & 1) : 0;
-        mbar_wait(t_full(g), use & 1);
+        const int use = (g ? tu1 : tu0) + (XBUF == 2 ? (j >> 1) : j);      // fills of this group's X so far (== kf for FWD)
+        const int slot = (MODE == MODE_FWD && XSLOTS == 2) ? (use & 1) : 0;
+        mbar_wait(t_full(g, slot), ((MODE == MODE_FWD && XSLOTS == 2) ? (use >> 1) : use) & 1);
         fence_after();
         if (leader) {
           const uint64_t bS = dSmn + (uint64_t)(s2 * (C::STAGE_BYTES >> 4));
@@ -350,8 +355,6 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       }
       tu0 += per_g0;
       tu1 += per_g1;
-      kf0 += per_g0;
-      kf1 += per_g1;
     }
   } else {
     // ------------------------------------------------------------------ transform groups (warps 2-5, 6-9)
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
           }
           tmem_wait_st();
           fence_before();
-          mbar_arrive(t_full(g));
+          mbar_arrive(t_full(g, slot));
         }
         // ---- merge the two groups: M = max(m_0, m_1), w_g = exp2((m_g - M) c), L = sum w_g l_g, O = sum w_g O_g / L
         sred[(g * BM + row) * 2] = m;
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
             }
             tmem_wait_st();
             fence_before();
-            mbar_arrive(t_full(g));
+            mbar_arrive(t_full(g, 0));
           }
         // ---- epilogue: accumulators -> bf16 rows
         mbar_wait(acc_full, wi & 1);

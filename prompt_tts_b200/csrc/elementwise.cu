@@ -481,6 +481,87 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 }
 
 
+// ---- graph-safe optimiser state: everything that changes from step to step lives in device memory, so one captured step replays
+// correctly.  `st` = PT_OPT_STATE_FLOATS fp32 words (see include/prompt_tts_b200.h): hyper-parameters written by the host (or by an LR
+// scheduler, at any time), the step counter incremented HERE, and the per-step coefficients the elementwise kernel reads.
+__global__ void adamw_prepare_kernel(float* __restrict__ st, const float* __restrict__ gnorm_sq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float lr = st[PT_OPT_LR], b1 = st[PT_OPT_BETA1], b2 = st[PT_OPT_BETA2], wd = st[PT_OPT_WD], max_norm = st[PT_OPT_MAX_NORM],
+              gscale = st[PT_OPT_GSCALE];
+  const int step = __float_as_int(st[PT_OPT_STEP]) + 1;
+  st[PT_OPT_STEP] = __int_as_float(step);
+  // torch.optim.AdamW: bias_correction = 1 - beta ** step (python doubles)
+  const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+  float clip = gscale;
+  float norm = 0.f;
+  if (gnorm_sq != nullptr) {
+    norm = sqrtf(*gnorm_sq) * gscale;
+    if (max_norm > 0.f) clip *= fminf(1.f, max_norm / (norm + 1e-6f));   // torch.nn.utils.clip_grad_norm_
+  }
+  st[PT_OPT_CLIP] = clip;
+  st[PT_OPT_STEP_SIZE] = (float)((double)lr / bc1);
+  st[PT_OPT_INV_SQRT_BC2] = (float)(1.0 / sqrt(bc2));
+  st[PT_OPT_DECAY] = 1.f - lr * wd;
+  st[PT_OPT_GNORM] = norm;
+}
+
+// p, g, m, v fp32 flat buffers in one common layout; w (optional) the bf16 shadow of p in the same layout: the GEMM operands are
+// views of it, so the updated weights need no re-pack pass.  4 elements per thread per iteration (n % 4 == 0).
+template <bool G_BF16>
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float* __restrict__ p, const void* __restrict__ gv, float* __restrict__ m,
+                                                        float* __restrict__ v, bf16* __restrict__ w, long long n4,
+                                                        const float* __restrict__ st) {
+  const float clip = st[PT_OPT_CLIP], step_size = st[PT_OPT_STEP_SIZE], isb2 = st[PT_OPT_INV_SQRT_BC2], decay = st[PT_OPT_DECAY];
+  const float b1 = st[PT_OPT_BETA1], b2 = st[PT_OPT_BETA2], eps = st[PT_OPT_EPS];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pi = reinterpret_cast<const float4*>(p)[i];
+    float4 mi = reinterpret_cast<const float4*>(m)[i];
+    float4 vi = reinterpret_cast<const float4*>(v)[i];
+    float gi[4];
+    if (G_BF16) {
+      const uint2 t = reinterpret_cast<const uint2*>(gv)[i];
+      const float2 a = bf2_to_f2(t.x), b = bf2_to_f2(t.y);
+      gi[0] = a.x, gi[1] = a.y, gi[2] = b.x, gi[3] = b.y;
+    } else {
+      const float4 t = reinterpret_cast<const float4*>(gv)[i];
+      gi[0] = t.x, gi[1] = t.y, gi[2] = t.z, gi[3] = t.w;
+    }
+    float pp[4] = {pi.x, pi.y, pi.z, pi.w}, mm[4] = {mi.x, mi.y, mi.z, mi.w}, vv[4] = {vi.x, vi.y, vi.z, vi.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = gi[j] * clip;
+      const float pd = pp[j] * decay;
+      mm[j] = b1 * mm[j] + (1.f - b1) * g;
+      vv[j] = b2 * vv[j] + (1.f - b2) * g * g;
+      const float denom = sqrtf(vv[j]) * isb2 + eps;
+      pp[j] = pd - step_size * (mm[j] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (w != nullptr) reinterpret_cast<uint2*>(w)[i] = make_uint2(f2_to_bf2(pp[0], pp[1]), f2_to_bf2(pp[2], pp[3]));
+  }
+}
+
+__global__ void sumsq_bf16_kernel(const bf16* __restrict__ x, long long n8, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    load8(x + i * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(f[j], f[j], acc);
+  }
+  acc = warp_sum(acc);
+  __shared__ float sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
 // DDPM ancestral step (diffusers 0.15 DDPMScheduler.step, epsilon prediction, clip_sample, fixed_small variance):
 //   x0 = clamp((x_t - sqrt(1-acp_t) eps) / sqrt(acp_t), -1, 1);  x_prev = c_x0 * x0 + c_xt * x_t + sigma * noise
 // with optional in-painting of the first `keep` frames of every [C, T] plane from `known` (speech-prompt protocol of the sampler).
@@ -692,6 +773,30 @@ extern "C" int pt_adamw_step(float* p, const float* g, float* m, float* v, int64
   PT_REQUIRE(n > 0 && step >= 1, "adamw: n=%lld step=%d", (long long)n, step);
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<grid_for(n, 1024, 4), 256, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, gnorm_sq, max_norm, gscale);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+
+extern "C" int pt_sumsq_bf16(const void* x, int64_t n, float* out, void* stream) {
+  PT_REQUIRE(n > 0 && n % 8 == 0, "sumsq_bf16: n=%lld must be a positive multiple of 8", (long long)n);
+  sumsq_bf16_kernel<<<grid_for(n / 8, 1024, 4), 256, 0, ST>>>((const bf16*)x, n / 8, out);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+extern "C" int pt_adamw_prepare(float* state, const float* gnorm_sq, void* stream) {
+  PT_REQUIRE(state != nullptr, "adamw_prepare: null state");
+  adamw_prepare_kernel<<<1, 32, 0, ST>>>(state, gnorm_sq);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+extern "C" int pt_adamw_step_dev(float* p, const void* g, int g_is_bf16, float* m, float* v, void* w_bf16, int64_t n, const float* state,
+                                 void* stream) {
+  PT_REQUIRE(n > 0 && n % 4 == 0, "adamw_step_dev: n=%lld must be a positive multiple of 4", (long long)n);
+  PT_REQUIRE(p && g && m && v && state, "adamw_step_dev: null pointer");
+  if (g_is_bf16)
+    adamw_dev_kernel<true><<<grid_for(n / 4, 1024, 4), 256, 0, ST>>>(p, g, m, v, (bf16*)w_bf16, n / 4, state);
+  else
+    adamw_dev_kernel<false><<<grid_for(n / 4, 1024, 4), 256, 0, ST>>>(p, g, m, v, (bf16*)w_bf16, n / 4, state);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }

@@ -29,7 +29,14 @@ def _oracle_autocast(cfg, sd, inp):
     return {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
 
 
-@pytest.mark.parametrize("cfg_name,B,T", [("tiny", 2, 16), ("tiny3", 3, 32), ("tiny3", 2, 136)])
+# Sizes: the two toy configs at >= 272 (batch x frame) positions, `mid` = the real level-0/1 widths (320 / 640 channels, head dims
+# 40 / 80, GroupNorm groups of 10 / 20 channels, 768-d text context) and `1d_config` = BASELINE.json's model at B = 2, T = 752
+# (4 levels, head dims 40 / 80 / 160, Lk = 550, stream-K weight gradients).  Measured on B200 (gpurun_out/r2a, r2b; out / global
+# gradient): tiny 8x64 1.2e-2 / 1.0e-2, tiny3 2x136 1.2e-2 / 1.4e-2, tiny3 8x128 1.3e-2 / 0.9e-2, mid 2x64 1.1e-2 / 1.1e-2,
+# 1d_config 2x752 1.1e-2 / 0.8e-2.  With fewer than ~100 positions per weight-gradient sum (tiny3 3x32: 2.07e-2, tiny 2x16: 1.95e-2;
+# the reference's own torch.autocast(bf16) run: 2.30e-2 / 2.45e-2) bf16 rounding noise does not average out and NO bf16 path meets
+# 2e-2, which is why the toy cases are not run that small; the bar itself is not relaxed anywhere.
+@pytest.mark.parametrize("cfg_name,B,T", [("tiny", 8, 64), ("tiny3", 2, 136), ("tiny3", 8, 128), ("mid", 2, 64), ("1d_config", 2, 752)])
 def test_full_model_fwd_bwd(cuda, cfg_name, B, T):
     from prompt_tts_b200.models import TTSSingleSpeaker
     cfg = load_cfg(cfg_name)
@@ -67,10 +74,8 @@ def test_full_model_fwd_bwd(cuda, cfg_name, B, T):
     gac = torch.cat([ac[k].flatten() for _, k in worst])
     e_ac = rel(gac, gr)
     print(f"\n[{cfg_name} B={B} T={T}] out {e_out:.2e} grad(all) {e_all:.2e} (reference under torch.autocast(bf16): {e_ac:.2e}) worst {worst[:4]}")
-    # north-star: 2e-2.  Where the reference's own bf16 run cannot meet 2e-2 against its fp32 self (tiny batches sit at
-    # the bf16 rounding floor), the bar is to be no noisier than the reference's bf16 run.
-    limit = TOL if e_ac <= TOL else e_ac
-    assert e_all < limit, f"global grad rel err {e_all} (limit {limit}, reference autocast {e_ac})"
+    # north-star: 2e-2 on outputs AND gradients, no escape clause
+    assert e_all < TOL, f"global grad rel err {e_all} (reference under autocast: {e_ac})"
     # per-tensor outliers: small tensors deep in the net carry the largest bf16 noise; bound them by the error the
     # reference itself shows when it runs under torch.autocast(bf16) on the same inputs (x3), or 5e-2, whichever is larger
     bad = [(e, k, rel(ac[k], ref_grads[k])) for e, k in worst if e > max(5e-2, 3 * rel(ac[k], ref_grads[k]))]
