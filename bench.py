@@ -161,11 +161,12 @@ def run_ours(args):
     cfg = load_cfg(CFG)
     torch.manual_seed(0)
     model = TTSSingleSpeaker(cfg).to(dev)
-    grad_sync = None
-    if world > 1:
-        from prompt_tts_b200.dp import GradSync
-        grad_sync = GradSync(model, world_size=world, bucket_mb=float(os.environ.get("PT_BUCKET_MB", "128")))
+    from prompt_tts_b200.dp import GradSync
+    from prompt_tts_b200.optim import FusedClipAdamW
+    comm_dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[os.environ.get("PT_COMM_DTYPE", "fp32")]
+    grad_sync = GradSync(model, world_size=world, bucket_mb=float(os.environ.get("PT_BUCKET_MB", "128")), comm_dtype=comm_dtype)
     stepper = DenoiserTrainStep(model, grad_sync=grad_sync)
+    opt = FusedClipAdamW(stepper)
     inp = synth(cfg, BATCH, T_FRAMES, 1000 + rank, dev)
     host = {k: v.cpu().pin_memory() for k, v in inp.items()}
     loss_buf = torch.zeros((), dtype=torch.float32, device=dev)
@@ -174,14 +175,15 @@ def run_ours(args):
     def step():
         return stepper(inp["x0"], inp["noise"], inp["t"], inp["ids"], inp["mask"], loss_out=loss_buf)
 
-    # launches per step (eager) + warm-up of caches / packed weights
+    # First step: defines the flat gradient layout.  Then the optimiser takes the parameters into its flat fp32 master buffer and its
+    # bf16 shadow -- the GEMM weight operands are views of the shadow from here on (what training runs with), so neither the timed
+    # fwd+bwd step nor the complete step contains a weight re-pack.
     lib = _lib.lib()
-    for _ in range(2):
-        for p in model.parameters():
-            p.grad = None
-        l0 = lib.pt_launch_count()
-        step()
-        launches_per_step = lib.pt_launch_count() - l0
+    step()
+    opt.attach()
+    l0 = lib.pt_launch_count()
+    step()
+    launches_per_step = lib.pt_launch_count() - l0
     torch.cuda.synchronize()
 
     # per-GEMM event timing over one eager step: the roofline of the dominant kernel family (tcgen05 GEMM)
@@ -190,16 +192,12 @@ def run_ours(args):
     use_graph = not args.no_graph
     graph = None
     if use_graph:
-        for p in model.parameters():
-            p.grad = None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        for p in model.parameters():
-            p.grad = None
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             step()
@@ -208,8 +206,6 @@ def run_ours(args):
         if graph is not None:
             graph.replay()
         else:
-            for p in model.parameters():
-                p.grad = None
             step()
 
     def barrier():
@@ -249,19 +245,33 @@ def run_ours(args):
     ck = clocks.stop() if rank == 0 else None
     loss_val = float(loss_buf.item())
 
-    # The complete training step of train.py:100-120: the step above + clip_grad_norm_(1.0) + AdamW
-    # (two fused kernels over the flat buffers) + the bf16 re-pack of the updated weights, captured in one graph.
+    # compute-only step at N > 1 (same box, same minute): the step with the gradient exchange switched off -> exposed communication
+    nocomm_ms = None
+    if world > 1 and use_graph:
+        def step_nocomm():
+            stepper.accumulation_steps, stepper.micro = 2, 0        # first micro-step of a window of two: zero, no exchange
+            r = step()
+            stepper.accumulation_steps, stepper.micro = 1, 0
+            return r
+        step_nocomm()
+        torch.cuda.synchronize()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            step_nocomm()
+        for _ in range(2):
+            g2.replay()
+        nocomm_ms = timed(g2.replay, args.steps) / args.steps
+        del g2
+
+    # The complete training step of train.py:100-120: the step above + clip_grad_norm_(1.0) + AdamW: sum of
+    # squares, a one-thread coefficient kernel (step counter / bias corrections / clip factor in device memory) and one AdamW kernel
+    # that also writes the bf16 shadow the GEMMs read -- captured in one graph, replayed with a correctly advancing step count.
     full_ms = None
     if not args.no_full_step:
-        from prompt_tts_b200.optim import FusedClipAdamW
-        opt = FusedClipAdamW(stepper)
         graph = None
-        for p in model.parameters():
-            p.grad = None
         step()
-        opt.step()                          # builds the flat master buffer; parameters now alias it
+        opt.step()
         torch.cuda.synchronize()
-        stepper.cache.epoch += 1            # stale packs at capture time => the re-pack kernels are part of the graph
         full_graph = torch.cuda.CUDAGraph() if use_graph else None
         if full_graph is not None:
             with torch.cuda.graph(full_graph):
@@ -278,6 +288,7 @@ def run_ours(args):
             full_step()
         full_ms = timed(full_step, args.steps) / args.steps
         full_loss = float(loss_buf.item())
+        full_steps_taken = opt.step_count
         full_graph = None
 
     if rank == 0:
@@ -295,7 +306,8 @@ def run_ours(args):
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         traffic, traffic_note = None, "no ncu capture found under profiles/"
         try:   # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (not measured live)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))
+            tpath = os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")
+            tr = json.load(open(tpath if os.path.exists(tpath) else os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             traffic_note = f"{tr['kernel']} {tr['shape']}: {traffic / 1e6:.1f} MB DRAM vs {tr['algorithmic_bytes'] / 1e6:.1f} MB algorithmic; {tr['source']}"
         except Exception:
@@ -323,8 +335,15 @@ def run_ours(args):
         }
         if full_ms is not None:
             line["train_step_full"] = {"ms_per_step": full_ms, "frames_per_s": frames / (full_ms / 1e3), "loss_after": full_loss,
+                                       "optimizer_steps": full_steps_taken,
                                        "includes": "add_noise + fwd + MSE + bwd" + (" + NCCL gradient all-reduce" if world > 1 else "")
-                                                   + " + global-norm clip + AdamW (fused, flat buffers) + bf16 weight re-pack, one CUDA graph"}
+                                                   + " + global-norm clip + AdamW writing the bf16 GEMM weights (device-side step counter), one CUDA graph"}
+        if nocomm_ms is not None:
+            line["exposed_comm_ms"] = ms_step - nocomm_ms
+            line["compute_only_ms_per_step"] = nocomm_ms
+            line["comm"] = {"dtype": os.environ.get("PT_COMM_DTYPE", "fp32"), "bucket_mb": float(os.environ.get("PT_BUCKET_MB", "128")),
+                            "buckets_per_step": grad_sync.n_buckets_last, "bytes_per_step": grad_sync.total * (4 if comm_dtype == torch.float32 else 2),
+                            "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
         if world == 1 and not args.no_rvq:
             line["rvq"] = rvq_throughput(dev, torch, ops, peaks.get("hbm_gbs", 6500.0))
         if world == 1 and not args.no_sampling:
@@ -344,14 +363,18 @@ def run_ours(args):
             line["cpu_baseline"] = cb
         emit(line)
     if world > 1:
-        # Tear down without destroy_process_group(): with NCCL work captured in a live CUDA graph it can block forever.
-        # Everything measured is already printed; leave through a barrier and a hard exit (exit code 0).
+        # Tear down: the captured graphs (which hold NCCL work) are dropped BEFORE the communicator, then destroy_process_group().
+        # A watchdog turns a teardown that still blocks into a clean exit -- everything measured is already printed.
+        import gc
         graph = None
+        gc.collect()
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
         os._exit(0)
 
 

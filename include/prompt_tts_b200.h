@@ -24,7 +24,7 @@
  *   pt_upsample2_*     nearest x2                                  tts/ldm/resnet.py:41-44
  *   pt_time_sinusoid   Timesteps                                   tts/ldm/unet_1d_condition.py:209,622
  *   pt_text_embed_*    Embedding + transposed PE                   tts/models.py:32-52,112-115
- *   pt_rvq_encode      encodec ResidualVectorQuantization.encode   data_preparation/generate_code.py:48
+ *   pt_rvq_encode_ws   encodec ResidualVectorQuantization.encode   data_preparation/generate_code.py:48
  *   pt_rvq_decode      encodec ResidualVectorQuantization.decode   decode_codec.py:16
  *   pt_codes_affine    codes/1023 -> Normalize(0.5,0.5)            tts/dataloader.py:64,77,168-170
  *   pt_add_noise, pt_mse_*        train-step glue                  train.py:96-98,107
@@ -219,9 +219,8 @@ int pt_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* d
 /* codes[b, q, t] = argmin_j || r_q[b, :, t] - E[q, j, :] ||  (first index wins ties), r_{q+1} = r_q - E[q, code]
  * latents [B, D, T] fp32 (reference layout), codebooks [Q, K, D] fp32, codes [B, Q, T] int64.
  * Distances are evaluated exactly as the reference does: -(|r|^2 - 2 r.e + |e|^2) in fp32, the dot
- * product accumulated in ascending d order with fused multiply-add. */
-int pt_rvq_encode(const float* latents, const float* codebooks, int64_t* codes, int B, int D, int T, int Q, int K, void* stream);
-/* allocation-free variant: cb_sq is caller scratch [Q, K] fp32 (pt_rvq_encode keeps one library-owned table instead) */
+ * product accumulated in ascending d order with fused multiply-add.
+ * cb_sq: caller-provided scratch [Q, K] fp32 (|e|^2 per code, filled here) -- the library owns no device memory. */
 int pt_rvq_encode_ws(const float* latents, const float* codebooks, float* cb_sq, int64_t* codes, int B, int D, int T, int Q, int K, void* stream);
 int pt_rvq_cb_sq(const float* codebooks, float* out, int Q, int K, int D, void* stream);
 /* latents[b, :, t] = sum_q E[q, codes[b,q,t], :]  (q ascending, fp32) */

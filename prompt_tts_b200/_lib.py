@@ -122,7 +122,6 @@ _SIGS = {
     "add_noise": "ppppppilp",
     "mse_fwd_bwd": "pppplfp",
     "ddpm_step": "pppppliiffp",
-    "rvq_encode": "pppiiiiip",
     "rvq_encode_ws": "ppppiiiiip",
     "rvq_cb_sq": "ppiiip",
     "rvq_decode": "pppiiiiip",

@@ -65,7 +65,6 @@ struct ACfg {
   static constexpr int BUDGET = (MODE == MODE_DKV ? 205 : 221) * 1024;                  // of 227 KB: leaves room for alignment slack, barriers, statistics
   static constexpr int NSTAGE_FIT = (BUDGET - FIXED) / STAGE_BYTES;
   static constexpr int NSTAGE = NSTAGE_FIT >= 8 ? 8 : NSTAGE_FIT;   // deep ring: bytes in flight must cover the TMA round trip
-  static constexpr int LOOKAHEAD = XBUF == 2 ? (NSTAGE >= 3 ? 2 : (NSTAGE >= 2 ? 1 : 0)) : 0;   // stage-1 MMAs issued ahead of stage 2
   static constexpr int OFF_S = NX * R_BYTES;
   static constexpr int OFF_BAR = OFF_S + NSTAGE * STAGE_BYTES;
   static constexpr int OFF_STAT = OFF_BAR + 512;
@@ -361,7 +360,6 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     const int g = (warp - 2) >> 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;                // row of the 128-row tile owned by this thread
-    const int tg = (warp - 2 - g * 4) * 32 + lane;   // 0..127 within the group
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     const bool active = XBUF == 2 || g == 0;      // with one X buffer only group 0 transforms (group 1 helps in the epilogue)
     const int jstep = XBUF == 2 ? 2 : 1;
@@ -641,11 +639,7 @@ int encode_heads(CUtensorMap* tm, const void* ptr, int D, int L, int H, int B, l
 
 template <int MODE, int DP>
 int launch_attn(const AParams& ap, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CUDA_OK(cudaFuncSetAttribute(attn_kernel<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<MODE, DP>::SMEM_BYTES));
-    attr_set = true;
-  }
+  PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(attn_kernel<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<MODE, DP>::SMEM_BYTES));
   const long long work = (long long)grid.x * grid.y * grid.z;   // (row blocks, heads, batch) -> one persistent CTA per SM
   const int sms = pt_num_sms();
   attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 352, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);

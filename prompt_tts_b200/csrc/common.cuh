@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/prompt_tts_b200.h"
 
 typedef __nv_bfloat16 bf16;
@@ -35,14 +37,30 @@ extern unsigned long long g_pt_launches;  // kernels launched by this library (a
     PT_CUDA_OK(cudaGetLastError());  \
   } while (0)
 
+// Run `expr` (a cudaFuncSetAttribute call: per-device state) once per device and per call site, thread-safely.  A process-wide
+// `static bool` would leave a second device of the same process without its opt-in shared memory.
+#define PT_ONCE_PER_DEVICE(expr)                                              \
+  do {                                                                        \
+    static std::atomic<unsigned long long> done__{0};                         \
+    int dev__ = 0;                                                            \
+    PT_CUDA_OK(cudaGetDevice(&dev__));                                        \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                    \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) {                  \
+      PT_CUDA_OK(expr);                                                       \
+      done__.fetch_or(bit__, std::memory_order_release);                      \
+    }                                                                         \
+  } while (0)
+
 extern int g_pt_sm_reserve;  // SMs the persistent kernels leave free (api.cu: pt_set_sm_reserve)
 static inline int pt_num_sms_physical() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -344,14 +344,15 @@ __global__ void time_sinusoid_kernel(const int64_t* __restrict__ t, float* __res
 }
 
 __global__ void text_embed_fwd_kernel(const int32_t* __restrict__ ids, const float* __restrict__ E, const float* __restrict__ pe,
-                                      bf16* __restrict__ y, long long BL, int L, int D) {
+                                      bf16* __restrict__ y, long long BL, int L, int D, int V) {
   const int nv = D >> 3;
   const long long total = BL * nv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / nv;
     const int v = (int)(i % nv);
     const int l = (int)(r % L);
-    const float* e = E + (long long)ids[r] * D + v * 8;
+    const int id = min(max(ids[r], 0), V - 1);     // nn.Embedding raises on an out-of-range id; a kernel cannot, so it never reads outside E
+    const float* e = E + (long long)id * D + v * 8;
     const float* p = pe + (long long)l * D + v * 8;
     float f[8];
 #pragma unroll
@@ -422,7 +423,7 @@ __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __re
                                  const float* __restrict__ sa, const float* __restrict__ sb, float* __restrict__ xt, long long total,
                                  long long per_sample) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int64_t ti = t[i / per_sample];
+    const int64_t ti = min(max(t[i / per_sample], (int64_t)0), (int64_t)999);   // the 1000-entry schedule tables (train.py:32-36)
     xt[i] = sa[ti] * x0[i] + sb[ti] * noise[i];
   }
 }
@@ -714,7 +715,7 @@ extern "C" int pt_time_sinusoid(const int64_t* t, float* out, int B, int dim, vo
 }
 extern "C" int pt_text_embed_fwd(const int32_t* ids, const float* E, const float* pe, void* y, int B, int L, int D, int V, void* stream) {
   PT_REQUIRE(B > 0 && L > 0 && D % 8 == 0 && V > 0, "text_embed_fwd: D=%d", D);
-  text_embed_fwd_kernel<<<grid_for((long long)B * L * (D / 8), 256), 256, 0, ST>>>(ids, E, pe, (bf16*)y, (long long)B * L, L, D);
+  text_embed_fwd_kernel<<<grid_for((long long)B * L * (D / 8), 256), 256, 0, ST>>>(ids, E, pe, (bf16*)y, (long long)B * L, L, D, V);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }

@@ -58,6 +58,7 @@ struct alignas(64) KParams {
   long long rsm, rsz2, rsz3;
   long long bz2_stride;
   long long osn;
+  int vec_red;          // fp32 atomic output: rows are contiguous and 16-byte aligned -> red.global.add.v4.f32
 };
 
 template <int BN>
@@ -75,7 +76,7 @@ struct Cfg {
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int EPI_COLS = 32;                     // columns per epilogue pass
   static constexpr int EPI_BF16_BYTES = EPI_WARPS * 32 * EPI_COLS * 2;   // one dense 32 x 32 bf16 store tile per warp
-  static constexpr int EPI_F32_BYTES = EPI_WARPS * 32 * 17 * 4;   // fp32 transpose tile per warp: 32 x 16 (+1)
+  static constexpr int EPI_F32_BYTES = EPI_WARPS * 32 * 17 * 4;   // fp32 transpose tile per warp: 32 x 16 (+1), or 32 x 16 swizzled
   static constexpr int EPI_BYTES = EPI_BF16_BYTES > EPI_F32_BYTES ? EPI_BF16_BYTES : EPI_F32_BYTES;
   static constexpr int F32_COLS = 16;   // columns per transpose pass of the atomic epilogue
   static constexpr int BAR_BYTES = 512;     // keeps the epilogue staging 512-byte aligned (period of the 64-byte swizzle)
@@ -477,9 +478,40 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
                   }
                 }
               }
+            } else if (p.vec_red) {
+              // PT_OUT_F32_ATOMIC_ADD, contiguous 16-byte aligned rows: transpose through a warp-private 32 x 16 tile (16-byte chunks
+              // XOR-swizzled by the row pair: conflict-free both ways) and flush with red.global.add.v4.f32 -- four floats per lane
+              // request, four lanes per 64-byte row segment, 8 rows per warp instruction (4 instructions per pass instead of 16)
+              float* vt = reinterpret_cast<float*>(sepi) + ew * (32 * FC);
+#pragma unroll
+              for (int g = 0; g < FC / 4; ++g)
+                *reinterpret_cast<float4*>(vt + lane * FC + ((g ^ ((lane >> 1) & 3)) << 2)) = make_float4(f[g * 4], f[g * 4 + 1], f[g * 4 + 2], f[g * 4 + 3]);
+              __syncwarp();
+              const int c4 = lane & 3, rsub = lane >> 2;
+              const int n = nb + c4 * 4;
+              if (n < p.N) {
+                float* o = reinterpret_cast<float*>(p.out) + zoff + n;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                  const int r = it * 8 + rsub;
+                  if (mrow0 + r < p.M) {
+                    const float4 t = *reinterpret_cast<const float4*>(vt + r * FC + ((c4 ^ ((r >> 1) & 3)) << 2));
+                    float* dst = o + (long long)(mrow0 + r) * p.osm;
+                    if (n + 4 <= p.N) {
+                      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+                    } else {
+                      const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                      for (int j = 0; j < 4; ++j)
+                        if (n + j < p.N) atomicAdd(dst + j, tv[j]);
+                    }
+                  }
+                }
+              }
+              __syncwarp();
             } else {
-              // PT_OUT_F32_ATOMIC_ADD: transpose through a warp-private tile so that one warp-wide RED covers consecutive columns of
-              // two rows (8 floats per 32-byte L2 sector instead of 1)
+              // PT_OUT_F32_ATOMIC_ADD, strided output: transpose through a warp-private tile so that one warp-wide RED covers
+              // consecutive columns of two rows (8 floats per 32-byte L2 sector instead of 1)
 #pragma unroll
               for (int j = 0; j < FC; ++j) tile[lane * (FC + 1) + j] = f[j];
               __syncwarp();
@@ -575,11 +607,7 @@ int encode_output(CUtensorMap* tm, const pt_gemm_t* g) {
 
 template <int BN, int MC>
 int launch(const KParams& kp, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
-    attr_set = true;
-  }
+  PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(gemm_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
   if (MC == 1) {
     gemm_kernel<BN, MC><<<grid, Cfg<BN>::THREADS, Cfg<BN>::SMEM_BYTES, st>>>(kp);
   } else {
@@ -749,6 +777,9 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   kp.bz2_stride = g->bias_z2_stride ? g->bias_z2_stride : g->N;
   kp.osn = g->out_stride_n ? g->out_stride_n : 1;
   PT_REQUIRE(kp.osn == 1 || g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: out_stride_n needs PT_OUT_F32_ATOMIC_ADD");
+  kp.vec_red = (g->out_dtype == PT_OUT_F32_ATOMIC_ADD && kp.osn == 1 && g->out_stride_m % 4 == 0 && g->out_stride_z2 % 4 == 0 &&
+                g->out_stride_z3 % 4 == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0 && !getenv("PT_GEMM_SCALAR_RED"))
+                   ? 1 : 0;
 
   // persistent grid: one CTA per SM for the wide tiles, two for the narrow ones (fewer when there is less work)
   const long long slots = (long long)sms * (bn <= 128 ? 2 : 1) / mc;     // clusters (or single CTAs) that can be resident

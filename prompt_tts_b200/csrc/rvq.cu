@@ -167,7 +167,7 @@ __global__ void rvq_decode_kernel(const int64_t* __restrict__ codes, const float
       if (f < nframes) {
         const long long b = f / T, t = f % T;
         for (int q = 0; q < Q; ++q) {
-          const long long c = codes[(b * Q + q) * T + t];
+          const long long c = min(max((long long)codes[(b * Q + q) * T + t], 0ll), (long long)K - 1);   // never read outside the codebook
           const float4 e = *reinterpret_cast<const float4*>(cb + ((long long)q * K + c) * RD + lane * 4);
           acc.x += e.x;
           acc.y += e.y;
@@ -204,9 +204,6 @@ __global__ void codes_affine_inv_kernel(const float* __restrict__ x, int64_t* __
   }
 }
 
-float* g_cbsq = nullptr;
-size_t g_cbsq_cap = 0;
-
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
@@ -226,26 +223,11 @@ extern "C" int pt_rvq_encode_ws(const float* latents, const float* codebooks, fl
   PT_REQUIRE(D == RD, "rvq_encode: latent dimension must be %d (EnCodec), got %d", RD, D);
   if (int r = pt_rvq_cb_sq(codebooks, cb_sq, Q, K, D, stream)) return r;
   const size_t smem = sizeof(float) * (RD * TF + RD * TC + TF + 16 * TF) + sizeof(int) * (16 * TF + TF);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CUDA_OK(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long nframes = (long long)B * T;
   rvq_encode_kernel<<<(unsigned)((nframes + TF - 1) / TF), 256, smem, ST>>>(latents, codebooks, cb_sq, codes, nframes, T, Q, K);
   PT_LAUNCH_CHECK();
   return PT_OK;
-}
-
-extern "C" int pt_rvq_encode(const float* latents, const float* codebooks, int64_t* codes, int B, int D, int T, int Q, int K, void* stream) {
-  // the |e|^2 table lives in a library-owned scratch buffer (grown on demand, outside stream capture)
-  const size_t need = sizeof(float) * (size_t)Q * K;
-  if (need > g_cbsq_cap) {
-    if (g_cbsq) cudaFree(g_cbsq);
-    PT_CUDA_OK(cudaMalloc(&g_cbsq, need));
-    g_cbsq_cap = need;
-  }
-  return pt_rvq_encode_ws(latents, codebooks, g_cbsq, codes, B, D, T, Q, K, stream);
 }
 
 extern "C" int pt_rvq_decode(const int64_t* codes, const float* codebooks, float* latents, int B, int D, int T, int Q, int K, void* stream) {

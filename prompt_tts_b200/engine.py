@@ -31,27 +31,57 @@ class Var:
 
 
 class PackCache:
-    """bf16 GEMM-layout copies of fp32 parameters, refreshed when a parameter's version counter moves."""
+    """bf16 GEMM-layout copies of fp32 parameters.
+
+    Two kinds of entries:
+      * static  -- views into an optimiser-owned bf16 shadow of the flat master buffer (`optim.FusedClipAdamW`): the AdamW kernel
+        writes them, nothing is ever re-packed.  Guarded by the parameters' version counters, so an in-place write from outside
+        (`load_state_dict`, `p.data.copy_`) refreshes the slice before it is used.
+      * cached  -- packed on demand and re-packed when a parameter's version counter / storage moves (any torch optimiser).  While
+        the current stream is being CAPTURED the re-pack always runs, into the same buffer: a captured step must contain the
+        re-pack kernels, or its GEMMs would read the weights frozen at capture time while the optimiser updates the fp32 masters
+        between replays.
+    """
 
     def __init__(self):
         self._d: Dict[tuple, Tuple[tuple, torch.Tensor]] = {}
-        self.epoch = 0      # bumped by optimisers that update parameters through raw pointers (no version-counter change)
+        self.static: Dict[tuple, list] = {}     # key -> [versions, view, refresh()]
+        self.epoch = 0      # bumped by optimisers that update parameters through raw pointers without maintaining a static shadow
+
+    def add_static(self, kind: str, params: Sequence[torch.Tensor], view: torch.Tensor, refresh: Optional[Callable[[], None]]) -> None:
+        key = (kind,) + tuple(id(p) for p in params)
+        self.static[key] = [tuple(p._version for p in params), view, refresh, list(params)]
 
     def get(self, params: Sequence[torch.Tensor], kind: str) -> torch.Tensor:
         key = (kind,) + tuple(id(p) for p in params)
+        st = self.static.get(key)
+        if st is not None:
+            ver = tuple(p._version for p in params)
+            if ver != st[0]:
+                if st[2] is not None:
+                    st[2]()
+                st[0] = ver
+            return st[1]
         ver = (self.epoch,) + tuple((p._version, p.data_ptr()) for p in params)
         hit = self._d.get(key)
-        if hit is not None and hit[0] == ver:
+        capturing = torch.cuda.is_current_stream_capturing() if params[0].is_cuda else False
+        if hit is not None and hit[0] == ver and not capturing:
             return hit[1]
+        prev = hit[1] if hit is not None else None
         if kind == "conv":      # [Co, Ci, k] -> [Co, k*Ci]
             (w,) = params
-            out = ops.pack_conv_weight(w.detach())
+            if not w.is_contiguous():
+                raise ops._lib.PtError("conv weight is a non-contiguous view (optimiser-managed) but has no static bf16 shadow")
+            out = ops.pack_conv_weight(w.detach(), out=prev)
         elif kind == "bias":    # fp32 concatenation of 1-D parameters (a single one is used in place)
-            out = params[0].detach() if len(params) == 1 else torch.cat([p.detach() for p in params])
+            if len(params) == 1:
+                out = params[0].detach()
+            else:
+                out = torch.cat([p.detach() for p in params], out=prev) if prev is not None else torch.cat([p.detach() for p in params])
         else:                   # "lin": rows of all params stacked, cast to bf16 ([N, K]; 1x1 convs are [N, K, 1])
             rows = sum(p.shape[0] for p in params)
             K = params[0].numel() // params[0].shape[0]
-            out = torch.empty(rows, K, dtype=BF16, device=params[0].device)
+            out = prev if prev is not None else torch.empty(rows, K, dtype=BF16, device=params[0].device)
             r = 0
             for p in params:
                 ops.cast_bf16(p.detach().reshape(p.shape[0], K), out[r:r + p.shape[0]])
@@ -68,9 +98,9 @@ class Tape:
         self.pgrads: Dict[int, torch.Tensor] = {}
         self.params: Dict[int, torch.Tensor] = {}
         self.post: List[Callable[[], None]] = []   # run after the reverse sweep
-        self.pgrad_order: List[Tuple[Sequence[torch.Tensor], torch.Tensor]] = []   # (params, buffer) in completion order
-        self.grad_alloc: Optional[Callable[[Sequence[torch.Tensor]], Optional[torch.Tensor]]] = None   # flat-buffer provider (dp.GradSync)
-        self.on_ready: Optional[Callable[[List[Tuple[Sequence[torch.Tensor], torch.Tensor]]], None]] = None
+        self.pgrad_order: List[Tuple[Sequence[torch.Tensor], torch.Tensor, str]] = []   # (params, buffer, kind) in completion order
+        self.grad_alloc: Optional[Callable[[Sequence[torch.Tensor], str], Optional[torch.Tensor]]] = None   # flat-buffer provider (dp.GradSync)
+        self.on_ready: Optional[Callable[[List[Tuple[Sequence[torch.Tensor], torch.Tensor, str]]], None]] = None
         # inference only: step-invariant cross-attention K/V projections of the text encoding, keyed by attention module
         # (the sampler passes the same dict to each of its 100 denoiser forwards)
         self.kv_cache: Optional[Dict[int, "Var"]] = None
@@ -79,34 +109,64 @@ class Tape:
         if self.recording:
             self.bwd.append(fn)
 
-    def pgrad(self, p: torch.Tensor) -> torch.Tensor:
-        g = self.pgrads.get(id(p))
-        if g is None:
-            buf = self.grad_alloc([p]) if self.grad_alloc is not None else None
-            g = buf.view(p.shape) if buf is not None else torch.zeros(p.shape, dtype=F32, device=p.device)
+    # ---- parameter-gradient buffers.  One buffer per GROUP of parameters (a single one, or the stacked rows of a fused QKV / KV /
+    # time-projection weight), fp32, accumulated into by the backward kernels.  Kinds:
+    #   "plain"  the buffer has the parameter's own layout
+    #   "cat"    [sum rows, K]: row slices are the gradients of the group's parameters
+    #   "conv"   k=3 conv weight [Co, Ci, 3] accumulated TAP-MAJOR as [Co, 3, Ci] (the GEMM layout: contiguous output columns, so the
+    #            stream-K flush uses vector REDs, and the flat master / shadow of the fused optimiser need no permutation); the
+    #            gradient handed to torch is the permuted VIEW [Co, Ci, 3] of it.
+    def _register(self, params: Sequence[torch.Tensor], kind: str, buf: torch.Tensor) -> None:
+        if kind == "plain":
+            (p,) = params
+            self.pgrads[id(p)] = buf.view(p.shape)
+            self.params[id(p)] = p
+        elif kind == "conv":
+            (p,) = params
+            Co, Ci, k = p.shape
+            packed = buf.view(Co, k, Ci)
+            g = packed.permute(0, 2, 1)
+            g._pt_buf = packed  # type: ignore[attr-defined]
             self.pgrads[id(p)] = g
             self.params[id(p)] = p
-            self.pgrad_order.append(([p], g))
-        return g
+        else:
+            rows = sum(p.shape[0] for p in params)
+            K = params[0].numel() // params[0].shape[0]
+            cat = buf.view(rows, K)
+            r = 0
+            for p in params:
+                v = cat[r:r + p.shape[0]].view(p.shape)
+                v._pt_buf = cat  # type: ignore[attr-defined]
+                self.pgrads[id(p)] = v
+                self.params[id(p)] = p
+                r += p.shape[0]
+
+    def _grad_buf(self, params: Sequence[torch.Tensor], kind: str) -> torch.Tensor:
+        g = self.pgrads.get(id(params[0]))
+        if g is None:
+            n = sum(p.numel() for p in params)
+            buf = self.grad_alloc(params, kind) if self.grad_alloc is not None else None
+            if buf is None:
+                buf = torch.zeros(n, dtype=F32, device=params[0].device)
+            self._register(params, kind, buf)
+            self.pgrad_order.append((list(params), buf, kind))
+            g = self.pgrads[id(params[0])]
+        return getattr(g, "_pt_buf", g)
+
+    def rebind(self, params: Sequence[torch.Tensor], kind: str, buf: torch.Tensor) -> None:
+        """Point the gradients of `params` at `buf` (dp.GradSync moves the first step's buffers into its flat buffer)."""
+        self._register(params, kind, buf)
+
+    def pgrad(self, p: torch.Tensor) -> torch.Tensor:
+        return self._grad_buf([p], "plain")
 
     def pgrad_cat(self, params: Sequence[torch.Tensor]) -> torch.Tensor:
         """One fp32 buffer [sum rows, K] whose row slices are the gradients of `params` (fused QKV / KV weights)."""
-        if id(params[0]) in self.pgrads:
-            g0 = self.pgrads[id(params[0])]
-            return g0._pt_cat  # type: ignore[attr-defined]
-        rows = sum(p.shape[0] for p in params)
-        K = params[0].numel() // params[0].shape[0]
-        buf = self.grad_alloc(params) if self.grad_alloc is not None else None
-        buf = buf.view(rows, K) if buf is not None else torch.zeros(rows, K, dtype=F32, device=params[0].device)
-        self.pgrad_order.append((list(params), buf))
-        r = 0
-        for p in params:
-            v = buf[r:r + p.shape[0]].view(p.shape)
-            v._pt_cat = buf  # type: ignore[attr-defined]
-            self.pgrads[id(p)] = v
-            self.params[id(p)] = p
-            r += p.shape[0]
-        return buf
+        return self._grad_buf(params, "cat")
+
+    def pgrad_conv(self, p: torch.Tensor) -> torch.Tensor:
+        """fp32 [Co, 3, Ci] tap-major accumulation buffer of a k=3 conv weight (its torch gradient is the permuted view)."""
+        return self._grad_buf([p], "conv")
 
     def backward(self) -> None:
         done = 0
@@ -167,7 +227,7 @@ def linear(tape: Tape, x: Var, wparams: Sequence[torch.Tensor], bias: Optional[S
         dy2 = dy.reshape(M, N)
         if bias is not None:
             ops.colsum(dy2, tape.pgrad_cat(bias) if len(bias) > 1 else tape.pgrad(bias[0]))
-        gw = tape.pgrad_cat(wparams) if len(wparams) > 1 else tape.pgrad(wparams[0]).view(N, K)
+        gw = (tape.pgrad_cat(wparams) if len(wparams) > 1 else tape.pgrad(wparams[0])).view(N, K)
         _wgrad_gemm(ops.operand(dy2, False), ops.operand(x2, False), ops.segment(M), N, K, gw, K)
         if x.needs_grad:
             dx = torch.empty_like(x2) if (x.grad is None or not x.owned) else x.grad.reshape(M, K)
@@ -220,21 +280,20 @@ def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: 
         ops.colsum(dy.view(B * Lo, Co), tape.pgrad(bias))
         if tshift is not None and tshift.dproj is not None:
             ops.batch_colsum(dy, tshift.dproj[:, tshift.offset:], tshift.dproj.stride(0))
-        # weight gradient: one MN-major x MN-major GEMM per tap, written straight into the [Co, Ci, 3] parameter gradient
-        # (fp32 atomic accumulate with column stride 3 -- no packed temporary, no un-pack pass)
-        g3 = tape.pgrad(wparam).view(Co, Ci * 3)
+        # weight gradient: MN-major x MN-major GEMMs accumulated (fp32 atomics, stream-K) into the tap-major [Co, 3, Ci] buffer
+        g3 = tape.pgrad_conv(wparam)
         dy_op = ops.operand(dy, False, batched=True)
         if stride == 1:
-            # the three taps in ONE stream-K launch: z2 = tap shifts the rows of x by tap - 1 and the output column by tap
+            # the three taps in ONE stream-K launch: z2 = tap shifts the rows of x by tap - 1 and the output by tap * Ci
             seg = ops.segment(Lo, b_k0=-1, b_k0_z2=1, nrep=B, rep_is_batch=True)
-            ops.gemm([dy_op], [ops.operand(xd, False, batched=True)], [seg], Co, Ci, g3, out_strides=(3 * Ci, 1, 0), nz2=3,
-                     out_mode=OUT_F32_ATOMIC_ADD, out_stride_n=3)
+            ops.gemm([dy_op], [ops.operand(xd, False, batched=True)], [seg], Co, Ci, g3, out_strides=(3 * Ci, Ci, 0), nz2=3,
+                     out_mode=OUT_F32_ATOMIC_ADD)
         else:
             for t, (ai, sh) in enumerate(taps):
                 xs = xd[:, 0::2] if ai == 0 else xd[:, 1::2]
                 seg = ops.segment(Lo, b_k0=sh, nrep=B, rep_is_batch=True)
-                ops.gemm([dy_op], [ops.operand(xs, False, batched=True)], [seg], Co, Ci, g3[:, t:],
-                         out_strides=(3 * Ci, 0, 0), out_mode=OUT_F32_ATOMIC_ADD, out_stride_n=3)
+                ops.gemm([dy_op], [ops.operand(xs, False, batched=True)], [seg], Co, Ci, g3[:, t],
+                         out_strides=(3 * Ci, 0, 0), out_mode=OUT_F32_ATOMIC_ADD)
         if x.needs_grad:
             dy_k = ops.operand(dy, True, batched=True)
             wp_mn = ops.operand(wp, False)

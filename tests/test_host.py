@@ -78,31 +78,62 @@ def test_product_does_not_import_oracle():
 
 
 def test_gradsync_gloo_world2():
-    """Two CPU ranks over gloo drive GradSync's bucket logic with a fake tape: after finish() both ranks hold the mean."""
+    """Two CPU ranks over gloo drive GradSync with the real tape's gradient bookkeeping (plain, stacked and tap-major conv groups):
+    parameters are broadcast from rank 0, every step both ranks hold the mean, micro-steps without sync accumulate locally and
+    the last one reduces the window's sum, and a changed completion order is refused."""
     code = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)
 from prompt_tts_b200.dp import GradSync
+from prompt_tts_b200.engine import Tape, PackCache
 rank = int(os.environ["RANK"])
 dist.init_process_group("gloo", rank=rank, world_size=2)
-class FakeTape:
-    def __init__(self): self.pgrad_order=[]; self.on_ready=None; self.grad_alloc=None
-params = [torch.nn.Parameter(torch.zeros(n)) for n in (1000, 3000, 500, 70000)]
+torch.manual_seed(rank)
 model = torch.nn.Module()
+model.a = torch.nn.Parameter(torch.randn(1000)); model.b = torch.nn.Parameter(torch.randn(30, 100))
+model.q = torch.nn.Parameter(torch.randn(16, 8)); model.k = torch.nn.Parameter(torch.randn(24, 8))
+model.c = torch.nn.Parameter(torch.randn(12, 10, 3)); model.d = torch.nn.Parameter(torch.randn(70001))
 gs = GradSync(model, world_size=2, bucket_mb=0.01)
+ref = [torch.zeros(1)]
+dist.broadcast(ref[0], 0)
+chk = model.a.detach().clone(); dist.broadcast(chk, 0)
+assert torch.equal(chk, model.a.detach()), "parameters must be broadcast from rank 0 at construction"
 for step in range(3):
-    tape = FakeTape(); gs.attach(tape)
-    for i, p in enumerate(params):
-        buf = tape.grad_alloc([p]) if tape.grad_alloc else None
-        g = buf.view(p.shape) if buf is not None else torch.zeros(p.shape)
-        g += float((rank + 1) * (i + 1) * (step + 1))
-        tape.pgrad_order.append(([p], g))
-        if tape.on_ready: tape.on_ready(tape.pgrad_order[-1:])
+    tape = Tape(PackCache()); gs.attach(tape)
+    done = 0
+    for i, get in enumerate([lambda: tape.pgrad(model.a), lambda: tape.pgrad(model.b), lambda: tape.pgrad_cat([model.q, model.k]),
+                             lambda: tape.pgrad_conv(model.c), lambda: tape.pgrad(model.d)]):
+        buf = get(); buf += float((rank + 1) * (i + 1) * (step + 1))
+        if tape.on_ready and len(tape.pgrad_order) > done:
+            tape.on_ready(tape.pgrad_order[done:]); done = len(tape.pgrad_order)
     gs.finish()
-    for i, (_, g) in enumerate(tape.pgrad_order):
+    for i, p in enumerate([model.a, model.b, model.q, model.c, model.d]):
+        g = tape.pgrads[id(p)]
+        assert g.shape == p.shape
         want = 1.5 * (i + 1) * (step + 1)
-        assert torch.allclose(g, torch.full_like(g, want)), (step, i, g[:3], want)
+        assert torch.allclose(g, torch.full_like(g, want)), (step, i, g.flatten()[:3], want)
+        assert g.untyped_storage().data_ptr() == gs.flat.untyped_storage().data_ptr(), "param.grad must be a view of the flat buffer from step 1 on"
+    assert tape.pgrads[id(model.k)].shape == model.k.shape and not tape.pgrads[id(model.c)].is_contiguous()
     if step > 0: assert gs.n_buckets_last > 1
+# accumulation window of two micro-steps: no exchange in the first, the sum is reduced in the second
+for micro in range(2):
+    tape = Tape(PackCache()); gs.attach(tape, zero=micro == 0, sync=micro == 1)
+    done = 0
+    for i, get in enumerate([lambda: tape.pgrad(model.a), lambda: tape.pgrad(model.b), lambda: tape.pgrad_cat([model.q, model.k]),
+                             lambda: tape.pgrad_conv(model.c), lambda: tape.pgrad(model.d)]):
+        buf = get(); buf += float(rank + 1)
+        tape.on_ready(tape.pgrad_order[done:]); done = len(tape.pgrad_order)
+    gs.finish()
+    want = float(rank + 1) if micro == 0 else 3.0
+    assert torch.allclose(tape.pgrads[id(model.d)], torch.full((70001,), want)), (micro, tape.pgrads[id(model.d)][:3])
+# a different completion order is an error, not a silently wrong bucket
+tape = Tape(PackCache()); gs.attach(tape)
+tape.pgrad(model.b)
+try:
+    tape.on_ready(tape.pgrad_order[0:]); bad = False
+except RuntimeError:
+    bad = True
+assert bad
 dist.destroy_process_group()
 print("OK", rank)
 ''' % ROOT
