@@ -122,6 +122,59 @@ def cpu_reference_step_time(steps, warmup, threads=None):
                       f"{warmup} warm-up; oracle/ref_model.py restatement of the reference modules on torch CPU kernels"}, sec
 
 
+def gpu_eager_baseline(dev, steps=3, warmup=2):
+    """SURVEY 2.1 / BASELINE.md section 1: the bar on the GPU is eager PyTorch running the reference modules on the same B200.
+    The oracle restatement (oracle/ref_model.py: the reference's module arithmetic on torch library kernels -- cuDNN / cuBLAS / SDPA)
+    under torch.autocast(bf16), full train step of train.py:100-120 (forward, MSE, backward, clip_grad_norm_, AdamW(fused=False)) at
+    the largest batch of {32, 16, 8} that fits.  A baseline leg only: nothing of it is on the product path."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_model
+    cfg = load_cfg(CFG)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    for Bc in (BATCH, 16, 8):
+        try:
+            sd = ref_model.random_state_dict(cfg, seed=0, device=dev)
+            params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "inv_freq" not in k]
+            opt = torch.optim.AdamW(params, lr=1e-5, betas=(0.95, 0.999), weight_decay=1e-6, eps=1e-8)
+            inp = synth(cfg, Bc, T_FRAMES, 0, dev)
+
+            def one(with_opt):
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss, _ = ref_model.train_step_loss(sd, cfg, inp["x0"], inp["noise"], inp["t"], inp["ids"], inp["mask"])
+                loss.backward()
+                if with_opt:
+                    torch.nn.utils.clip_grad_norm_(params, 1.0)
+                    opt.step()
+                opt.zero_grad(set_to_none=True)
+
+            res = {}
+            for name, with_opt in (("fwd_bwd", False), ("full_step", True)):
+                for _ in range(warmup):
+                    one(with_opt)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(steps):
+                    one(with_opt)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                res[name] = {"ms_per_step": ms, "frames_per_s": Bc * T_FRAMES / (ms / 1e3)}
+            res.update({"batch": Bc, "frames": T_FRAMES, "kind": "port",
+                        "what": "oracle/ref_model.py (reference module arithmetic on torch cuDNN/cuBLAS/SDPA kernels) under torch.autocast(bf16), "
+                                "eager, fp32 master weights, TF32 allowed for the fp32 leftovers; peak memory "
+                                f"{torch.cuda.max_memory_allocated(dev) / 2**30:.1f} GiB"})
+            del sd, params, opt
+            torch.cuda.empty_cache()
+            return res
+        except torch.cuda.OutOfMemoryError:
+            sd = params = opt = None
+            torch.cuda.empty_cache()
+    return {"unavailable": "out of memory at batch 8"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -344,23 +397,49 @@ def run_ours(args):
             line["comm"] = {"dtype": os.environ.get("PT_COMM_DTYPE", "fp32"), "bucket_mb": float(os.environ.get("PT_BUCKET_MB", "128")),
                             "buckets_per_step": grad_sync.n_buckets_last, "bytes_per_step": grad_sync.total * (4 if comm_dtype == torch.float32 else 2),
                             "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
-        if world == 1 and not args.no_rvq:
-            line["rvq"] = rvq_throughput(dev, torch, ops, peaks.get("hbm_gbs", 6500.0))
-        if world == 1 and not args.no_sampling:
-            # secondary figure of BASELINE.json's metric (configs[3]): sampling real-time factor, denoiser only
-            del graph
-            graph = None
-            for p in model.parameters():
-                p.grad = None
-            torch.cuda.empty_cache()
-            line["sampling"] = sampling_rtf(model, cfg, dev, torch, peak)
+    # RVQ and sampling shard by clip / utterance with no collective -- every rank does its share, the line reports
+    # units of all ranks / the slowest rank's device time.
+    graph = None
+    for p in model.parameters():
+        p.grad = None
+    torch.cuda.empty_cache()
+    peaks_all = {}
+    try:
+        peaks_all = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    rvq = samp = None
+    if not args.no_rvq:
+        rvq = rvq_throughput(dev, torch, ops, peaks_all.get("hbm_gbs", 6500.0), rank, world, max_over_ranks)
+    if not args.no_sampling:
+        samp = sampling_rtf(model, cfg, dev, torch, peaks_all.get("bf16_tflops_sustained", 1400.0), rank, world, max_over_ranks)
+    if rank == 0:
+        if rvq is not None:
+            line["rvq"] = rvq
+        if samp is not None:
+            line["sampling"] = samp
         if world == 1 and not args.no_cpu_baseline:
+            del stepper, opt, grad_sync
+            model = None
+            torch.cuda.empty_cache()
             cb, _ = cpu_reference_step_time(2, 1)
             try:
                 cb["rvq"] = cpu_rvq_baseline()
             except Exception as e:   # a baseline figure must never take the bench line down
                 cb["rvq"] = {"unavailable": str(e)[:120]}
             line["cpu_baseline"] = cb
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(dev)
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"unavailable": str(e)[:160]}
         emit(line)
     if world > 1:
         # Tear down: the captured graphs (which hold NCCL work) are dropped BEFORE the communicator, then destroy_process_group().
@@ -378,29 +457,31 @@ def run_ours(args):
         os._exit(0)
 
 
-def sampling_rtf(model, cfg, dev, torch, peak_tflops):
+def sampling_rtf(model, cfg, dev, torch, peak_tflops, rank=0, world=1, max_over_ranks=lambda x: x):
     """BASELINE.json configs[3] / SURVEY 8d config 4: 100 DDPM steps, batch 64 x 20 s utterances (1504 frames at 75 fps) with a
     3 s (225-frame) speech prompt in-painted at every step; text encoder once, cross-attention K/V cached, one captured denoiser
     forward replayed per step.  RTF = seconds of GPU time / seconds of audio generated (denoiser only, codec decoder excluded)."""
     from prompt_tts_b200.sample import DDPMSampler
     Bs, Ts, P, steps = 64, 1504, 225, 100
-    inp = synth(cfg, Bs, Ts, 4000, dev)
+    inp = synth(cfg, Bs, Ts, 4000 + rank, dev)
     prompt = inp["x0"][..., :P].contiguous()
     smp = DDPMSampler(model, n_infer=steps)
     model.eval()
+    DDPMSampler(model, n_infer=4).sample(inp["ids"], Ts, prompt=prompt, seed=1)      # untimed: first-use costs (allocator pools, weight packs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     x = smp.sample(inp["ids"], Ts, prompt=prompt, seed=0)
     e1.record()
     torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) / 1e3
-    audio_s = Bs * Ts / 75.0
-    flop = Bs * (45.2e9 + steps * 428.0e9)           # SURVEY 8d: text encoder once + 100 UNet forwards at T = 1504, per utterance
-    return {"rtf": sec / audio_s, "seconds": sec, "audio_seconds": audio_s, "steps": steps, "batch": Bs, "frames": Ts, "prompt_frames": P,
-            "tflops": flop / sec / 1e12, "frac_of_tensor_roofline": flop / sec / 1e12 / peak_tflops,
+    sec = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+    audio_s = world * Bs * Ts / 75.0
+    flop = world * Bs * (45.2e9 + steps * 428.0e9)   # SURVEY 8d: text encoder once + 100 UNet forwards at T = 1504, per utterance
+    return {"rtf": sec / audio_s, "seconds": sec, "audio_seconds": audio_s, "steps": steps, "batch": Bs, "batch_per_gpu": Bs, "n_gpus": world,
+            "frames": Ts, "prompt_frames": P,
+            "tflops": flop / sec / 1e12, "frac_of_tensor_roofline": flop / sec / 1e12 / (peak_tflops * world),
             "finite": bool(torch.isfinite(x).all().item()),
-            "note": "includes the one eager warm-up forward and the graph capture of the loop (first two of the 100 steps)"}
+            "note": "one complete sample() call after an untimed 4-step call: includes its own eager first step and the capture of the loop"}
 
 
 def cpu_rvq_baseline(n_clips=2, T=900):
@@ -423,21 +504,23 @@ def cpu_rvq_baseline(n_clips=2, T=900):
             "sample": f"{n_clips} clips x {T} frames, 8 x 1024 x 128 codebooks; oracle/rvq_oracle.c"}
 
 
-def rvq_throughput(dev, torch, ops, hbm_gbs):
+def rvq_throughput(dev, torch, ops, hbm_gbs, rank=0, world=1, max_over_ranks=lambda x: x):
     """BASELINE.json configs[4] / SURVEY 8d config 5: RVQ quantise (8 x 1024 codebooks, 128-d) + code-embedding sum over 13,100 clips
-    zero-padded to 900 frames, in the reference's batches of 32 (generate_code.py:94).  One batch of synthetic latents is generated
-    on the device and reused for every batch of the set (the set itself would be 6 GB); codes must decode/re-encode consistently."""
+    zero-padded to 900 frames, in the reference's batches of 32 (generate_code.py:94), clips dealt round-robin to the ranks (no
+    collective).  One batch of synthetic latents per rank is generated on the device and reused for every batch of its share (the set
+    itself would be 6 GB); codes must decode consistently with the sequential fp32 codeword sum."""
     n_clips, T, bs, D, Q, K = 13100, 900, 32, 128, 8, 1024
-    g = torch.Generator(device=dev).manual_seed(0)
-    cb = torch.randn(Q, K, D, device=dev, generator=g)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    cb = torch.randn(Q, K, D, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
     lat = torch.randn(bs, D, T, device=dev, generator=g)
     codes = ops.rvq_encode(lat, cb)
     dec = ops.rvq_decode(codes, cb)
     ref = torch.zeros_like(dec)
     for q in range(Q):                       # the reference's order: q ascending, fp32 adds
         ref += cb[q][codes[:, q]].permute(0, 2, 1)
-    ok = bool(torch.equal(dec, ref))
+    ok = bool(torch.equal(dec, ref)) and bool(torch.equal(ops.rvq_decode(codes, cb, gather_l2=True), ref))
     n_batches = (n_clips + bs - 1) // bs
+    mine = (n_batches - rank + world - 1) // world          # batches rank, rank + world, ...
 
     def timed(fn, n):
         fn()
@@ -450,18 +533,26 @@ def rvq_throughput(dev, torch, ops, hbm_gbs):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / 1e3
 
-    t_enc = timed(lambda: ops.rvq_encode(lat, cb), n_batches)
-    # decode: 16 reference batches per launch (512 clips) -- at 32 clips a launch lasts ~3 us and the Python call dominates
+    t_enc = max_over_ranks(timed(lambda: ops.rvq_encode(lat, cb), mine))
+    # decode: 16 reference batches per launch (512 clips) -- at 32 clips a launch lasts a few us and the Python call dominates
     big = codes.repeat(16, 1, 1)
-    t_dec = timed(lambda: ops.rvq_decode(big, cb), (n_batches + 15) // 16)
+    out = torch.empty(big.shape[0], D, T, device=dev)
+    scratch = torch.empty(big.numel(), dtype=torch.int16, device=dev)
+    from prompt_tts_b200.ops import _p, _stream, call
+    nl = (mine + 15) // 16
+    t_dec = max_over_ranks(timed(lambda: call("rvq_decode_ws", _p(big), _p(cb), _p(out), _p(scratch), big.shape[0], D, T, Q, K, _stream()), nl))
+    t_dec_l2 = max_over_ranks(timed(lambda: call("rvq_decode", _p(big), _p(cb), _p(out), big.shape[0], D, T, Q, K, _stream()), nl))
     frames = n_batches * bs * T
-    return {"clips": n_clips, "frames": frames, "encode_frames_per_s": frames / t_enc, "encode_seconds": t_enc,
+    frames_dec = world * nl * 16 * bs * T if world > 1 else nl * 16 * bs * T
+    return {"clips": n_clips, "frames": frames, "n_gpus": world, "encode_frames_per_s": frames / t_enc, "encode_seconds": t_enc,
             "encode_fp32_tflops": frames * 2.097e6 / t_enc / 1e12,
-            "decode_frames_per_s": frames / t_dec, "decode_seconds": t_dec, "decode_gbs": frames * 576 / t_dec / 1e9,
-            "decode_frac_of_hbm_roofline": frames * 576 / t_dec / 1e9 / hbm_gbs,
-            "note": "codes bit-exact against the oracle in tests/test_kernels_gpu.py; encode is exact fp32 on the FMA pipe (2.097 MFLOP/frame), "
-                    "decode moves 576 B/frame over HBM but gathers 8 x 512 B codebook rows per frame from the 4 MB (L2-resident) table, so L2 gather "
-                    "bandwidth (~4 KB/frame) bounds it, not HBM; timed at 512 clips per launch", "decode_equals_sequential_codeword_sum": ok}
+            "decode_frames_per_s": frames_dec / t_dec, "decode_seconds": t_dec * frames / frames_dec, "decode_gbs": frames_dec * 576 / t_dec / 1e9,
+            "decode_frac_of_hbm_roofline": frames_dec * 576 / t_dec / 1e9 / (hbm_gbs * world),
+            "decode_l2_gather_kernel_frames_per_s": frames_dec / t_dec_l2,
+            "note": "codes bit-exact against the oracle in tests/test_kernels_gpu.py; encode is exact fp32 on the FMA pipe (2.097 MFLOP/frame); "
+                    "decode = uint16 narrowing pre-pass + shared-memory-resident 4-float codebook slices (576 B/frame of HBM traffic, 4 KB/frame "
+                    "of on-chip gathers: LDS bandwidth bounds it); the round-1 kernel gathered the same 4 KB/frame through L2; timed at 512 clips "
+                    "per launch into preallocated buffers", "decode_equals_sequential_codeword_sum": ok}
 
 
 def gemm_profile(step, model, ops, torch):

@@ -225,6 +225,10 @@ int pt_rvq_encode_ws(const float* latents, const float* codebooks, float* cb_sq,
 int pt_rvq_cb_sq(const float* codebooks, float* out, int Q, int K, int D, void* stream);
 /* latents[b, :, t] = sum_q E[q, codes[b,q,t], :]  (q ascending, fp32) */
 int pt_rvq_decode(const int64_t* codes, const float* codebooks, float* latents, int B, int D, int T, int Q, int K, void* stream);
+/* same result (bit-equal), faster: scratch = caller-provided B*Q*T uint16 for the narrowed codes; a CTA keeps a 4-float slice of all
+ * Q codebooks in shared memory instead of gathering 512-byte rows through L2.  Falls back to pt_rvq_decode if Q*K*16 B > 200 KB. */
+int pt_rvq_decode_ws(const int64_t* codes, const float* codebooks, float* latents, void* scratch, int B, int D, int T, int Q, int K,
+                     void* stream);
 /* x0 = (codes / 1023 - 0.5) / 0.5  as fp32, and its inverse  codes = clamp(round((x + 1) * 511.5), 0, 1023) */
 int pt_codes_affine(const int64_t* codes, float* x0, int64_t n, void* stream);
 int pt_codes_affine_inv(const float* x, int64_t* codes, int64_t n, void* stream);

@@ -125,6 +125,7 @@ _SIGS = {
     "rvq_encode_ws": "ppppiiiiip",
     "rvq_cb_sq": "ppiiip",
     "rvq_decode": "pppiiiiip",
+    "rvq_decode_ws": "ppppiiiiip",
     "codes_affine": "pplp",
     "codes_affine_inv": "pplp",
     "sumsq_f32": "plpp",

@@ -190,6 +190,56 @@ __global__ void rvq_decode_kernel(const int64_t* __restrict__ codes, const float
   }
 }
 
+// ---- decode, shared-memory variant.  The L2-gather kernel above moves 8 x 512 B of codebook rows per frame through L2 (4 KB per
+// frame against 576 B of HBM traffic): it runs at the L2 bandwidth, not the HBM roofline.  Here a CTA owns a 4-float slice of the
+// latent dimension and keeps that slice of ALL Q codebooks in shared memory (Q x K x 16 B = 128 KB for 8 x 1024); a thread owns a
+// frame: 8 code loads (coalesced along t), 8 conflict-prone but on-chip LDS.128, the sum in q order (bit-equal to the sequential
+// fp32 sum), 4 coalesced stores.  The int64 codes are narrowed to uint16 by a pre-pass, so the 32 slices re-read 16 B per frame
+// from L2 instead of 64 B.
+__global__ void rvq_pack_codes_kernel(const int64_t* __restrict__ codes, uint16_t* __restrict__ out, long long n, int K) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (uint16_t)min(max((long long)codes[i], 0ll), (long long)K - 1);
+}
+
+constexpr int DEC_THREADS = 512;
+__global__ void __launch_bounds__(DEC_THREADS, 1) rvq_decode_smem_kernel(const uint16_t* __restrict__ codes, const float* __restrict__ cb,
+                                                                        float* __restrict__ lat, long long nframes, int T, int Q, int K,
+                                                                        int chunks) {
+  extern __shared__ float4 scb[];        // [Q][K] : dims d0 .. d0+3 of every code
+  const int slice = blockIdx.x % (RD / 4), chunk = blockIdx.x / (RD / 4);
+  const int d0 = slice * 4;
+  for (int i = threadIdx.x; i < Q * K; i += DEC_THREADS) scb[i] = *reinterpret_cast<const float4*>(cb + (long long)i * RD + d0);
+  __syncthreads();
+  const long long per = ((nframes + chunks - 1) / chunks + 31) / 32 * 32;      // whole warps of consecutive frames
+  const long long f_begin = (long long)chunk * per, f_end = min(nframes, f_begin + per);
+  for (long long f = f_begin + threadIdx.x; f < f_end; f += DEC_THREADS) {
+    const long long b = f / T;
+    const int t = (int)(f - b * T);
+    const uint16_t* cp = codes + (b * Q) * T + t;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (Q == 8) {
+      uint16_t c[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) c[q] = cp[(long long)q * T];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 e = scb[q * K + c[q]];
+        acc.x += e.x, acc.y += e.y, acc.z += e.z, acc.w += e.w;
+      }
+    } else {
+      for (int q = 0; q < Q; ++q) {
+        const float4 e = scb[q * K + cp[(long long)q * T]];
+        acc.x += e.x, acc.y += e.y, acc.z += e.z, acc.w += e.w;
+      }
+    }
+    float* o = lat + (b * RD + d0) * T + t;
+    o[0] = acc.x;
+    o[(long long)T] = acc.y;
+    o[2ll * T] = acc.z;
+    o[3ll * T] = acc.w;
+  }
+}
+
 __global__ void codes_affine_kernel(const int64_t* __restrict__ codes, float* __restrict__ x0, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     // dataloader.py:64,77,168-170: Normalize(0.5, 0.5)(codes / 1023) = (c/1023 - 0.5) / 0.5, each step rounded to fp32
@@ -238,6 +288,29 @@ extern "C" int pt_rvq_decode(const int64_t* codes, const float* codebooks, float
   const long long cap = 16ll * pt_num_sms();
   if (blocks > cap) blocks = cap;
   rvq_decode_kernel<<<(unsigned)blocks, 256, 0, ST>>>(codes, codebooks, latents, nframes, T, Q, K);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+
+// scratch: caller-provided, B * Q * T uint16 (the narrowed codes)
+extern "C" int pt_rvq_decode_ws(const int64_t* codes, const float* codebooks, float* latents, void* scratch, int B, int D, int T, int Q, int K,
+                                void* stream) {
+  PT_REQUIRE(B > 0 && T > 0 && Q > 0 && K > 0, "rvq_decode: B=%d T=%d Q=%d K=%d", B, T, Q, K);
+  PT_REQUIRE(D == RD, "rvq_decode: latent dimension must be %d (EnCodec), got %d", RD, D);
+  const size_t smem = (size_t)Q * K * sizeof(float4);
+  if (scratch == nullptr || smem > 200 * 1024 || K > 65536) return pt_rvq_decode(codes, codebooks, latents, B, D, T, Q, K, stream);
+  const long long nframes = (long long)B * T, ncodes = nframes * Q;
+  long long pb = (ncodes + 255) / 256;
+  if (pb > 8ll * pt_num_sms()) pb = 8ll * pt_num_sms();
+  rvq_pack_codes_kernel<<<(unsigned)pb, 256, 0, ST>>>(codes, (uint16_t*)scratch, ncodes, K);
+  PT_LAUNCH_CHECK();
+  PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(rvq_decode_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  // one CTA per SM: 32 slices x `chunks` frame ranges; every CTA pays one 128 KB codebook-slice load, so give it >= 4 K frames
+  int chunks = pt_num_sms() / (RD / 4);
+  if (chunks < 1) chunks = 1;
+  while (chunks > 1 && nframes / chunks < 4096) --chunks;
+  rvq_decode_smem_kernel<<<(unsigned)(chunks * (RD / 4)), DEC_THREADS, smem, ST>>>((const uint16_t*)scratch, codebooks, latents, nframes, T, Q, K,
+                                                                                   chunks);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }

@@ -306,7 +306,7 @@ def rvq_encode(latents, codebooks):
     return codes
 
 
-def rvq_decode(codes, codebooks):
+def rvq_decode(codes, codebooks, gather_l2: bool = False):
     """codes [B, Q, T] int64 -> latents [B, 128, T] fp32 = sum_q E_q[codes_q]."""
     _need(codes, torch.int64, "rvq_decode codes"); _need(codebooks, F32, "rvq_decode codebooks")
     codes, codebooks = codes.contiguous(), codebooks.contiguous()
@@ -314,7 +314,11 @@ def rvq_decode(codes, codebooks):
     Q2, K, D = codebooks.shape
     assert Q == Q2
     lat = torch.empty(B, D, T, dtype=F32, device=codes.device)
-    call("rvq_decode", _p(codes), _p(codebooks), _p(lat), B, D, T, Q, K, _stream())
+    if gather_l2:      # round-1 kernel: codebook rows gathered through L2 (kept for A/B measurements and Q*K too large for shared memory)
+        call("rvq_decode", _p(codes), _p(codebooks), _p(lat), B, D, T, Q, K, _stream())
+    else:
+        scratch = torch.empty(B * Q * T, dtype=torch.int16, device=codes.device)
+        call("rvq_decode_ws", _p(codes), _p(codebooks), _p(lat), _p(scratch), B, D, T, Q, K, _stream())
     return lat
 
 
