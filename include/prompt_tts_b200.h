@@ -249,10 +249,14 @@ int pt_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float
  * bf16).  `w_bf16` (optional) receives bf16(p) in the same flat layout: the GEMM weight operands are views of it (no re-pack). */
 enum {
   PT_OPT_LR = 0, PT_OPT_BETA1, PT_OPT_BETA2, PT_OPT_EPS, PT_OPT_WD, PT_OPT_MAX_NORM, PT_OPT_GSCALE, PT_OPT_STEP,
-  PT_OPT_CLIP, PT_OPT_STEP_SIZE, PT_OPT_INV_SQRT_BC2, PT_OPT_DECAY, PT_OPT_GNORM, PT_OPT_STATE_FLOATS = 16
+  PT_OPT_CLIP, PT_OPT_STEP_SIZE, PT_OPT_INV_SQRT_BC2, PT_OPT_DECAY, PT_OPT_GNORM, PT_OPT_GNORM_SQ, PT_OPT_STATE_FLOATS = 16
 };
 int pt_sumsq_bf16(const void* x, int64_t n, float* out, void* stream);
 int pt_adamw_prepare(float* state, const float* gnorm_sq, void* stream);
+/* deterministic global norm (bit-identical on every rank for identical gradients): `nparts` blocks write one partial sum of squares
+ * each, pt_adamw_prepare_det adds them in a fixed order; the squared norm is left in slot PT_OPT_GNORM_SQ */
+int pt_sumsq_partials(const void* x, int x_is_bf16, int64_t n, float* partials, int nparts, void* stream);
+int pt_adamw_prepare_det(float* state, const float* partials, int nparts, void* stream);
 int pt_adamw_step_dev(float* p, const void* g, int g_is_bf16, float* m, float* v, void* w_bf16, int64_t n, const float* state,
                       void* stream);
 

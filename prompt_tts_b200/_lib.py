@@ -132,6 +132,8 @@ _SIGS = {
     "adamw_step": "pppplfffffipffp",
     "sumsq_bf16": "plpp",
     "adamw_prepare": "ppp",
+    "sumsq_partials": "pilpip",
+    "adamw_prepare_det": "ppip",
     "adamw_step_dev": "ppippplpp",
 }
 _CT = {"p": C.c_void_p, "i": C.c_int, "l": C.c_int64, "f": C.c_float}

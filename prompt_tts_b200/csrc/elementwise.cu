@@ -485,8 +485,55 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 // ---- graph-safe optimiser state: everything that changes from step to step lives in device memory, so one captured step replays
 // correctly.  `st` = PT_OPT_STATE_FLOATS fp32 words (see include/prompt_tts_b200.h): hyper-parameters written by the host (or by an LR
 // scheduler, at any time), the step counter incremented HERE, and the per-step coefficients the elementwise kernel reads.
-__global__ void adamw_prepare_kernel(float* __restrict__ st, const float* __restrict__ gnorm_sq) {
+// Deterministic global norm: every block writes ONE partial sum of squares (fixed block -> element mapping, fixed in-block tree),
+// and the coefficient kernel adds the partials in a fixed order.  Atomic accumulation would round differently from run to run -- and
+// from rank to rank: data-parallel replicas that clip by norms differing in the last bit drift apart, which DDP + clip_grad_norm_
+// in the reference never do.
+template <bool IN_BF16>
+__global__ void __launch_bounds__(256) sumsq_partials_kernel(const void* __restrict__ xv, long long n, float* __restrict__ partials) {
+  float acc = 0.f;
+  if (IN_BF16) {
+    const bf16* x = reinterpret_cast<const bf16*>(xv);
+    const long long n8 = n >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+      float f[8];
+      load8(x + i * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(f[j], f[j], acc);
+    }
+  } else {
+    const float4* x = reinterpret_cast<const float4*>(xv);
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 t = x[i];
+      acc = fmaf(t.x, t.x, acc), acc = fmaf(t.y, t.y, acc), acc = fmaf(t.z, t.z, acc), acc = fmaf(t.w, t.w, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += sh[w];
+    partials[blockIdx.x] = v;
+  }
+}
+
+__global__ void adamw_prepare_kernel(float* __restrict__ st, const float* __restrict__ gnorm_sq, const float* __restrict__ partials, int nparts) {
+  __shared__ float tot;
+  if (partials != nullptr) {      // fixed-order sum of the per-block partials: lane l adds l, l + 32, ...; then the shuffle tree
+    float a = 0.f;
+    for (int i = threadIdx.x; i < nparts; i += 32) a += partials[i];
+    a = warp_sum(a);
+    if (threadIdx.x == 0) tot = a;
+  } else if (threadIdx.x == 0) {
+    tot = gnorm_sq != nullptr ? *gnorm_sq : -1.f;
+  }
+  __syncwarp();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float sumsq = tot;
   const float lr = st[PT_OPT_LR], b1 = st[PT_OPT_BETA1], b2 = st[PT_OPT_BETA2], wd = st[PT_OPT_WD], max_norm = st[PT_OPT_MAX_NORM],
               gscale = st[PT_OPT_GSCALE];
   const int step = __float_as_int(st[PT_OPT_STEP]) + 1;
@@ -495,10 +542,11 @@ __global__ void adamw_prepare_kernel(float* __restrict__ st, const float* __rest
   const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
   float clip = gscale;
   float norm = 0.f;
-  if (gnorm_sq != nullptr) {
-    norm = sqrtf(*gnorm_sq) * gscale;
+  if (sumsq >= 0.f) {
+    norm = sqrtf(sumsq) * gscale;
     if (max_norm > 0.f) clip *= fminf(1.f, max_norm / (norm + 1e-6f));   // torch.nn.utils.clip_grad_norm_
   }
+  st[PT_OPT_GNORM_SQ] = fmaxf(sumsq, 0.f);
   st[PT_OPT_CLIP] = clip;
   st[PT_OPT_STEP_SIZE] = (float)((double)lr / bc1);
   st[PT_OPT_INV_SQRT_BC2] = (float)(1.0 / sqrt(bc2));
@@ -786,7 +834,20 @@ extern "C" int pt_sumsq_bf16(const void* x, int64_t n, float* out, void* stream)
 }
 extern "C" int pt_adamw_prepare(float* state, const float* gnorm_sq, void* stream) {
   PT_REQUIRE(state != nullptr, "adamw_prepare: null state");
-  adamw_prepare_kernel<<<1, 32, 0, ST>>>(state, gnorm_sq);
+  adamw_prepare_kernel<<<1, 32, 0, ST>>>(state, gnorm_sq, nullptr, 0);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+extern "C" int pt_sumsq_partials(const void* x, int x_is_bf16, int64_t n, float* partials, int nparts, void* stream) {
+  PT_REQUIRE(n > 0 && n % 8 == 0 && nparts >= 1 && nparts <= 65535, "sumsq_partials: n=%lld (multiple of 8) nparts=%d", (long long)n, nparts);
+  if (x_is_bf16) sumsq_partials_kernel<true><<<nparts, 256, 0, ST>>>(x, n, partials);
+  else sumsq_partials_kernel<false><<<nparts, 256, 0, ST>>>(x, n, partials);
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+extern "C" int pt_adamw_prepare_det(float* state, const float* partials, int nparts, void* stream) {
+  PT_REQUIRE(state != nullptr && partials != nullptr && nparts >= 1, "adamw_prepare_det: null pointer");
+  adamw_prepare_kernel<<<1, 32, 0, ST>>>(state, nullptr, partials, nparts);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }

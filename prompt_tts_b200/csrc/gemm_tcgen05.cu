@@ -61,12 +61,15 @@ struct alignas(64) KParams {
   int vec_red;          // fp32 atomic output: rows are contiguous and 16-byte aligned -> red.global.add.v4.f32
 };
 
-template <int BN>
+// PAIR: the kernel runs as CTA pairs (tcgen05 cta_group::2): one 256 x BN tile per pair, each CTA holds its own 128 rows of A and
+// HALF of the B tile (the pair's MMA reads both halves), i.e. 32 KB instead of 48 KB of operands per SM and k-iteration at BN = 256.
+template <int BN, bool PAIR = false>
 struct Cfg {
-  static constexpr int BN_S = (BN + 63) / 64 * 64;       // smem rows reserved for B (MN-major needs whole 64-blocks)
+  static constexpr int BN_LOAD = PAIR ? BN / 2 : BN;     // B rows (N) this CTA loads per stage
+  static constexpr int BN_S = (BN_LOAD + 63) / 64 * 64;  // smem rows reserved for B (MN-major needs whole 64-blocks)
   static constexpr int B_STAGE_BYTES = BN_S * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int CTAS_PER_SM = BN <= 128 ? 2 : 1;  // narrow tiles: two persistent CTAs per SM hide each other's issue latency
+  static constexpr int CTAS_PER_SM = (BN <= 128 && !PAIR) ? 2 : 1;  // narrow tiles: two persistent CTAs per SM hide each other's issue latency
   // Epilogue warps.  One warp per TMEM lane quarter is a single dependent instruction stream per SM sub-partition: ~1700
   // instructions per 128 x 256 tile at an IPC of ~0.13 = 13k clocks, more than the mainloop of any K < 1000 (ncu on
   // 24064 x 2560 x 320: same 87 us with K = 64 as with K = 320).  Wide tiles (one CTA per SM) therefore get TWO warps per
@@ -75,7 +78,8 @@ struct Cfg {
   static constexpr int EPI_SPLIT = EPI_WARPS / 4;        // warps sharing one lane quarter
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int EPI_COLS = 32;                     // columns per epilogue pass
-  static constexpr int EPI_BF16_BYTES = EPI_WARPS * 32 * EPI_COLS * 2;   // one dense 32 x 32 bf16 store tile per warp
+  static constexpr int EPI_BUFS = 2;                      // store tiles per warp: pass k+1 is staged while TMA still reads the tile of pass k
+  static constexpr int EPI_BF16_BYTES = EPI_WARPS * EPI_BUFS * 32 * EPI_COLS * 2;   // dense 32 x 32 bf16 store tiles
   static constexpr int EPI_F32_BYTES = EPI_WARPS * 32 * 17 * 4;   // fp32 transpose tile per warp: 32 x 16 (+1), or 32 x 16 swizzled
   static constexpr int EPI_BYTES = EPI_BF16_BYTES > EPI_F32_BYTES ? EPI_BF16_BYTES : EPI_F32_BYTES;
   static constexpr int F32_COLS = 16;   // columns per transpose pass of the atomic epilogue
@@ -130,9 +134,13 @@ struct Sched {
 // MC = 1: independent CTAs.  MC = 2: clusters of two CTAs work on vertically adjacent 128-row tiles of the same column block;
 // each loads its own A tile and HALF of the B tile, multicast into both CTAs' shared memory, which halves the B traffic from L2
 // (operand delivery, ~64 B/clk/SM, is what limits the 256-wide tiles).  A stage is reusable when BOTH CTAs' MMAs have retired.
-template <int BN, int MC>
-__global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_kernel(const __grid_constant__ KParams p) {
-  using C = Cfg<BN>;
+// PAIR (MC = 2): the two CTAs of a cluster are a tcgen05 CTA pair working on ONE 256-row tile.  Rank 0 (the leader) issues
+// tcgen05.mma.cta_group::2; every CTA's TMA loads signal the LEADER's full barrier; stage release and accumulator-ready are
+// multicast commits to both CTAs; both epilogues hand the accumulator back on the leader's tmem_empty barrier.
+template <int BN, int MC, bool PAIR>
+__global__ void __launch_bounds__(Cfg<BN, PAIR>::THREADS, Cfg<BN, PAIR>::CTAS_PER_SM) gemm_kernel(const __grid_constant__ KParams p) {
+  using C = Cfg<BN, PAIR>;
+  static_assert(!PAIR || MC == 2, "a CTA pair is a cluster of two");
   const int crank = MC > 1 ? (int)cluster_ctarank() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -155,17 +163,22 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB[p.seg[0].b_idx])) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), MC);      // one tcgen05.commit arrival per CTA of the cluster
+      mbar_init(empty_bar(s), PAIR ? 1 : MC);      // one tcgen05.commit arrival per issuing CTA (PAIR: the leader's multicast commit)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 32 * C::EPI_WARPS);
+      mbar_init(tmem_empty_bar(a), PAIR ? 2 * C::EPI_WARPS : 32 * C::EPI_WARPS);   // PAIR: one elected lane per epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -191,7 +204,9 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform control flow, one elected lane issues)
     const bool leader = elect_one();
-    const uint32_t tx_bytes = A_STAGE_BYTES + (p.b_kmajor ? BN * BK * 2 : C::B_STAGE_BYTES);
+    const uint32_t tx_own = A_STAGE_BYTES + (p.b_kmajor ? C::BN_LOAD * BK * 2 : C::B_STAGE_BYTES);
+    const uint32_t tx_bytes = PAIR ? 2 * tx_own : tx_own;        // PAIR: the leader's barrier counts the bytes of both CTAs
+    const uint32_t full0_leader = PAIR ? mapa_u32(full_bar(0), 0) : 0;   // shared::cluster address of the leader's full[0]
     int s = 0;
     uint32_t ph = 1;
     while (sched.next(tile, it_begin, it_end)) {
@@ -213,7 +228,31 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
       for (int it = it_begin; it < it_end; ++it) {
         mbar_wait(empty_bar(s), ph);
         const pt_segment_t& sg = p.seg[seg];
-        if (leader) {
+        if (PAIR && leader) {
+          if (crank == 0) mbar_expect_tx(full_bar(s), tx_bytes);
+          const uint32_t sa = smem_base + s * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t fb = full0_leader + 8u * s;
+          const CUtensorMap* ta = &p.tmA[sg.a_idx];
+          const CUtensorMap* tb = &p.tmB[sg.b_idx];
+          const int bz2 = sg.rep_is_batch ? (sg.rep_c2_0 + rep) : z2;
+          const int a2 = p.a_batched[sg.a_idx] ? bz2 : 0, a3 = p.a_batched[sg.a_idx] ? z3 : 0;
+          const int b2 = p.b_batched[sg.b_idx] ? bz2 : 0, b3 = p.b_batched[sg.b_idx] ? z3 : 0;
+          const int ka = sg.a_k0 + kb * BK, kbb = sg.b_k0 + z2 * sg.b_k0_z2 + kb * BK;
+          const int nb0 = n0 + sg.b_mn_shift + crank * C::BN_LOAD;     // this CTA's half of the B tile
+          if (p.a_kmajor) {
+            tma_load_4d_pair(sa, ta, fb, ka, m0 + sg.a_mn_shift, a2, a3);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_4d_pair(sa + j * (BK * 128), ta, fb, m0 + sg.a_mn_shift + j * 64, ka, a2, a3);
+          }
+          if (p.b_kmajor) {
+            tma_load_4d_pair(sb, tb, fb, kbb, nb0, b2, b3);
+          } else {
+#pragma unroll
+            for (int j = 0; j < C::BN_S / 64; ++j) tma_load_4d_pair(sb + j * (BK * 128), tb, fb, nb0 + j * 64, kbb, b2, b3);
+          }
+        } else if (leader) {
           mbar_expect_tx(full_bar(s), tx_bytes);
           const uint32_t sa = smem_base + s * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -262,11 +301,12 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
         if (++s == C::STAGES) s = 0, ph ^= 1;
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
+  } else if (warp == 1 && (!PAIR || crank == 0)) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues;
+    // PAIR: only in the leader CTA, for both SMs)
     const bool leader = elect_one();
     // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
-    const uint32_t idesc = idesc_f16(p.a_kmajor ? 0 : 1, p.b_kmajor ? 0 : 1, BN, BM);
+    const uint32_t idesc = idesc_f16(p.a_kmajor ? 0 : 1, p.b_kmajor ? 0 : 1, BN, PAIR ? 2 * BM : BM);
     const uint32_t a_lbo = p.a_kmajor ? 0u : (uint32_t)(BK * 128), b_lbo = p.b_kmajor ? 0u : (uint32_t)(BK * 128);
     const uint32_t a_kstep = p.a_kmajor ? 2u : 128u, b_kstep = p.b_kmajor ? 2u : 128u;  // (bytes >> 4) per UMMA_K=16
     // UMMA descriptors are linear in the shared-memory address: bases once, (bytes >> 4) added per use
@@ -286,20 +326,39 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
         if (leader) {
           const uint64_t ad = adesc0 + (uint64_t)(s * (C::STAGE_BYTES >> 4));
           const uint64_t bd = bdesc0 + (uint64_t)(s * (C::STAGE_BYTES >> 4));
+          if constexpr (PAIR) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16(dcol, ad + (uint64_t)(k * a_kstep), bd + (uint64_t)(k * b_kstep), idesc, (it > it_begin || k > 0) ? 1u : 0u);
-          if (MC == 1) umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
-          else umma_commit_mc(empty_bar(s), (uint16_t)((1 << MC) - 1));   // ... in both CTAs: the peer multicasts into this stage too
-          if (it == it_end - 1) umma_commit(tmem_full_bar(acc));
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16_pair(dcol, ad + (uint64_t)(k * a_kstep), bd + (uint64_t)(k * b_kstep), idesc, (it > it_begin || k > 0) ? 1u : 0u);
+            umma_commit_pair(empty_bar(s), (uint16_t)3);                          // both CTAs' stages are free when these MMAs retire
+            if (it == it_end - 1) umma_commit_pair(tmem_full_bar(acc), (uint16_t)3);  // both epilogues may read their 128 rows
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16(dcol, ad + (uint64_t)(k * a_kstep), bd + (uint64_t)(k * b_kstep), idesc, (it > it_begin || k > 0) ? 1u : 0u);
+            if (MC == 1) umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+            else umma_commit_mc(empty_bar(s), (uint16_t)((1 << MC) - 1));   // ... in both CTAs: the peer multicasts into this stage too
+            if (it == it_end - 1) umma_commit(tmem_full_bar(acc));
+          }
         }
         __syncwarp();
         if (++s == C::STAGES) s = 0, ph ^= 1;
       }
       ++segi;
     }
-  } else {
+  } else if (warp >= 2) {
     // ------------------------------------------------------------ epilogue (warps 2..), overlapped with the next segment's mainloop
+    // hand an accumulator buffer back to the MMA issuer (PAIR: the leader's barrier, one elected lane per warp of both CTAs)
+    const uint32_t tmem_empty_leader0 = PAIR ? mapa_u32(tmem_empty_bar(0), 0) : 0;
+    auto release_acc = [&](int a) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if constexpr (PAIR) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader0 + 8u * a);
+      } else {
+        mbar_arrive(tmem_empty_bar(a));
+      }
+    };
     const int q = warp & 3;              // TMEM lane quarter this warp may touch
     const int ew = warp - 2;             // epilogue warp index: private staging tile
     const int half = ew >> 2;            // which of the EPI_SPLIT warps of this quarter: takes passes half, half + EPI_SPLIT, ...
@@ -307,6 +366,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
     constexpr int ET = 32 * C::EPI_WARPS;
     const int et = threadIdx.x - 64;
     int segi = 0;
+    int pc = 0;                          // bf16 path: store passes done by this warp (selects the staging tile)
     int staged_n0 = -1, staged_z2 = -1;
     while (sched.next(tile, it_begin, it_end)) {
       int m0, n0, z2, z3;
@@ -345,8 +405,11 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
         // Store tile of this warp: 32 rows x 64 bytes, dense, in the SWIZZLE_64B pattern of the output tensor map (16-byte chunk
         // index ^= address bits 7-8), which also makes the row-per-thread writes below bank-conflict free.  One elected lane hands
         // the tile to TMA: no LDS / STG / 64-bit address arithmetic / tail predicates in the epilogue (tails are clipped by TMA).
-        uint8_t* stg = sepi + ew * (32 * CH * 2);
-        const uint32_t stg_u32 = smem_u32(stg);
+        // Two tiles per warp, used alternately (`pc` = passes this warp has stored so far): waiting for TMA to finish READING the
+        // single tile before every pass serialised the epilogue with the store latency (4 passes x ~1 us per 128 x 256 tile, more
+        // than the whole mainloop of a K <= 640 GEMM).
+        uint8_t* stg_base = sepi + ew * (C::EPI_BUFS * 32 * CH * 2);
+        uint8_t* stg = stg_base + (pc & 1) * (32 * CH * 2);
         auto cell = [&](int row, int chunk) { return stg + row * (CH * 2) + ((chunk ^ ((row >> 1) & 3)) << 4); };
         const int mw = m0 + q * 32;                // first row of this warp
         const int crow = lane / VPR, cvec = lane % VPR;
@@ -368,8 +431,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
         mbar_wait(tmem_full_bar(acc), full_parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (last_k < 0) {   // no column of this warp's passes is inside N: nothing to read, hand the buffer back
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(tmem_empty_bar(acc));
+          release_acc(acc);
         } else {
           tmem_ld32(tbase + (uint32_t)(half * CH), v[0]);
         }
@@ -385,10 +447,10 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
               if (has_res) load_res(c + ES, rr[(k + 1) & 1]);
             } else {
               // the accumulator is in registers: hand the TMEM buffer back to the MMA warp
-              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              mbar_arrive(tmem_empty_bar(acc));
+              release_acc(acc);
             }
-            if (lane == 0) tma_store_wait_read();   // the previous store of this warp has finished reading the tile
+            stg = stg_base + (pc & 1) * (32 * CH * 2);
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used THIS tile (two passes ago) has read it
             __syncwarp();
             if (has_res) {   // residual rows arrive coalesced (8 rows x 64 bytes per access) and are re-read row-per-thread
 #pragma unroll
@@ -421,9 +483,10 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_4d(&p.tmO, stg_u32, nb, mw, z2, z3);
+              tma_store_4d(&p.tmO, smem_u32(stg), nb, mw, z2, z3);
               tma_store_commit();
             }
+            ++pc;
           }
         }
       } else {
@@ -440,8 +503,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
         mbar_wait(tmem_full_bar(acc), full_parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (last_k < 0) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(tmem_empty_bar(acc));
+          release_acc(acc);
         } else {
           tmem_ld16(tbase + (uint32_t)(half * FC), v[0]);
         }
@@ -458,8 +520,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
             if (k < last_k) {
               tmem_ld16(tbase + (uint32_t)((c + ES) * FC), v[(k + 1) & 1]);
             } else {
-              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              mbar_arrive(tmem_empty_bar(acc));
+              release_acc(acc);
             }
             float f[FC];
 #pragma unroll
@@ -537,7 +598,8 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, Cfg<BN>::CTAS_PER_SM) gemm_k
   __syncthreads();
   if (MC > 1) cluster_sync_all();      // do not leave while the peer can still multicast into / arrive on this CTA's shared memory
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -605,16 +667,17 @@ int encode_output(CUtensorMap* tm, const pt_gemm_t* g) {
   return PT_OK;
 }
 
-template <int BN, int MC>
+template <int BN, int MC, bool PAIR = false>
 int launch(const KParams& kp, dim3 grid, cudaStream_t st) {
-  PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(gemm_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+  using CF = Cfg<BN, PAIR>;
+  PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(gemm_kernel<BN, MC, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
   if (MC == 1) {
-    gemm_kernel<BN, MC><<<grid, Cfg<BN>::THREADS, Cfg<BN>::SMEM_BYTES, st>>>(kp);
+    gemm_kernel<BN, MC, PAIR><<<grid, CF::THREADS, CF::SMEM_BYTES, st>>>(kp);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(Cfg<BN>::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+    cfg.blockDim = dim3(CF::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = CF::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -630,15 +693,15 @@ int launch(const KParams& kp, dim3 grid, cudaStream_t st) {
       int n = 0;
       cudaLaunchConfig_t q = cfg;
       q.gridDim = dim3((unsigned)(pt_num_sms_physical() / MC * MC), 1, 1);
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, MC>, &q) != cudaSuccess || n < 1) {
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, MC, PAIR>, &q) != cudaSuccess || n < 1) {
         (void)cudaGetLastError();
         n = pt_num_sms_physical() / MC;
       }
       max_clusters = n;
-      if (getenv("PT_GEMM_DEBUG")) fprintf(stderr, "[pt_gemm] BN=%d cluster=%d: %d clusters resident at once\n", BN, MC, n);
+      if (getenv("PT_GEMM_DEBUG")) fprintf(stderr, "[pt_gemm] BN=%d cluster=%d pair=%d: %d clusters resident at once\n", BN, MC, (int)PAIR, n);
     }
     if ((int)grid.x / MC > max_clusters) cfg.gridDim = dim3((unsigned)(max_clusters * MC), 1, 1);
-    PT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, MC>, kp));
+    PT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, MC, PAIR>, kp));
   }
   PT_LAUNCH_CHECK();
   return PT_OK;
@@ -732,6 +795,10 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   // (a cluster of four sharing B in quarters was measured too: 24064 x 2560 x 320 67 -> 74 us, 6016 x 3840 x 1280 57 -> 64 us --
   // what limits the mainloop is each SM's own ingest rate, ~64 B/clk, which multicast does not change)
   const int mc = (bn == 256 && mt >= 2 && allow_cluster && !streamk) ? 2 : 1;
+  // ... and those clusters run as tcgen05 CTA pairs (cta_group::2: one 256 x 256 tile per pair, each SM ingests 32 KB instead of
+  // 48 KB per k-iteration) unless an odd, small number of row tiles would leave a quarter of a pair's work empty
+  static const bool no_pair = getenv("PT_GEMM_NO_PAIR") != nullptr;
+  const bool pair = mc == 2 && !no_pair && (mt % 2 == 0 || mt >= 8);
   for (int i = 0; i < 2; ++i) {
     if (a_used[i]) {
       int r = encode_operand(&kp.tmA[i], g->a[i], BM, i ? "A1" : "A0");
@@ -793,6 +860,6 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
     case 160: return launch<160, 1>(kp, grid, st);
     case 192: return launch<192, 1>(kp, grid, st);
     case 224: return launch<224, 1>(kp, grid, st);
-    default: return mc == 2 ? launch<256, 2>(kp, grid, st) : launch<256, 1>(kp, grid, st);
+    default: return mc == 2 ? (pair ? launch<256, 2, true>(kp, grid, st) : launch<256, 2>(kp, grid, st)) : launch<256, 1>(kp, grid, st);
   }
 }

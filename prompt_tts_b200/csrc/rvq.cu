@@ -201,42 +201,56 @@ __global__ void rvq_pack_codes_kernel(const int64_t* __restrict__ codes, uint16_
     out[i] = (uint16_t)min(max((long long)codes[i], 0ll), (long long)K - 1);
 }
 
-constexpr int DEC_THREADS = 512;
+constexpr int DEC_THREADS = 1024;
+constexpr int DEC_FPT = 4;      // frames per thread in flight: the loop is latency-bound (code loads from L2, then dependent LDS)
 __global__ void __launch_bounds__(DEC_THREADS, 1) rvq_decode_smem_kernel(const uint16_t* __restrict__ codes, const float* __restrict__ cb,
                                                                         float* __restrict__ lat, long long nframes, int T, int Q, int K,
                                                                         int chunks) {
   extern __shared__ float4 scb[];        // [Q][K] : dims d0 .. d0+3 of every code
   const int slice = blockIdx.x % (RD / 4), chunk = blockIdx.x / (RD / 4);
   const int d0 = slice * 4;
-  for (int i = threadIdx.x; i < Q * K; i += DEC_THREADS) scb[i] = *reinterpret_cast<const float4*>(cb + (long long)i * RD + d0);
+  for (int i = threadIdx.x; i < Q * K; i += DEC_THREADS) scb[i] = __ldg(reinterpret_cast<const float4*>(cb + (long long)i * RD + d0));
   __syncthreads();
   const long long per = ((nframes + chunks - 1) / chunks + 31) / 32 * 32;      // whole warps of consecutive frames
   const long long f_begin = (long long)chunk * per, f_end = min(nframes, f_begin + per);
-  for (long long f = f_begin + threadIdx.x; f < f_end; f += DEC_THREADS) {
-    const long long b = f / T;
-    const int t = (int)(f - b * T);
-    const uint16_t* cp = codes + (b * Q) * T + t;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (Q == 8) {
-      uint16_t c[8];
+  for (long long f0 = f_begin + threadIdx.x; f0 < f_end; f0 += DEC_THREADS * DEC_FPT) {
+    uint16_t c[DEC_FPT][8];
+    long long ob[DEC_FPT];
+    bool ok[DEC_FPT];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) c[q] = cp[(long long)q * T];
+    for (int u = 0; u < DEC_FPT; ++u) {
+      const long long f = f0 + (long long)u * DEC_THREADS;
+      ok[u] = f < f_end;
+      const long long fc = ok[u] ? f : f_begin;
+      const long long b = fc / T;
+      const int t = (int)(fc - b * T);
+      ob[u] = (b * RD + d0) * T + t;
+      const uint16_t* cp = codes + (b * Q) * T + t;
+      if (Q == 8) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 e = scb[q * K + c[q]];
-        acc.x += e.x, acc.y += e.y, acc.z += e.z, acc.w += e.w;
-      }
-    } else {
-      for (int q = 0; q < Q; ++q) {
-        const float4 e = scb[q * K + cp[(long long)q * T]];
-        acc.x += e.x, acc.y += e.y, acc.z += e.z, acc.w += e.w;
+        for (int q = 0; q < 8; ++q) c[u][q] = __ldg(cp + (long long)q * T);
+      } else {
+        for (int q = 0; q < 8; ++q) c[u][q] = q < Q ? __ldg(cp + (long long)q * T) : (uint16_t)0;
       }
     }
-    float* o = lat + (b * RD + d0) * T + t;
-    o[0] = acc.x;
-    o[(long long)T] = acc.y;
-    o[2ll * T] = acc.z;
-    o[3ll * T] = acc.w;
+#pragma unroll
+    for (int u = 0; u < DEC_FPT; ++u) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < Q) {      // q ascending, fp32 adds: bit-equal to the sequential codeword sum
+          const float4 e = scb[q * K + c[u][q]];
+          acc.x += e.x, acc.y += e.y, acc.z += e.z, acc.w += e.w;
+        }
+      }
+      if (ok[u]) {
+        float* o = lat + ob[u];
+        __stcs(o, acc.x);
+        __stcs(o + (long long)T, acc.y);
+        __stcs(o + 2ll * T, acc.z);
+        __stcs(o + 3ll * T, acc.w);
+      }
+    }
   }
 }
 
@@ -298,7 +312,7 @@ extern "C" int pt_rvq_decode_ws(const int64_t* codes, const float* codebooks, fl
   PT_REQUIRE(B > 0 && T > 0 && Q > 0 && K > 0, "rvq_decode: B=%d T=%d Q=%d K=%d", B, T, Q, K);
   PT_REQUIRE(D == RD, "rvq_decode: latent dimension must be %d (EnCodec), got %d", RD, D);
   const size_t smem = (size_t)Q * K * sizeof(float4);
-  if (scratch == nullptr || smem > 200 * 1024 || K > 65536) return pt_rvq_decode(codes, codebooks, latents, B, D, T, Q, K, stream);
+  if (scratch == nullptr || smem > 200 * 1024 || K > 65536 || Q > 8) return pt_rvq_decode(codes, codebooks, latents, B, D, T, Q, K, stream);
   const long long nframes = (long long)B * T, ncodes = nframes * Q;
   long long pb = (ncodes + 255) / 256;
   if (pb > 8ll * pt_num_sms()) pb = 8ll * pt_num_sms();

@@ -23,7 +23,8 @@ import torch
 from . import ops
 
 # slots of the device-side state (include/prompt_tts_b200.h)
-LR, BETA1, BETA2, EPS, WD, MAX_NORM, GSCALE, STEP, CLIP, STEP_SIZE, INV_SQRT_BC2, DECAY, GNORM, NSTATE = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 16
+LR, BETA1, BETA2, EPS, WD, MAX_NORM, GSCALE, STEP, CLIP, STEP_SIZE, INV_SQRT_BC2, DECAY, GNORM, GNORM_SQ, NSTATE = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16
+NPARTS = 1184      # blocks of the deterministic norm reduction (8 per SM)
 
 
 class FusedClipAdamW:
@@ -31,7 +32,7 @@ class FusedClipAdamW:
                  max_norm: float = 1.0):
         self.stepper = stepper
         self.lr, self.betas, self.wd, self.eps, self.max_norm = lr, betas, weight_decay, eps, max_norm
-        self.pflat = self.m = self.v = self.wflat = self.gnorm_sq = self.state = None
+        self.pflat = self.m = self.v = self.wflat = self.partials = self.state = None
 
     # ------------------------------------------------------------------------------------------ flat state
     def attach(self) -> None:
@@ -73,7 +74,7 @@ class FusedClipAdamW:
         ops.cast_bf16(self.pflat, self.wflat)
         self.m = torch.zeros_like(self.pflat)
         self.v = torch.zeros_like(self.pflat)
-        self.gnorm_sq = torch.zeros((), dtype=torch.float32, device=dev)
+        self.partials = torch.zeros(NPARTS, dtype=torch.float32, device=dev)
         host = [0.0] * NSTATE
         host[LR], host[BETA1], host[BETA2], host[EPS], host[WD], host[MAX_NORM], host[GSCALE] = (
             self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.max_norm if self.max_norm else 0.0, 1.0)
@@ -107,20 +108,22 @@ class FusedClipAdamW:
         """Clip to max_norm (global L2 norm over all gradients, like clip_grad_norm_) and apply AdamW in place.
         Returns the squared gradient norm as a 0-d device tensor (no synchronisation).  A no-op on micro-steps that do not
         synchronise gradients (accelerate's optimizer wrapper under `accumulate`, train.py:80,118)."""
+        self.attach()
         if not getattr(self.stepper, "sync_gradients", True):
             return self.gnorm_sq
-        self.attach()
         gs = self.stepper.grad_sync
         g_bf16 = gs.comm is not None and not gs.cast_back
-        self.gnorm_sq.zero_()
-        if g_bf16:
-            ops.call("sumsq_bf16", ops._p(gs.comm), gs.total, ops._p(self.gnorm_sq), ops._stream())
-        else:
-            ops.call("sumsq_f32", ops._p(gs.flat), gs.total, ops._p(self.gnorm_sq), ops._stream())
-        ops.call("adamw_prepare", ops._p(self.state), ops._p(self.gnorm_sq), ops._stream())
+        # global norm, deterministically (identical gradients -> bit-identical clip factor on every rank: replicas never drift apart)
+        ops.call("sumsq_partials", ops._p(gs.comm if g_bf16 else gs.flat), 1 if g_bf16 else 0, gs.total, ops._p(self.partials), NPARTS, ops._stream())
+        ops.call("adamw_prepare_det", ops._p(self.state), ops._p(self.partials), NPARTS, ops._stream())
         ops.call("adamw_step_dev", ops._p(self.pflat), ops._p(gs.comm if g_bf16 else gs.flat), 1 if g_bf16 else 0, ops._p(self.m),
                  ops._p(self.v), ops._p(self.wflat), gs.total, ops._p(self.state), ops._stream())
         return self.gnorm_sq
+
+    @property
+    def gnorm_sq(self) -> torch.Tensor:
+        """Squared global gradient norm of the last step (0-d device tensor, no synchronisation)."""
+        return self.state[GNORM_SQ]
 
     # ------------------------------------------------------------------------------------------ checkpoints (train.py:141-143)
     def state_dict(self) -> Dict[str, torch.Tensor]:

@@ -50,6 +50,52 @@ def test_cluster_multicast_agrees_with_single_cta(cuda, M, N, K):
     assert rel(outs[0], A.float() @ B.float().t()) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,b_kmajor", [(1024, 512, 960, True), (2048, 1280, 320, True), (1152, 640, 448, False), (4096, 320, 200, False),
+                                           (1100, 2560, 64, True)])
+def test_cta_pair_mode(cuda, M, N, K, b_kmajor):
+    """block_n = 256 with an even (or >= 8) number of row tiles runs as tcgen05 CTA pairs (cta_group::2: one 256 x 256 tile per
+    pair, each CTA holding half of B); block_n = 257 is the same tile width on independent CTAs.  Same k order -> identical bits.
+    Ragged M (the second CTA of the last pair partly / fully out of bounds), ragged N and K, both B majornesses, fused epilogue."""
+    from prompt_tts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = bf(torch.randn(M, K, device=cuda, generator=g))
+    B = bf(torch.randn(N, K, device=cuda, generator=g)) if b_kmajor else bf(torch.randn(K, N, device=cuda, generator=g))
+    bias = torch.randn(N, device=cuda, generator=g)
+    res = bf(torch.randn(M, N, device=cuda, generator=g))
+    outs = []
+    for bn in (256, 257):
+        o = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
+        for _ in range(3):      # several launches: barrier phases / TMEM allocation are per launch, the schedule is persistent
+            ops.gemm([ops.operand(A, True)], [ops.operand(B, b_kmajor)], [ops.segment(K)], M, N, o, bias=bias, residual=res, block_n=bn)
+        outs.append(o)
+    torch.cuda.synchronize()
+    ref = A.float() @ (B.float().t() if b_kmajor else B.float()) + bias + res.float()
+    assert torch.isfinite(outs[0].float()).all()
+    assert rel(outs[0], ref) < 4e-3
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_cta_pair_mode_batched_conv(cuda):
+    """The k=3 convolution as it runs at level 0 of the bench model (3 shifted segments, batch on z2, time shift + residual epilogue)
+    with the 256-wide pair tiles forced, against F.conv1d."""
+    from prompt_tts_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Bn, L, Ci, Co = 4, 752, 192, 512
+    x = bf(torch.randn(Bn, L, Ci, device=cuda, generator=g))
+    w = bf(torch.randn(Co, Ci, 3, device=cuda, generator=g) * 0.1)
+    wp = w.permute(0, 2, 1).reshape(Co, 3 * Ci).contiguous()
+    bias = torch.randn(Co, device=cuda, generator=g)
+    shift = torch.randn(Bn, Co, device=cuda, generator=g)
+    res = bf(torch.randn(Bn, L, Co, device=cuda, generator=g))
+    o = torch.full((Bn, L, Co), float("nan"), device=cuda, dtype=torch.bfloat16)
+    segs = [ops.segment(Ci, a_shift=t - 1, b_k0=t * Ci) for t in range(3)]
+    ops.gemm([ops.operand(x, True, batched=True)], [ops.operand(wp, True)], segs, L, Co, o, out_strides=(Co, L * Co, 0), nz2=Bn, bias=bias,
+             bias_z2=shift, bias_z2_stride=Co, residual=res, res_strides=(Co, L * Co, 0), block_n=256)
+    torch.cuda.synchronize()
+    ref = F.conv1d(x.float().transpose(1, 2), w.float(), bias, padding=1) + shift[:, :, None] + res.float().transpose(1, 2)
+    assert rel(o.float().transpose(1, 2), ref) < 4e-3
+
+
 @pytest.mark.parametrize("bn", [64, 128, 160, 192, 224, 256])
 def test_every_tile_width(cuda, bn):
     from prompt_tts_b200 import ops
