@@ -78,7 +78,12 @@ struct Cfg {
   static constexpr int EPI_SPLIT = EPI_WARPS / 4;        // warps sharing one lane quarter
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int EPI_COLS = 32;                     // columns per epilogue pass
-  static constexpr int EPI_BUFS = 2;                      // store tiles per warp: pass k+1 is staged while TMA still reads the tile of pass k
+#ifndef PT_EPI_BUFS
+#define PT_EPI_BUFS 1
+#endif
+  // Store tiles per warp.  Two (pass k+1 staged while TMA still reads the tile of pass k) were measured against one in a same-box
+  // A/B of the whole step: 45.39 / 45.20 vs 45.27 / 45.46 ms -- no difference, so the default keeps the shared memory for the ring.
+  static constexpr int EPI_BUFS = CTAS_PER_SM == 1 ? PT_EPI_BUFS : 1;
   static constexpr int EPI_BF16_BYTES = EPI_WARPS * EPI_BUFS * 32 * EPI_COLS * 2;   // dense 32 x 32 bf16 store tiles
   static constexpr int EPI_F32_BYTES = EPI_WARPS * 32 * 17 * 4;   // fp32 transpose tile per warp: 32 x 16 (+1), or 32 x 16 swizzled
   static constexpr int EPI_BYTES = EPI_BF16_BYTES > EPI_F32_BYTES ? EPI_BF16_BYTES : EPI_F32_BYTES;
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(Cfg<BN, PAIR>::THREADS, Cfg<BN, PAIR>::CTAS_PE
         // single tile before every pass serialised the epilogue with the store latency (4 passes x ~1 us per 128 x 256 tile, more
         // than the whole mainloop of a K <= 640 GEMM).
         uint8_t* stg_base = sepi + ew * (C::EPI_BUFS * 32 * CH * 2);
-        uint8_t* stg = stg_base + (pc & 1) * (32 * CH * 2);
+        uint8_t* stg = stg_base + (pc & (C::EPI_BUFS - 1)) * (32 * CH * 2);
         auto cell = [&](int row, int chunk) { return stg + row * (CH * 2) + ((chunk ^ ((row >> 1) & 3)) << 4); };
         const int mw = m0 + q * 32;                // first row of this warp
         const int crow = lane / VPR, cvec = lane % VPR;
@@ -449,8 +454,11 @@ __global__ void __launch_bounds__(Cfg<BN, PAIR>::THREADS, Cfg<BN, PAIR>::CTAS_PE
               // the accumulator is in registers: hand the TMEM buffer back to the MMA warp
               release_acc(acc);
             }
-            stg = stg_base + (pc & 1) * (32 * CH * 2);
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used THIS tile (two passes ago) has read it
+            stg = stg_base + (pc & (C::EPI_BUFS - 1)) * (32 * CH * 2);
+            if (lane == 0) {   // the store that last used THIS tile has read it
+              if (C::EPI_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
             __syncwarp();
             if (has_res) {   // residual rows arrive coalesced (8 rows x 64 bytes per access) and are re-read row-per-thread
 #pragma unroll
@@ -798,7 +806,10 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   // ... and those clusters run as tcgen05 CTA pairs (cta_group::2: one 256 x 256 tile per pair, each SM ingests 32 KB instead of
   // 48 KB per k-iteration) unless an odd, small number of row tiles would leave a quarter of a pair's work empty
   static const bool no_pair = getenv("PT_GEMM_NO_PAIR") != nullptr;
-  const bool pair = mc == 2 && !no_pair && (mt % 2 == 0 || mt >= 8);
+  // Measured per shape (tools/gemm_sweep.py, profiles/r02_gemm_sweep.txt): the pair wins 3-10 % from 16 k-iterations per tile up
+  // (K >= 1024) and loses up to 20 % on short contractions, where the cross-SM commit / barrier round trip per tile is not amortised
+  // (24064 x 2560 x 320: 62 vs 51 us).
+  const bool pair = mc == 2 && !no_pair && (mt % 2 == 0 || mt >= 8) && total >= 16;
   for (int i = 0; i < 2; ++i) {
     if (a_used[i]) {
       int r = encode_operand(&kp.tmA[i], g->a[i], BM, i ? "A1" : "A0");

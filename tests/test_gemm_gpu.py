@@ -50,10 +50,10 @@ def test_cluster_multicast_agrees_with_single_cta(cuda, M, N, K):
     assert rel(outs[0], A.float() @ B.float().t()) < 4e-3
 
 
-@pytest.mark.parametrize("M,N,K,b_kmajor", [(1024, 512, 960, True), (2048, 1280, 320, True), (1152, 640, 448, False), (4096, 320, 200, False),
-                                           (1100, 2560, 64, True)])
+@pytest.mark.parametrize("M,N,K,b_kmajor", [(1024, 512, 1088, True), (2048, 1280, 1024, True), (1152, 640, 1472, False), (4096, 320, 1032, False),
+                                           (1100, 2560, 1024, True), (2048, 1280, 320, True)])
 def test_cta_pair_mode(cuda, M, N, K, b_kmajor):
-    """block_n = 256 with an even (or >= 8) number of row tiles runs as tcgen05 CTA pairs (cta_group::2: one 256 x 256 tile per
+    """block_n = 256 with an even (or >= 8) number of row tiles and >= 16 k-iterations runs as tcgen05 CTA pairs (cta_group::2: one 256 x 256 tile per
     pair, each CTA holding half of B); block_n = 257 is the same tile width on independent CTAs.  Same k order -> identical bits.
     Ragged M (the second CTA of the last pair partly / fully out of bounds), ragged N and K, both B majornesses, fused epilogue."""
     from prompt_tts_b200 import ops
@@ -80,7 +80,7 @@ def test_cta_pair_mode_batched_conv(cuda):
     with the 256-wide pair tiles forced, against F.conv1d."""
     from prompt_tts_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(5)
-    Bn, L, Ci, Co = 4, 752, 192, 512
+    Bn, L, Ci, Co = 4, 752, 384, 512
     x = bf(torch.randn(Bn, L, Ci, device=cuda, generator=g))
     w = bf(torch.randn(Co, Ci, 3, device=cuda, generator=g) * 0.1)
     wp = w.permute(0, 2, 1).reshape(Co, 3 * Ci).contiguous()
