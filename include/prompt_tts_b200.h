@@ -185,6 +185,8 @@ int pt_pack_conv_weight(const float* w, void* wp, int Co, int Ci, int k, void* s
 int pt_unpack_conv_wgrad(const float* gp, float* g, int Co, int Ci, int k, int accumulate, void* stream);
 /* column sums of a bf16 matrix: out[c] += sum_r x[r, c]  (bias gradients) */
 int pt_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int cols, void* stream);
+/* the same reduction in a 128-thread / 4 KB shape that fits beside a persistent GEMM CTA on the same SM (for launches on a second stream) */
+int pt_colsum_bf16_lite(const void* x, int64_t ld, float* out, int64_t rows, int cols, void* stream);
 /* per-(batch, channel) sum over L of dy[B, L, C] (time-shift gradient): out[b * out_stride + c] fp32 (overwritten) */
 int pt_batch_colsum_bf16(const void* x, float* out, int64_t out_stride, int B, int L, int C, void* stream);
 

@@ -111,6 +111,7 @@ _SIGS = {
     "pack_conv_weight": "ppiiip",
     "unpack_conv_wgrad": "ppiiiip",
     "colsum_bf16": "plplip",
+    "colsum_bf16_lite": "plplip",
     "batch_colsum_bf16": "ppliiip",
     "conv_in_fwd": "ppppiiiip",
     "conv_in_bwd": "ppppiiiip",

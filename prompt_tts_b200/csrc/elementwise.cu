@@ -332,6 +332,50 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   }
 }
 
+// The same reduction sized to run BESIDE a persistent GEMM / attention CTA on the same SM (those leave ~11 K registers and ~8 KB of
+// shared memory per SM): 128 threads, 4 KB of shared memory.  Bias gradients are off the backward's critical path; launched on a
+// second stream they fill the SMs' idle resources and the gaps at kernel boundaries instead of a slot of their own in the stream.
+__global__ void __launch_bounds__(128, 4) colsum_lite_kernel(const bf16* __restrict__ x, long long ld, float* __restrict__ out, long long rows, int cols,
+                                                             int rows_per_cta, long long batch_stride, long long out_stride) {
+  __shared__ float sh[4][256];
+  x += (long long)blockIdx.z * batch_stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (c < cols) {
+    const bf16* xc = x + c;
+    long long r = r0 + warp;
+    for (; r + 12 < r1; r += 16) {
+      float f0[8], f1[8], f2[8], f3[8];
+      load8(xc + r * ld, f0);
+      load8(xc + (r + 4) * ld, f1);
+      load8(xc + (r + 8) * ld, f2);
+      load8(xc + (r + 12) * ld, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; r < r1; r += 4) {
+      float f0[8];
+      load8(xc + r * ld, f0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f0[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[warp][lane * 8 + j] = s[j];
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int cl = threadIdx.x + h * 128;
+    const int cc = blockIdx.x * 256 + cl;
+    if (cc < cols) atomicAdd(&out[(long long)blockIdx.z * out_stride + cc], (sh[0][cl] + sh[1][cl]) + (sh[2][cl] + sh[3][cl]));
+  }
+}
+
 __global__ void time_sinusoid_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int B, int dim) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -733,7 +777,7 @@ extern "C" int pt_unpack_conv_wgrad(const float* gp, float* g, int Co, int Ci, i
 }
 
 static int colsum_launch(const bf16* x, long long ld, float* out, long long rows, int cols, int nbatch, long long batch_stride,
-                         long long out_stride, cudaStream_t st) {
+                         long long out_stride, cudaStream_t st, bool lite = false) {
   PT_REQUIRE(cols % 8 == 0 && ld % 8 == 0 && nbatch >= 1 && nbatch <= 65535, "colsum: cols=%d", cols);
   const int cblocks = (cols + 255) / 256;
   long long want = (8ll * pt_num_sms() + (long long)nbatch * cblocks - 1) / ((long long)nbatch * cblocks);
@@ -742,13 +786,20 @@ static int colsum_launch(const bf16* x, long long ld, float* out, long long rows
   if (rpc < 64) rpc = 64;
   const unsigned rchunks = (unsigned)((rows + rpc - 1) / rpc);
   PT_REQUIRE(rchunks <= 65535, "colsum: too many row chunks");
-  colsum_kernel<<<dim3(cblocks, rchunks, nbatch), 256, 0, st>>>(x, ld, out, rows, cols, (int)rpc, batch_stride, out_stride);
+  if (lite)
+    colsum_lite_kernel<<<dim3(cblocks, rchunks, nbatch), 128, 0, st>>>(x, ld, out, rows, cols, (int)rpc, batch_stride, out_stride);
+  else
+    colsum_kernel<<<dim3(cblocks, rchunks, nbatch), 256, 0, st>>>(x, ld, out, rows, cols, (int)rpc, batch_stride, out_stride);
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
 extern "C" int pt_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int cols, void* stream) {
   PT_REQUIRE(rows > 0 && cols > 0, "colsum: rows=%lld cols=%d", (long long)rows, cols);
   return colsum_launch((const bf16*)x, ld, out, rows, cols, 1, 0, cols, ST);
+}
+extern "C" int pt_colsum_bf16_lite(const void* x, int64_t ld, float* out, int64_t rows, int cols, void* stream) {
+  PT_REQUIRE(rows > 0 && cols > 0, "colsum: rows=%lld cols=%d", (long long)rows, cols);
+  return colsum_launch((const bf16*)x, ld, out, rows, cols, 1, 0, cols, ST, true);
 }
 extern "C" int pt_batch_colsum_bf16(const void* x, float* out, int64_t out_stride, int B, int L, int C, void* stream) {
   PT_REQUIRE(B > 0 && L > 0 && C > 0 && out_stride >= C, "batch_colsum: B=%d L=%d C=%d", B, L, C);

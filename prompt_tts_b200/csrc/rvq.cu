@@ -42,8 +42,12 @@ __global__ void __launch_bounds__(256, 1) rvq_encode_kernel(const float* __restr
   }
   __syncthreads();
 
-  const int tf = tid % 16;   // frame group: frames tf*8 .. tf*8+7
+  // frame group of this thread: frames tf*4 .. tf*4+3 and 64 + tf*4 .. 64 + tf*4+3.  Two 16-byte loads per d whose addresses are 16 bytes
+  // apart across the 16 lanes of a frame group (contiguous 256 bytes = 2 wavefronts); the first version gave a thread 8 CONSECUTIVE
+  // frames, i.e. 32-byte lane stride = 4-way bank conflicts on every residual load (ncu: 39 % of all shared wavefronts were conflicts).
+  const int tf = tid % 16;
   const int tc = tid / 16;   // code group:  codes  tc*8 .. tc*8+7 of the tile
+  auto fidx = [&](int i) { return (i < 4 ? 0 : 64 - 4) + tf * 4 + i; };   // frame of this thread's i-th accumulator row
 
   for (int q = 0; q < Q; ++q) {
     // |r|^2 per frame, ascending d with fmaf (one thread per frame)
@@ -80,8 +84,8 @@ __global__ void __launch_bounds__(256, 1) rvq_encode_kernel(const float* __restr
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 #pragma unroll 4
       for (int d = 0; d < RD; ++d) {
-        const float4 xa = *reinterpret_cast<const float4*>(sx + d * TF + tf * 8);
-        const float4 xb = *reinterpret_cast<const float4*>(sx + d * TF + tf * 8 + 4);
+        const float4 xa = *reinterpret_cast<const float4*>(sx + d * TF + tf * 4);
+        const float4 xb = *reinterpret_cast<const float4*>(sx + d * TF + 64 + tf * 4);
         const float4 ea = *reinterpret_cast<const float4*>(se + d * TC + tc * 8);
         const float4 eb = *reinterpret_cast<const float4*>(se + d * TC + tc * 8 + 4);
         const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(256, 1) rvq_encode_kernel(const float* __restr
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             // dist = -((xx - 2*dot) + ee), the reference's evaluation order, each step rounded to fp32
-            const float dist = -__fadd_rn(__fsub_rn(sxx[tf * 8 + i], __fmul_rn(2.f, acc[i][j])), ee);
+            const float dist = -__fadd_rn(__fsub_rn(sxx[fidx(i)], __fmul_rn(2.f, acc[i][j])), ee);
             if (dist > best[i]) {  // ascending code order within the thread: strict > keeps the first maximum
               best[i] = dist;
               bidx[i] = code;
@@ -111,8 +115,8 @@ __global__ void __launch_bounds__(256, 1) rvq_encode_kernel(const float* __restr
     // reduce over the 16 code groups: larger value wins, equal values -> smaller index
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      sbv[tc * TF + tf * 8 + i] = best[i];
-      sbi[tc * TF + tf * 8 + i] = bidx[i];
+      sbv[tc * TF + fidx(i)] = best[i];
+      sbi[tc * TF + fidx(i)] = bidx[i];
     }
     __syncthreads();
     if (tid < TF) {

@@ -93,6 +93,8 @@ class GradSync:
         self._sent = hi
         if self.world == 1:
             return
+        if self._tape is not None and hasattr(self._tape, "join_side"):
+            self._tape.join_side()      # bias gradients computed on the side stream belong to this bucket too
         if self.comm_dtype == torch.bfloat16:
             from . import ops
             ops.cast_bf16(self.flat[lo:hi], self.comm[lo:hi])

@@ -10,6 +10,7 @@ Every tensor here is a torch CUDA tensor used as a memory handle; all arithmetic
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -30,6 +31,38 @@ class Var:
         self.needs_grad = needs_grad
 
 
+class SideLane:
+    """A second stream for backward work that nothing downstream waits for (bias gradients: only the optimiser / the gradient
+    exchange read them).  A 128-thread column-sum CTA fits beside a persistent GEMM or attention CTA on the same SM, so on its own
+    stream it runs in the resources and kernel-boundary gaps the main stream leaves idle (in-graph: parallel branches) instead of
+    taking a slot in the serial kernel sequence (183 launches, 1.17 ms of a 43 ms step).  Tensors read on the lane are kept alive until
+    the join."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device)
+        self.keep: List[torch.Tensor] = []
+        self.dirty = False
+
+    def run(self, fn: Callable[[], None], keep: Sequence[torch.Tensor] = ()) -> None:
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(keep)
+        self.dirty = True
+
+    def join(self) -> None:
+        if self.dirty:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.dirty = False
+            self.keep.clear()
+
+
+# Off by default: a same-box A/B of the bench step (two runs each, 20 graph replays) gave 44.32 ms without and 44.40 ms with the lane --
+# the column sums do overlap, but a persistent GEMM whose CTAs find an SM still busy with them starts that SM late, and the two
+# effects cancel.  Kept behind PT_SIDE_LANE=1 for runs where the bias gradients are a larger share.
+SIDE_LANE = os.environ.get("PT_SIDE_LANE", "0") == "1"
+
+
 class PackCache:
     """bf16 GEMM-layout copies of fp32 parameters.
 
@@ -46,6 +79,7 @@ class PackCache:
     def __init__(self):
         self._d: Dict[tuple, Tuple[tuple, torch.Tensor]] = {}
         self.static: Dict[tuple, list] = {}     # key -> [versions, view, refresh()]
+        self.lane: Optional[SideLane] = None    # created on first use (lives as long as the model's cache)
         self.epoch = 0      # bumped by optimisers that update parameters through raw pointers without maintaining a static shadow
 
     def add_static(self, kind: str, params: Sequence[torch.Tensor], view: torch.Tensor, refresh: Optional[Callable[[], None]]) -> None:
@@ -104,6 +138,8 @@ class Tape:
         # inference only: step-invariant cross-attention K/V projections of the text encoding, keyed by attention module
         # (the sampler passes the same dict to each of its 100 denoiser forwards)
         self.kv_cache: Optional[Dict[int, "Var"]] = None
+        # cross-attention K/V of all layers as ONE projection of the text encoding: id(attention module) -> (Var, k_off, v_off)
+        self.kv_group: Dict[int, Tuple["Var", int, int]] = {}
 
     def record(self, fn: Callable[[], None]) -> None:
         if self.recording:
@@ -168,6 +204,19 @@ class Tape:
         """fp32 [Co, 3, Ci] tap-major accumulation buffer of a k=3 conv weight (its torch gradient is the permuted view)."""
         return self._grad_buf([p], "conv")
 
+    def side_colsum(self, x2d: torch.Tensor, out: torch.Tensor) -> None:
+        """out[c] += sum_r x2d[r, c] (a bias gradient), off the critical path when a side lane is enabled."""
+        if not SIDE_LANE or not x2d.is_cuda:
+            ops.colsum(x2d, out)
+            return
+        if self.cache.lane is None:
+            self.cache.lane = SideLane(x2d.device)
+        self.cache.lane.run(lambda: ops.colsum(x2d, out, lite=True), keep=(x2d, out))
+
+    def join_side(self) -> None:
+        if self.cache.lane is not None:
+            self.cache.lane.join()
+
     def backward(self) -> None:
         done = 0
         for fn in reversed(self.bwd):
@@ -177,6 +226,7 @@ class Tape:
                 self.on_ready(self.pgrad_order[done:])
                 done = len(self.pgrad_order)
         self.bwd = []
+        self.join_side()
         for fn in self.post:
             fn()
         self.post = []
@@ -226,7 +276,7 @@ def linear(tape: Tape, x: Var, wparams: Sequence[torch.Tensor], bias: Optional[S
             dy = ops.cast_bf16(dy)
         dy2 = dy.reshape(M, N)
         if bias is not None:
-            ops.colsum(dy2, tape.pgrad_cat(bias) if len(bias) > 1 else tape.pgrad(bias[0]))
+            tape.side_colsum(dy2, tape.pgrad_cat(bias) if len(bias) > 1 else tape.pgrad(bias[0]))
         gw = (tape.pgrad_cat(wparams) if len(wparams) > 1 else tape.pgrad(wparams[0])).view(N, K)
         _wgrad_gemm(ops.operand(dy2, False), ops.operand(x2, False), ops.segment(M), N, K, gw, K)
         if x.needs_grad:
@@ -277,7 +327,7 @@ def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: 
         dy = y.grad
         if dy is None:
             return
-        ops.colsum(dy.view(B * Lo, Co), tape.pgrad(bias))
+        tape.side_colsum(dy.view(B * Lo, Co), tape.pgrad(bias))
         if tshift is not None and tshift.dproj is not None:
             ops.batch_colsum(dy, tshift.dproj[:, tshift.offset:], tshift.dproj.stride(0))
         # weight gradient: MN-major x MN-major GEMMs accumulated (fp32 atomics, stream-K) into the tap-major [Co, 3, Ci] buffer
@@ -361,11 +411,14 @@ def layernorm(tape: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor, eps: 
 
 
 # ------------------------------------------------------------------------------------------------ attention core
-def attention_core(tape: Tape, q_src: Var, q_off: int, kv_src: Var, k_off: int, v_off: int, heads: int, C: int) -> Var:
+def attention_core(tape: Tape, q_src: Var, q_off: int, kv_src: Var, k_off: int, v_off: int, heads: int, C: int,
+                   shared_kv: bool = False) -> Var:
     """softmax(Q K^T / sqrt(d)) V with Q = q_src[..., q_off:q_off+C], K/V column slices of kv_src (no mask, no dropout:
     diffusers AttnProcessor2_0 as the reference uses it).  q_src [B, Lq, Wq], kv_src [B, Lk, Wkv].  One fused tcgen05
     kernel forward (logits stay in TMEM), three backward (delta, dQ, dK/dV) that recompute the logits from the saved
-    log-sum-exp; gradients land in place in column slices of fused-projection-shaped buffers."""
+    log-sum-exp; gradients land in place in column slices of fused-projection-shaped buffers.
+    shared_kv: kv_src holds the K/V projections of SEVERAL attention layers side by side (one grouped GEMM over the text encoding);
+    every layer owns its own columns, so its dK/dV are written straight into those columns of one shared gradient buffer."""
     qd, kvd = q_src.data, kv_src.data
     B, Lq, _ = qd.shape
     d = C // heads
@@ -382,11 +435,16 @@ def attention_core(tape: Tape, q_src: Var, q_off: int, kv_src: Var, k_off: int, 
             return
         same = q_src is kv_src
         dq_buf = torch.empty_like(qd)
-        dkv_buf = dq_buf if same else torch.empty_like(kvd)
+        if shared_kv:
+            if kv_src.grad is None:       # first of the group to run backward; every column is written by exactly one layer
+                kv_src.grad, kv_src.owned = torch.empty_like(kvd), True
+            dkv_buf = kv_src.grad
+        else:
+            dkv_buf = dq_buf if same else torch.empty_like(kvd)
         ops.attn_bwd(qv, kv_, vv, o, lse, do, dq_buf[:, :, q_off:q_off + C], dkv_buf[:, :, k_off:k_off + C],
                      dkv_buf[:, :, v_off:v_off + C], heads, d, scale)
         accum(q_src, dq_buf, owned=True)
-        if not same:
+        if not same and not shared_kv:
             accum(kv_src, dkv_buf, owned=True)
 
     tape.record(bwd)
@@ -508,10 +566,12 @@ def get_cache(module) -> PackCache:
     return c
 
 
-def run_module(module, body, inputs, kinds, out_kind="ncl"):
+def run_module(module, body, inputs, kinds, out_kind="ncl", multi=False):
     """Public-forward helper: convert reference-layout inputs to tape Vars, run `body(tape, *vars)`, convert the
     result back and bridge to autograd.  kinds: 'ncl' fp32 [B, C, L] activation, 'blc' float [B, L, C] activation,
-    'f32' small fp32 tensor kept as is (differentiable), 'raw' passed through (no gradient)."""
+    'f32' small fp32 tensor kept as is (differentiable), 'raw' passed through (no gradient).
+    multi: `body` returns a list of Vars (the down blocks return the hidden state AND the skip states); the same Var may
+    appear more than once (the reference returns the last skip state as the hidden state too) -- its gradients add up."""
     params = [p for p in module.parameters()]
     cache = get_cache(module)
     for t in inputs:
@@ -529,13 +589,16 @@ def run_module(module, body, inputs, kinds, out_kind="ncl"):
                 vs.append(Var(t.detach().float().contiguous()))
             else:
                 vs.append(t.detach())
-        yv = body(tape, *vs)
-        out = ops.nlc_to_ncl(yv.data) if out_kind == "ncl" else ops.cast_f32(yv.data)
+        res = body(tape, *vs)
+        yvs = list(res) if multi else [res]
+        outs = tuple(ops.nlc_to_ncl(v.data) if out_kind == "ncl" else ops.cast_f32(v.data) for v in yvs)
 
         def seed(gouts):
-            g = gouts[0]
-            yv.grad = ops.ncl_to_nlc(g.float().contiguous()) if out_kind == "ncl" else ops.cast_bf16(g.float().contiguous())
-            yv.owned = True
+            for v, g in zip(yvs, gouts):
+                if g is None:
+                    continue
+                gg = ops.ncl_to_nlc(g.float().contiguous()) if out_kind == "ncl" else ops.cast_bf16(g.float().contiguous())
+                accum(v, gg, owned=True)
 
         def in_grads():
             r = []
@@ -550,6 +613,6 @@ def run_module(module, body, inputs, kinds, out_kind="ncl"):
                     r.append(v.grad)
             return r
 
-        return (out,), seed, in_grads
+        return outs, seed, in_grads
 
     return TapeFunction.apply(runner, cache, len(inputs), *inputs, *params)

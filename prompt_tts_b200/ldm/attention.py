@@ -35,6 +35,11 @@ class Attention(nn.Module):
         if ctx is None:
             qkv = E.linear(tape, hn, [self.to_q.weight, self.to_k.weight, self.to_v.weight])      # fused QKV GEMM
             o = E.attention_core(tape, qkv, 0, qkv, C, 2 * C, self.heads, C)
+        elif id(self) in tape.kv_group:
+            # this layer's K / V are columns of the grouped projection computed once per forward (Unet1DConditionModel._fwd)
+            q = E.linear(tape, hn, [self.to_q.weight])
+            kv_all, k_off, v_off = tape.kv_group[id(self)]
+            o = E.attention_core(tape, q, 0, kv_all, k_off, v_off, self.heads, C, shared_kv=True)
         else:
             q = E.linear(tape, hn, [self.to_q.weight])
             kv = None if tape.kv_cache is None or tape.recording else tape.kv_cache.get(id(self))

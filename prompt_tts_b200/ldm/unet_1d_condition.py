@@ -142,6 +142,39 @@ class Unet1DConditionModel(nn.Module):
             rs += list(b.resnets)
         return rs
 
+    def _cross_attentions(self):
+        """Every cross-attention module (attn2 of each BasicTransformerBlock) in forward order."""
+        out = []
+        blocks = list(self.down_blocks) + ([self.mid_block] if self.mid_block is not None else []) + list(self.up_blocks)
+        for b in blocks:
+            for t1d in getattr(b, "attentions", None) or []:
+                for tb in t1d.transformer_blocks:
+                    if tb.attn2 is not None:
+                        out.append(tb.attn2)
+        return out
+
+    def _group_cross_kv(self, tape, enc: E.Var) -> None:
+        """All cross-attention layers project the SAME text encoding (transformer_1d.py:258-265 -> diffusers Attention.to_k / to_v): one
+        GEMM [B*Lk, 768] x [768, sum 2C] instead of 16, one data-gradient GEMM with K = sum 2C instead of 16 accumulating passes over
+        the encoder gradient, one weight-gradient launch instead of 16.  When sampling (tape.kv_cache) the projection is step-invariant
+        and computed once."""
+        atts = self._cross_attentions()
+        if not atts or len({a.to_k.weight.shape[1] for a in atts}) != 1 or os.environ.get("PT_GROUP_KV", "1") == "0":
+            return
+        cached = tape.kv_cache is not None and not tape.recording
+        kv_all = tape.kv_cache.get("all") if cached else None
+        if kv_all is None:
+            ws = []
+            for a in atts:
+                ws += [a.to_k.weight, a.to_v.weight]
+            kv_all = E.linear(tape, enc, ws)
+            if cached:
+                tape.kv_cache["all"] = kv_all
+        off = 0
+        for a in atts:
+            tape.kv_group[id(a)] = (kv_all, off, off + a.inner)
+            off += 2 * a.inner
+
     def _fwd(self, tape, sample_ncl: torch.Tensor, t_i64: torch.Tensor, enc: E.Var, want_dx: bool = False):
         """sample_ncl fp32 [B, Cin, L] -> (fp32 [B, Cout, L], seed(grad_out) closure)."""
         B, Cin, L = sample_ncl.shape
@@ -155,6 +188,7 @@ class Unet1DConditionModel(nn.Module):
         e1 = E.linear(tape, sin, [self.time_embedding.linear_1.weight], [self.time_embedding.linear_1.bias], out_f32=True)
         emb = E.linear(tape, E.silu_f32(tape, e1), [self.time_embedding.linear_2.weight], [self.time_embedding.linear_2.bias], out_f32=True)
         shifts = time_projection(tape, emb, self._all_resnets())
+        self._group_cross_kv(tape, enc)
         si = 0
 
         def take(k):

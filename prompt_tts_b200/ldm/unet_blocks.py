@@ -141,8 +141,12 @@ class DownBlock1D(_BlockBase):
         return h, outs
 
     def forward(self, hidden_states, temb=None):
-        # the public forward of a multi-output block returns plain tensors without an autograd bridge per output
-        raise NotImplementedError("DownBlock1D.forward: call through Unet1DConditionModel (multi-output blocks are tape-internal)")
+        """-> (hidden_states, output_states) as unet_blocks.py:257-281: every resnet output (and the down-sampled state) is a skip."""
+        def body(tape, h, t):
+            hh, outs = self._fwd(tape, h, self._shifts(tape, t))
+            return [hh] + list(outs)
+        res = E.run_module(self, body, [hidden_states, temb], ["ncl", "f32"], multi=True)
+        return res[0], tuple(res[1:])
 
 
 class CrossAttnDownBlock1D(_BlockBase):
@@ -180,7 +184,12 @@ class CrossAttnDownBlock1D(_BlockBase):
         return h, outs
 
     def forward(self, hidden_states, temb=None, encoder_hidden_states=None, attention_mask=None, cross_attention_kwargs=None):
-        raise NotImplementedError("CrossAttnDownBlock1D.forward: call through Unet1DConditionModel (multi-output blocks are tape-internal)")
+        """-> (hidden_states, output_states) as unet_blocks.py:359-408 (attention_mask accepted and unused, as there)."""
+        def body(tape, h, t, e):
+            hh, outs = self._fwd(tape, h, self._shifts(tape, t), e)
+            return [hh] + list(outs)
+        res = E.run_module(self, body, [hidden_states, temb, encoder_hidden_states], ["ncl", "f32", "blc"], multi=True)
+        return res[0], tuple(res[1:])
 
 
 class CrossAttnUpBlock1D(_BlockBase):

@@ -265,9 +265,9 @@ def unpack_conv_wgrad(gp, g, accumulate=True):
     call("unpack_conv_wgrad", _p(gp), _p(g), Co, Ci, k, 1 if accumulate else 0, _stream())
 
 
-def colsum(x2d, out_f32, ld=None):
+def colsum(x2d, out_f32, ld=None, lite=False):
     rows, cols = x2d.shape
-    call("colsum_bf16", _p(x2d), ld if ld is not None else x2d.stride(0), _p(out_f32), rows, cols, _stream())
+    call("colsum_bf16_lite" if lite else "colsum_bf16", _p(x2d), ld if ld is not None else x2d.stride(0), _p(out_f32), rows, cols, _stream())
 
 
 def batch_colsum(x_blc, out_f32, out_stride):
