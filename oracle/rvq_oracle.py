@@ -30,14 +30,29 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def encode(latents: np.ndarray, codebooks: np.ndarray) -> np.ndarray:
-    """latents [B, D, T] f32, codebooks [Q, K, D] f32 -> codes [B, Q, T] int64."""
+def encode(latents: np.ndarray, codebooks: np.ndarray, threads: int = 1) -> np.ndarray:
+    """latents [B, D, T] f32, codebooks [Q, K, D] f32 -> codes [B, Q, T] int64.
+    threads > 1: clips are independent, so they are dealt to host threads (ctypes releases the GIL during the C call); every frame
+    is still evaluated by one thread in the C file's fixed order, so the result does not depend on the thread count."""
     latents = np.ascontiguousarray(latents, np.float32)
     codebooks = np.ascontiguousarray(codebooks, np.float32)
     B, D, T = latents.shape
     Q, K, _ = codebooks.shape
     codes = np.empty((B, Q, T), np.int64)
-    lib().rvq_oracle_encode(_ptr(latents), _ptr(codebooks), _ptr(codes), B, D, T, Q, K)
+    fn = lib().rvq_oracle_encode
+    threads = max(1, min(int(threads), B))
+    if threads == 1:
+        fn(_ptr(latents), _ptr(codebooks), _ptr(codes), B, D, T, Q, K)
+        return codes
+    from concurrent.futures import ThreadPoolExecutor
+    bounds = [B * i // threads for i in range(threads + 1)]
+
+    def part(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        if hi > lo:
+            fn(_ptr(latents[lo:hi]), _ptr(codebooks), _ptr(codes[lo:hi]), hi - lo, D, T, Q, K)
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(part, range(threads)))
     return codes
 
 

@@ -428,6 +428,42 @@ def test_rvq_matches_golden_and_oracle_bit_exact(cuda, name):
     assert np.array_equal(dec, rvq_oracle.decode(g["codes"].astype(np.int64), cb))
 
 
+def test_rvq_full_reference_batch_bit_exact(cuda):
+    """One complete reference batch (32 clips x 900 frames, generate_code.py:29-34,94-96; Gaussian latents and codebooks):
+    every one of the 230 400 codes equals the C oracle's, and against the encodec RVQ itself (transformers' line-for-line
+    restatement, run on the host cores with its library GEMM) the only frames that may differ are fp64 near-ties, where the
+    unspecified summation order of that GEMM decides."""
+    import rvq_oracle
+    from transformers import EncodecConfig
+    from transformers.models.encodec.modeling_encodec import EncodecResidualVectorQuantizer
+    from prompt_tts_b200 import ops
+    rs = np.random.RandomState(11)
+    cb = rs.standard_normal((8, 1024, 128)).astype(np.float32)
+    lat = rs.standard_normal((32, 128, 900)).astype(np.float32)
+    lat[20:, :, 650:] = 0.0                                   # zero-padded tails of short clips
+    codes = ops.rvq_encode(torch.from_numpy(lat).to(cuda), torch.from_numpy(cb).to(cuda)).cpu().numpy()
+    want = rvq_oracle.encode(lat, cb, threads=os.cpu_count() or 1)
+    assert np.array_equal(codes, want), f"{(codes != want).sum()} of {codes.size} codes differ from the oracle"
+    q = EncodecResidualVectorQuantizer(EncodecConfig())
+    with torch.no_grad():
+        for i in range(8):
+            q.layers[i].codebook.embed.copy_(torch.from_numpy(cb[i]))
+        ref = q.encode(torch.from_numpy(lat), 6.0).permute(1, 0, 2).numpy()
+    diff = codes != ref
+    if diff.any():
+        bad_frames = diff.any(axis=1)                          # [B, T]: a flip cascades to the later stages of the same frame
+        sub = lat.transpose(0, 2, 1)[bad_frames].T[None]       # [1, 128, n_bad]
+        _, margin = rvq_oracle.encode_fp64(np.ascontiguousarray(sub), cb)
+        first = diff.transpose(0, 2, 1)[bad_frames].argmax(axis=1)            # first differing stage per bad frame
+        m_first = margin[0].T[np.arange(len(first)), first]
+        assert (m_first < 1e-4).all(), f"a clear (non-tie) decision differs from encodec: margins {m_first[:8]}"
+    assert diff.mean() < 1e-3
+    dec = ops.rvq_decode(torch.from_numpy(ref).to(cuda), torch.from_numpy(cb).to(cuda)).cpu().numpy()
+    with torch.no_grad():
+        dec_ref = q.decode(torch.from_numpy(ref).permute(1, 0, 2)).numpy()
+    assert np.array_equal(dec, dec_ref)                        # embedding sum: bit-equal to encodec's own decode
+
+
 def test_rvq_ragged_and_properties(cuda):
     """LJSpeech-like batch (32 x 900 frames, reference layout generate_code.py:29-34): bit-exact against the oracle on a
     sample, plus size-independent properties: decode(encode(x)) reduces the residual at every stage; encode of an exact

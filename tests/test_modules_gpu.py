@@ -93,7 +93,8 @@ def test_transformer_1d_forward(cuda, C):
     out = m(x, encoder_hidden_states=e)
     assert isinstance(out, Transformer1DModelOutput)
     tup = m(x.detach(), encoder_hidden_states=e.detach(), return_dict=False)
-    assert isinstance(tup, tuple) and torch.equal(tup[0], out.sample.detach())
+    # (two runs are not bit-identical: GroupNorm statistics are accumulated with fp32 atomics, whose order can move a bf16 rounding)
+    assert isinstance(tup, tuple) and rel(tup[0], out.sample.detach()) < 2e-3
     _check(m, out.sample, ref_model.transformer_1d(sd, "m", xr, er, 8), [x, e], [xr, er], sd)
     assert m.proj_out.weight.grad is None or m.proj_out.weight.grad.abs().max() == 0      # constructed, never applied (:190 vs :275-279)
 
@@ -190,4 +191,4 @@ def test_text_encoder_and_unet_forward(cuda):
         t0 = int(inp["t"][0])
         a = model.unet(inp["x0"][:1], t0, encoder_hidden_states=ref_enc[:1].detach(), return_dict=False)[0]
         b = model.unet(inp["x0"][:1], torch.tensor(t0, device="cuda"), encoder_hidden_states=ref_enc[:1].detach()).sample
-    assert torch.equal(a, b)
+    assert rel(a, b) < 2e-3

@@ -1,5 +1,5 @@
 // Microbenchmark: throughput of ex2.approx.ftz.f32 (MUFU.EX2) per SM sub-partition, and of the FFMA + EX2 + FADD + F2FP mix of the
-// attention transform.  One CTA per SM, W warps per sub-partition.   nvcc -gencode arch=compute_100a,code=sm_100a -O3
+// attention transform.  One CTA per SM, W warps per sub-partition.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared (a statically linked cudart must not ship to the GPU box)
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -1,5 +1,5 @@
 // Microbenchmark: tcgen05.ld throughput per SM (how many bytes per clock TMEM -> registers), 1..8 warps loading concurrently.
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tmem_ld_bw tmem_ld_bw.cu && ./tmem_ld_bw
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o tmem_ld_bw tmem_ld_bw.cu && ./tmem_ld_bw
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
