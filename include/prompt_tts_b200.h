@@ -225,6 +225,16 @@ int pt_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* d
  * cb_sq: caller-provided scratch [Q, K] fp32 (|e|^2 per code, filled here) -- the library owns no device memory. */
 int pt_rvq_encode_ws(const float* latents, const float* codebooks, float* cb_sq, int64_t* codes, int B, int D, int T, int Q, int K, void* stream);
 int pt_rvq_cb_sq(const float* codebooks, float* out, int Q, int K, int D, void* stream);
+/* The same codes (bit-identical, by construction) with the exhaustive fp32 search replaced by a tensor-core pre-selection: tcgen05
+ * computes a bf16 approximation of every code's score, a rigorous error bound keeps the ~2 codes per frame and stage that can still be
+ * the maximum, and only those are re-evaluated with the reference's exact fp32 arithmetic (csrc/rvq_tc.cu).  K % 128 == 0, K <= 1024.
+ * scratch: pt_rvq_encode_tc_scratch_bytes(Q, K) bytes, 256-byte aligned, caller-owned; prep != 0 (re)derives the bf16 codebooks,
+ * |e|^2 and max |e| from `codebooks` into it (needed once per codebook set). */
+size_t pt_rvq_encode_tc_scratch_bytes(int Q, int K);
+/* diagnostic: later pt_rvq_encode_tc launches dump the approximate stage-0 scores of their first 128 frames into buf[128][K]; NULL = off */
+int pt_rvq_tc_debug_scores(float* buf);
+int pt_rvq_encode_tc(const float* latents, const float* codebooks, void* scratch, int prep, int64_t* codes, int B, int D, int T, int Q, int K,
+                     void* stream);
 /* latents[b, :, t] = sum_q E[q, codes[b,q,t], :]  (q ascending, fp32) */
 int pt_rvq_decode(const int64_t* codes, const float* codebooks, float* latents, int B, int D, int T, int Q, int K, void* stream);
 /* same result (bit-equal), faster: scratch = caller-provided B*Q*T uint16 for the narrowed codes; a CTA keeps a 4-float slice of all

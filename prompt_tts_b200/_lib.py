@@ -66,6 +66,8 @@ def lib():
         _lib.pt_last_error.restype = C.c_char_p
         _lib.pt_version.restype = C.c_int
         _lib.pt_launch_count.restype = C.c_ulonglong
+        _lib.pt_rvq_encode_tc_scratch_bytes.restype = C.c_size_t
+        _lib.pt_rvq_encode_tc_scratch_bytes.argtypes = [C.c_int, C.c_int]
     return _lib
 
 
@@ -125,6 +127,8 @@ _SIGS = {
     "ddpm_step": "pppppliiffp",
     "rvq_encode_ws": "ppppiiiiip",
     "rvq_cb_sq": "ppiiip",
+    "rvq_encode_tc": "pppipiiiiip",
+    "rvq_tc_debug_scores": "p",
     "rvq_decode": "pppiiiiip",
     "rvq_decode_ws": "ppppiiiiip",
     "codes_affine": "pplp",
@@ -138,7 +142,7 @@ _SIGS = {
     "adamw_step_dev": "ppippplpp",
 }
 _CT = {"p": C.c_void_p, "i": C.c_int, "l": C.c_int64, "f": C.c_float}
-EXPORTS = ["pt_version", "pt_last_error", "pt_launch_count"] + ["pt_" + k for k in _SIGS]
+EXPORTS = ["pt_version", "pt_last_error", "pt_launch_count", "pt_rvq_encode_tc_scratch_bytes"] + ["pt_" + k for k in _SIGS]
 
 
 def _bind(l):

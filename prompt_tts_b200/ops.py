@@ -293,16 +293,57 @@ def time_sinusoid(t_i64, dim):
     return out
 
 
-def rvq_encode(latents, codebooks):
-    """latents [B, 128, T] fp32, codebooks [Q, K, 128] fp32 -> codes [B, Q, T] int64."""
+class RvqPrepared:
+    """Device scratch of the tensor-core quantiser for ONE codebook set: bf16 codebooks, |e|^2, max |e| and the fallback counter.
+    Build it once with `rvq_prepare(codebooks)` and pass it to `rvq_encode(..., prepared=...)` to skip the (cheap) per-call
+    preparation; it must be rebuilt whenever the codebook values change."""
+
+    def __init__(self, codebooks: torch.Tensor):
+        Q, K, D = codebooks.shape
+        self.shape = (Q, K, D)
+        nbytes = int(_lib.lib().pt_rvq_encode_tc_scratch_bytes(Q, K))
+        self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=codebooks.device)
+        self.off = (-self.buf.data_ptr()) % 256
+        self.ready = False
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return C.c_void_p(self.buf.data_ptr() + self.off)
+
+    def overflow_frames(self) -> int:
+        """Frame-stages that fell back to the exhaustive scan since the last preparation (diagnostic; synchronises)."""
+        Q, K, D = self.shape
+        o = self.off + Q * K * 4 + 256 + Q * K * D * 2
+        return int(self.buf[o:o + 8].view(torch.int64).item())
+
+
+def rvq_prepare(codebooks: torch.Tensor) -> RvqPrepared:
+    _need(codebooks, F32, "rvq_prepare codebooks")
+    return RvqPrepared(codebooks.contiguous())
+
+
+def rvq_encode(latents, codebooks, exhaustive: bool = False, prepared: Optional[RvqPrepared] = None):
+    """latents [B, 128, T] fp32, codebooks [Q, K, 128] fp32 -> codes [B, Q, T] int64, bit-identical to the oracle.
+    Default: tensor-core pre-selection + exact fp32 re-ranking (csrc/rvq_tc.cu); `exhaustive` (or K not a multiple of 128 / > 1024):
+    the exact fp32 search over all codes on the FMA pipe (csrc/rvq.cu).  Both produce the same codes."""
     _need(latents, F32, "rvq_encode latents"); _need(codebooks, F32, "rvq_encode codebooks")
     latents, codebooks = latents.contiguous(), codebooks.contiguous()
     B, D, T = latents.shape
     Q, K, D2 = codebooks.shape
     assert D == D2
     codes = torch.empty(B, Q, T, dtype=torch.int64, device=latents.device)
-    cb_sq = torch.empty(Q, K, dtype=F32, device=latents.device)
-    call("rvq_encode_ws", _p(latents), _p(codebooks), _p(cb_sq), _p(codes), B, D, T, Q, K, _stream())
+    if exhaustive or K % 128 != 0 or K > 1024 or D != 128:
+        cb_sq = torch.empty(Q, K, dtype=F32, device=latents.device)
+        call("rvq_encode_ws", _p(latents), _p(codebooks), _p(cb_sq), _p(codes), B, D, T, Q, K, _stream())
+        return codes
+    if prepared is None:
+        prepared = RvqPrepared(codebooks)
+    elif prepared.shape != (Q, K, D):
+        raise _lib.PtError(f"rvq_encode: `prepared` was built for codebooks {prepared.shape}, got {(Q, K, D)}")
+    prep = 0 if prepared.ready else 1
+    call("rvq_encode_tc", _p(latents), _p(codebooks), prepared.ptr, prep, _p(codes), B, D, T, Q, K, _stream())
+    prepared.ready = True
+    rvq_encode.last_prepared = prepared
     return codes
 
 

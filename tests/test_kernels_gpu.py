@@ -464,6 +464,43 @@ def test_rvq_full_reference_batch_bit_exact(cuda):
     assert np.array_equal(dec, dec_ref)                        # embedding sum: bit-equal to encodec's own decode
 
 
+def test_rvq_tensor_core_preselect_equals_exhaustive(cuda):
+    """The two quantisers (tcgen05 pre-selection + exact re-rank, csrc/rvq_tc.cu; exhaustive fp32 search, csrc/rvq.cu) must give
+    the same codes on everything: Gaussian data at several scales (the error bound scales with |r| |e|), grid-valued data with exact
+    ties, zero frames, ragged frame counts -- and degenerate codebooks where hundreds of codes fall inside the rounding window, which
+    must take the exhaustive fallback (duplicated codes: the FIRST index wins)."""
+    import rvq_oracle
+    from prompt_tts_b200 import ops
+    g = gen(31)
+    for scale_x, scale_e, B, T in [(1.0, 1.0, 5, 333), (30.0, 0.05, 2, 129), (1e-3, 4.0, 3, 64), (1.0, 1.0, 1, 1)]:
+        cb = torch.randn(8, 1024, 128, device=cuda, generator=g) * scale_e
+        lat = torch.randn(B, 128, T, device=cuda, generator=g) * scale_x
+        lat[:, :, T // 2:T // 2 + 3] = 0.0
+        a, b = ops.rvq_encode(lat, cb), ops.rvq_encode(lat, cb, exhaustive=True)
+        assert torch.equal(a, b), (scale_x, scale_e, int((a != b).sum()))
+    # fewer codebooks / smaller codebooks (K = 256), and values on a coarse grid (exact ties are common)
+    cb = (torch.randint(-8, 9, (3, 256, 128), device=cuda, generator=g).float() / 16)
+    lat = (torch.randint(-16, 17, (4, 128, 200), device=cuda, generator=g).float() / 16)
+    a, b = ops.rvq_encode(lat, cb), ops.rvq_encode(lat, cb, exhaustive=True)
+    assert torch.equal(a, b)
+    assert np.array_equal(a.cpu().numpy(), rvq_oracle.encode(lat.cpu().numpy(), cb.cpu().numpy()))
+    # degenerate: every code appears 8 times -> each maximum is an 8-way exact tie; and a codebook of 1024 near-identical codes
+    base = torch.randn(8, 128, 128, device=cuda, generator=g)
+    cb = base.repeat_interleave(8, dim=1).contiguous()
+    lat = torch.randn(2, 128, 150, device=cuda, generator=g)
+    a, b = ops.rvq_encode(lat, cb), ops.rvq_encode(lat, cb, exhaustive=True)
+    assert torch.equal(a, b) and int((a % 8).max()) == 0
+    cb = (torch.randn(1, 1, 128, device=cuda, generator=g) + 1e-4 * torch.randn(2, 1024, 128, device=cuda, generator=g)).contiguous()
+    a, b = ops.rvq_encode(lat, cb), ops.rvq_encode(lat, cb, exhaustive=True)
+    assert torch.equal(a, b)
+    assert ops.rvq_encode.last_prepared.overflow_frames() > 0, "the near-identical codebook must have exercised the exhaustive fallback"
+    # a prepared handle is reusable across calls and gives the same codes
+    cb = torch.randn(8, 1024, 128, device=cuda, generator=g)
+    prep = ops.rvq_prepare(cb)
+    for _ in range(2):
+        assert torch.equal(ops.rvq_encode(lat, cb, prepared=prep), ops.rvq_encode(lat, cb, exhaustive=True))
+
+
 def test_rvq_ragged_and_properties(cuda):
     """LJSpeech-like batch (32 x 900 frames, reference layout generate_code.py:29-34): bit-exact against the oracle on a
     sample, plus size-independent properties: decode(encode(x)) reduces the residual at every stage; encode of an exact
