@@ -379,7 +379,9 @@ def run_ours(args):
             "clocks": ck,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "gemm_kernel<BN> (persistent tcgen05 GEMM family: every conv / linear contraction, forward, data- and weight-gradient)",
-                         "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_flops / 1e12, "peak_source": peak_src + " (of measured)",
+                         "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_flops / 1e12, "gemm_launches_per_step": gemm_profile.counts[0],
+                         "how": "the step's pt_gemm calls, in order, replayed back to back from one CUDA graph and bracketed by CUDA events (3 replays)",
+                         "peak_source": peak_src + " (of measured)",
                          "traffic_note": traffic_note,
                          "attention": {"kernel": "attn_kernel<mode, DP> (fused tcgen05 softmax attention fwd / dQ / dKV)", "ms_per_step": attn_ms,
                                        "tflop_per_step": attn_flops / 1e12, "achieved": attn_flops / (attn_ms / 1e3) / 1e12 if attn_ms > 0 else 0.0,
@@ -565,50 +567,71 @@ def rvq_throughput(dev, torch, ops, hbm_gbs, rank=0, world=1, max_over_ranks=lam
 
 
 def gemm_profile(step, model, ops, torch):
-    """One eager step with every pt_gemm / pt_attn_* call bracketed by CUDA events on the launching stream:
-    (algorithmic FLOPs, summed ms) of the GEMM family and of the fused-attention family."""
-    recs, arecs = [], []
-    orig, orig_af, orig_ab = ops.gemm, ops.attn_fwd, ops.attn_bwd
+    """Duration of the two tensor-core kernel families inside one step, measured live with CUDA events.
+    One eager step is run with every pt_gemm / pt_attn_* call recorded (arguments and the tensors behind them are kept alive); the
+    recorded calls of a family are then captured, in order and with nothing between them, in one CUDA graph, and that graph is
+    replayed and bracketed by events on the launching stream -- so the figure is the kernels' own time at the step's shapes (the
+    step's operands total ~30 GB: nothing survives in L2 from one launch to its next replay), without the host-side gaps an
+    event pair around each eager launch would include.  Returns (GEMM FLOPs, GEMM ms, attention FLOPs, attention ms) per step."""
+    gemm_calls, attn_calls, keep = [], [], []
+    orig, orig_af, orig_ab, orig_operand = ops.gemm, ops.attn_fwd, ops.attn_bwd, ops.operand
 
-    def ev():
-        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def rec_operand(t, kmajor, batched=False):
+        keep.append(t)
+        return orig_operand(t, kmajor, batched)
 
-    def timed_gemm(a, b, segs, M, N, out, **kw):
+    def rec_gemm(a, b, segs, M, N, out, **kw):
         k_total = sum(s.nk * s.nrep for s in segs)
         flops = 2.0 * M * N * k_total * kw.get("nz2", 1) * kw.get("nz3", 1)
-        e0, e1 = ev()
-        e0.record()
+        keep.extend([out] + [v for v in kw.values() if torch.is_tensor(v)])
+        gemm_calls.append((flops, lambda: orig(a, b, segs, M, N, out, **kw)))
         orig(a, b, segs, M, N, out, **kw)
-        e1.record()
-        recs.append((flops, e0, e1))
 
-    def timed_af(q, k, v, o, lse, heads, d, scale):
-        e0, e1 = ev()
-        e0.record()
+    def rec_af(q, k, v, o, lse, heads, d, scale):
+        keep.extend([q, k, v, o, lse])
+        attn_calls.append((4.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * d, lambda: orig_af(q, k, v, o, lse, heads, d, scale)))
         orig_af(q, k, v, o, lse, heads, d, scale)
-        e1.record()
-        arecs.append((4.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * d, e0, e1))
 
-    def timed_ab(q, k, v, o, lse, d_o, dq, dk, dv, heads, d, scale):
-        e0, e1 = ev()
-        e0.record()
+    def rec_ab(q, k, v, o, lse, d_o, dq, dk, dv, heads, d, scale):
+        keep.extend([q, k, v, o, lse, d_o, dq, dk, dv])
+        attn_calls.append((10.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * d,
+                           lambda: orig_ab(q, k, v, o, lse, d_o, dq, dk, dv, heads, d, scale)))
         orig_ab(q, k, v, o, lse, d_o, dq, dk, dv, heads, d, scale)
-        e1.record()
-        arecs.append((10.0 * q.shape[0] * heads * q.shape[1] * k.shape[1] * d, e0, e1))
 
-    ops.gemm, ops.attn_fwd, ops.attn_bwd = timed_gemm, timed_af, timed_ab
+    ops.gemm, ops.attn_fwd, ops.attn_bwd, ops.operand = rec_gemm, rec_af, rec_ab, rec_operand
     try:
-        for p in model.parameters():
-            p.grad = None
         step()
         torch.cuda.synchronize()
     finally:
-        ops.gemm, ops.attn_fwd, ops.attn_bwd = orig, orig_af, orig_ab
-    fl = sum(r[0] for r in recs)
-    ms = sum(r[1].elapsed_time(r[2]) for r in recs)
-    afl = sum(r[0] for r in arecs)
-    ams = sum(r[1].elapsed_time(r[2]) for r in arecs)
-    return fl, ms, afl, ams
+        ops.gemm, ops.attn_fwd, ops.attn_bwd, ops.operand = orig, orig_af, orig_ab, orig_operand
+
+    def family_ms(calls, reps=3):
+        if not calls:
+            return 0.0
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for _, fn in calls:
+                    fn()
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    gms, ams = family_ms(gemm_calls), family_ms(attn_calls)
+    fl, afl = sum(c[0] for c in gemm_calls), sum(c[0] for c in attn_calls)
+    n_gemm, n_attn = len(gemm_calls), len(attn_calls)
+    del gemm_calls, attn_calls, keep
+    gemm_profile.counts = (n_gemm, n_attn)
+    return fl, gms, afl, ams
 
 
 _REAL_STDOUT = None
