@@ -47,6 +47,7 @@ struct alignas(64) KParams {
   int a_batched[2], b_batched[2];
   int M, N, nz2, nz3;
   int mt, nt, tiles, work, streamk;   // mt counts groups of MC row tiles when the kernel runs as clusters of MC CTAs
+  int gm;                             // raster: row-tile groups of gm walk all column tiles before the next group starts
   int total_iters;
   void* out;
   int out_dtype;
@@ -191,12 +192,23 @@ __global__ void __launch_bounds__(Cfg<BN, PAIR>::THREADS, Cfg<BN, PAIR>::CTAS_PE
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(sgen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
-  // tile index -> (m0, n0, z2, z3); m fastest so that concurrently running CTAs share one B (weight) tile through L2
+  // tile index -> (m0, n0, z2, z3).  Within one (z2, z3) the tiles are walked in groups of `gm` row tiles: m fastest inside the
+  // group (concurrently running CTAs share one B = weight tile through L2), then the next column tile of the SAME rows, and only
+  // then the next group.  One wave of CTAs therefore covers (gm rows) x (all columns): every A row panel is fetched from DRAM once
+  // and reused from L2 by the CTAs of its columns.  With m fastest over ALL rows (the first version) an A operand larger than L2
+  // (24064 x 2560, 6016 x 10240: 123 MB) came from DRAM once per column tile: ncu on 6016 x 1280 x 10240 read 276 MB for 165 MB
+  // of operands.
   auto decode = [&](int tile, int& m0, int& n0, int& z2, int& z3) {
-    const int mt = tile % p.mt;
-    int r = tile / p.mt;
-    const int nt = r % p.nt;
-    r /= p.nt;
+    const int per_z = p.mt * p.nt;
+    int r = tile / per_z;
+    const int t = tile - r * per_z;
+    const int span = p.gm * p.nt;                 // tiles of one full group
+    const int grp = t / span;
+    const int first = grp * p.gm;
+    const int gsz = min(p.gm, p.mt - first);      // the last group may be shorter
+    const int q = t - grp * span;
+    const int mt = first + q % gsz;
+    const int nt = q / gsz;
     m0 = (mt * MC + crank) * BM;
     n0 = nt * BN;
     z2 = r % p.nz2;
@@ -840,6 +852,15 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   kp.tiles = (int)tiles;
   kp.work = (int)(tiles * total);
   kp.streamk = streamk ? 1 : 0;
+  {
+    // rows per raster group: about one wave of resident CTAs (clusters) spread over all column tiles
+    static const bool no_group = getenv("PT_GEMM_NO_GROUP") != nullptr;
+    const long long resident = (long long)sms * (bn <= 128 ? 2 : 1) / mc;
+    long long gm = (resident + nt / 2) / nt;
+    if (gm < 1) gm = 1;
+    if (gm > mtg || no_group || streamk) gm = mtg;
+    kp.gm = (int)gm;
+  }
   kp.out = g->out;
   kp.out_dtype = g->out_dtype;
   kp.osm = g->out_stride_m;
