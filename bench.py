@@ -297,6 +297,7 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     ck = clocks.stop() if rank == 0 else None
     loss_val = float(loss_buf.item())
+    n_buckets = grad_sync.n_buckets_last
 
     # compute-only step at N > 1 (same box, same minute): the step with the gradient exchange switched off -> exposed communication
     nocomm_ms = None
@@ -397,7 +398,7 @@ def run_ours(args):
             line["exposed_comm_ms"] = ms_step - nocomm_ms
             line["compute_only_ms_per_step"] = nocomm_ms
             line["comm"] = {"dtype": os.environ.get("PT_COMM_DTYPE", "fp32"), "bucket_mb": float(os.environ.get("PT_BUCKET_MB", "128")),
-                            "buckets_per_step": grad_sync.n_buckets_last, "bytes_per_step": grad_sync.total * (4 if comm_dtype == torch.float32 else 2),
+                            "buckets_per_step": n_buckets, "bytes_per_step": grad_sync.total * (4 if comm_dtype == torch.float32 else 2),
                             "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
     # RVQ and sampling shard by clip / utterance with no collective -- every rank does its share, the line reports
     # units of all ranks / the slowest rank's device time.
