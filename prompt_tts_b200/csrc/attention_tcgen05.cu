@@ -17,7 +17,7 @@
 // reference maximum only moves when a row's maximum grows by more than 2^8 (then that group's accumulator is rescaled in TMEM,
 // which is rare), and the two groups are merged exactly in the epilogue.
 //
-// Warp roles (352 threads): warp 0 TMA producer, warp 1 stage-1 MMA issuer, warp 10 stage-2 MMA issuer, warps 2-5 and 6-9 two
+// Warp roles (384 threads): warp 0 TMA producer, warps 1 and 11 stage-1 MMA issuers (one per group), warp 10 stage-2 MMA issuer, warps 2-5 and 6-9 two
 // transform groups that ping-pong over the streamed tiles (group g owns TMEM buffer X[g]),
 // so the tensor core computes the logits of tile j+1 while the CUDA cores exponentiate tile j.
 // Every streamed tile is used twice from the same shared-memory bytes: K-major as the B operand of stage 1 and
@@ -46,7 +46,27 @@ struct alignas(64) AParams {
   long long o_rs, o_bs;
   float* lse;          // FWD: written; DQ/DKV: read.  [B, H, Lq]
   const float* delta;  // DQ/DKV.                      [B, H, Lq]
+#ifdef PT_ATTN_TRACE
+  unsigned long long* trace;   // development builds only (tools/attn_trace.py): [12 warps][1024 events][id, clock] of CTA 0
+#endif
 };
+
+#ifdef PT_ATTN_TRACE
+unsigned long long* g_attn_trace = nullptr;
+int g_attn_trace_mode = -1;   // trace only kernels of this MODE (-1: all)
+#define TR(id)                                                                   \
+  do {                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_n < 1024) {     \
+      p.trace[(warp * 1024 + tr_n) * 2] = (unsigned long long)(id);              \
+      p.trace[(warp * 1024 + tr_n) * 2 + 1] = (unsigned long long)clock64();     \
+      ++tr_n;                                                                    \
+    }                                                                            \
+  } while (0)
+#define PT_ATTN_SET_TRACE(ap) (ap).trace = g_attn_trace
+#else
+#define TR(id)
+#define PT_ATTN_SET_TRACE(ap)
+#endif
 
 template <int MODE, int DP>
 struct ACfg {
@@ -74,7 +94,14 @@ struct ACfg {
   static constexpr int XW = 128;                             // TMEM columns per X buffer (two 64-column products)
   static constexpr int X_COLS = MODE == MODE_FWD ? 2 * XSLOTS * BN : XBUF * XW;
   static constexpr int ACC_STRIDE = DP;
-  static constexpr int TMEM_USED = X_COLS + NACC_T * ACC_STRIDE;
+  // Backward: the transformed tiles (dS; P^T and dS^T) get their OWN TMEM columns when there is room (32 columns per 64 x bf16), so
+  // the logit buffer is free as soon as the transform has READ it and stage 1 refills it while the transform still computes.  Written
+  // over the logits (the first version) the buffer came back only after stage 2 had consumed them: transform -> stage 2 -> stage 1 ->
+  // transform is ~1000 clocks (per-warp event trace, tools/attn_trace.py) during which the group had nothing to do.
+  static constexpr int T_PER_G = MODE == MODE_FWD ? 0 : NACC * (BN / 2);
+  static constexpr bool SEP_T = MODE != MODE_FWD && (XBUF * XW + XBUF * T_PER_G + NACC_T * ACC_STRIDE <= 512);
+  static constexpr int T_COLS = SEP_T ? XBUF * T_PER_G : 0;
+  static constexpr int TMEM_USED = X_COLS + T_COLS + NACC_T * ACC_STRIDE;
   static constexpr int TMEM_COLS = TMEM_USED <= 64 ? 64 : (TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512));
   static_assert(NSTAGE >= 1, "smem budget");
   static_assert(TMEM_USED <= 512, "TMEM budget");
@@ -120,7 +147,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t* v, int c, int ncol, fl
 }
 
 template <int MODE, int DP>
-__global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AParams p) {
+__global__ void __launch_bounds__(384, 1) attn_kernel(const __grid_constant__ AParams p) {
   using C = ACfg<MODE, DP>;
   constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE, XSLOTS = C::XSLOTS;
   extern __shared__ uint8_t smem_raw[];
@@ -149,6 +176,9 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   float* sred = sstat + (MODE == MODE_DKV ? 2 * C::STAT_COLS : 0);      // [2][BM]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef PT_ATTN_TRACE
+  int tr_n = 0;
+#endif
   const int n_tiles = (p.Ls + BN - 1) / BN;
   const int ks1 = (p.D + 15) >> 4;            // stage-1 k-steps (head dim, zero padded to a multiple of 16)
   const int nd = ks1 << 4;                    // stage-2 N
@@ -166,7 +196,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     for (int i = 0; i < NX; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmR[i])) : "memory");
     for (int i = 0; i < 2; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmS[i])) : "memory");
     mbar_init(r_full, 1);
-    mbar_init(r_empty, 1);
+    mbar_init(r_empty, XBUF == 2 ? 2 : 1);      // one arrival per stage-1 issuer
     for (int s = 0; s < 8; ++s) {
       mbar_init(s_full(s), 1);
       mbar_init(s_empty(s), 1);
@@ -194,7 +224,9 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
   // X buffers: FWD gives each group two 64-column slots (stage 1 runs a whole tile ahead of the group); the backward
   // modes need X1 | X2 per tile and have TMEM for one 128-column buffer per group only
   auto xcol = [&](int g, int slot_or_x) { return (uint32_t)(MODE == MODE_FWD ? (g * XSLOTS + slot_or_x) * BN : g * C::XW + slot_or_x * BN); };
-  auto acccol = [&](int a) { return (uint32_t)(C::X_COLS + a * C::ACC_STRIDE); };
+  auto acccol = [&](int a) { return (uint32_t)(C::X_COLS + C::T_COLS + a * C::ACC_STRIDE); };
+  // backward: where transformed tile `a` of group g goes (its own columns, or over logit product `a`)
+  auto tcol = [&](int g, int a) { return C::SEP_T ? (uint32_t)(C::X_COLS + g * C::T_PER_G + a * (BN / 2)) : xcol(g, a); };
   auto gsel = [&](int j) { return XBUF == 2 ? (j & 1) : 0; };
   // tiles of one sweep handled by group g
   const int per_g0 = XBUF == 2 ? (n_tiles + 1) >> 1 : n_tiles, per_g1 = XBUF == 2 ? n_tiles >> 1 : 0;
@@ -216,7 +248,9 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
           for (int kb = 0; kb < KB; ++kb) tma_load_4d(sR + x * C::R_BYTES + kb * (BM * 128), &p.tmR[x], r_full, kb * 64, r0, h, b);
       }
       auto load_tile = [&](const CUtensorMap* t0, const CUtensorMap* t1, int row0, int row1) {
+        TR(40);
         mbar_wait(s_empty(s), ph);
+        TR(41);
         if (leader) {
           mbar_expect_tx(s_full(s), 2 * C::S_BYTES);
           const uint32_t dst = sS + s * C::STAGE_BYTES;
@@ -229,65 +263,52 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
       };
       for (int j = 0; j < n_tiles; ++j) load_tile(&p.tmS[0], &p.tmS[1], j * BN, j * BN);
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ stage-1 MMA issuer (warp-uniform control flow, one elected lane issues)
-    // Runs ahead of the transform groups as far as the ring and the X buffers allow; never waits on stage 2.
-    const bool leader = elect_one();
-    const uint32_t idesc1 = idesc_f16(0, 0, BN, BM);
-    // UMMA descriptors are linear in the shared-memory address: precompute the bases, add (bytes >> 4) per use
-    const uint64_t dR = umma_desc(sR, 0, 1024);            // resident tiles, K-major
-    const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view
-    int s1 = 0, ph1 = 0;   // ring position / parity of the next tile
-    int kb0 = 0, kb1 = 0;  // X fills done by earlier work items, per group
-    // An X slot is released by the stage-2 commit (P / dS were written over the logits and have been consumed); the x_empty path
-    // (release by the transform threads) is kept for tiles whose logits are only read.  Per slot i = g*2+slot: what the last fill was
-    // (2 bits: 0 none, 1 read-only, 2 main) and the parity of the next phase of each of its two barriers.
-    uint32_t last_kind = 0, par_x = 0, par_p = 0;
-    auto wait_slot_free = [&](int g, int slot, uint32_t kind) {
-      const int i = g * 2 + slot;
-      const uint32_t prev = (last_kind >> (2 * i)) & 3u;
-      if (prev == 1u) {
-        mbar_wait(x_empty(g, slot), (par_x >> i) & 1u);
-        par_x ^= 1u << i;
-      } else if (prev == 2u) {
-        mbar_wait(p_empty(g, slot), (par_p >> i) & 1u);
-        par_p ^= 1u << i;
-      }
-      last_kind = (last_kind & ~(3u << (2 * i))) | (kind << (2 * i));
-    };
-    int wi = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
-      mbar_wait(r_full, wi & 1);
-      if (MODE == MODE_FWD) {
-        // tile j (64 streamed rows) goes to group j & 1; that group's k-th tile overall uses X slot k % XSLOTS
-        for (int j = 0; j < n_tiles; ++j) {
-          const int g = j & 1;
-          const int k = (g ? kb1 : kb0) + (j >> 1);
-          const int slot = XSLOTS == 2 ? (k & 1) : 0;
-          mbar_wait(s_full(s1), ph1);
-          wait_slot_free(g, slot, 2u);
-          fence_after();
-          if (leader) {
-            const uint64_t b0 = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
-            const uint32_t dcol = tmem + xcol(g, slot);
-#pragma unroll
-            for (int kk = 0; kk < DP / 16; ++kk)
-              if (kk < ks1)
-                umma_f16(dcol, dR + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2),
-                         b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2), idesc1, kk > 0 ? 1u : 0u);
-            umma_commit(x_full(g, slot));
-            if (j == n_tiles - 1) umma_commit(r_empty);
-          }
-          __syncwarp();
-          if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
+  } else if (warp == 1 || warp == 11) {
+    // ------------------------------------------------------------------ stage-1 MMA issuers, one per transform group (warp-uniform
+    // control flow, one elected lane issues).  Each runs ahead of its group as far as the ring and the X buffers allow and never
+    // waits on stage 2.  One issuer for both groups (the first version) was the serial bottleneck of all three kernels: per tile it
+    // waits for the ring stage, waits for the X buffer, converts ~25 operands to uniform registers and issues up to 8 MMAs + commits --
+    // 1000-1400 clocks of dependent scalar work per tile (per-warp event trace, tools/attn_trace.py), i.e. the whole tile time.
+    const int ig = warp == 1 ? 0 : 1;
+    if (XBUF == 2 || ig == 0) {
+      const bool leader = elect_one();
+      const uint32_t idesc1 = idesc_f16(0, 0, BN, BM);
+      // UMMA descriptors are linear in the shared-memory address: precompute the bases, add (bytes >> 4) per use
+      const uint64_t dR = umma_desc(sR, 0, 1024);            // resident tiles, K-major
+      const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view
+      const int jstep1 = XBUF == 2 ? 2 : 1;
+      int tbase = 0;         // streamed tiles of earlier work items (ring position of tile j = (tbase + j) % NSTAGE)
+      int kb = 0;            // X fills of this group by earlier work items
+      // FWD: an X slot is released by the stage-2 commit (P was written over the logits and has been consumed).  Backward with separate
+      // T columns: by the transform threads once they have read the logits (x_empty).  Per slot: what the last fill was (2 bits: 0 none,
+      // 1 released by x_empty, 2 by p_empty) and the parity of the next phase of each of its two barriers.
+      uint32_t last_kind = 0, par_x = 0, par_p = 0;
+      auto wait_slot_free = [&](int slot, uint32_t kind) {
+        const uint32_t prev = (last_kind >> (2 * slot)) & 3u;
+        if (prev == 1u) {
+          mbar_wait(x_empty(ig, slot), (par_x >> slot) & 1u);
+          par_x ^= 1u << slot;
+        } else if (prev == 2u) {
+          mbar_wait(p_empty(ig, slot), (par_p >> slot) & 1u);
+          par_p ^= 1u << slot;
         }
-        kb0 += per_g0;
-        kb1 += per_g1;
-      } else {
-        for (int j = 0; j < n_tiles; ++j) {
-          const int g = gsel(j);
+        last_kind = (last_kind & ~(3u << (2 * slot))) | (kind << (2 * slot));
+      };
+      int wi = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
+        mbar_wait(r_full, wi & 1);
+        for (int j = XBUF == 2 ? ig : 0; j < n_tiles; j += jstep1) {
+          const int t = tbase + j;
+          const int s1 = t % NSTAGE;
+          const uint32_t ph1 = (uint32_t)(t / NSTAGE) & 1u;
+          // FWD: the group's k-th tile overall uses X slot k % XSLOTS; backward: one buffer (X1 | X2)
+          const int k = kb + (XBUF == 2 ? (j >> 1) : j);
+          const int slot = (MODE == MODE_FWD && XSLOTS == 2) ? (k & 1) : 0;
+          TR(20);
           mbar_wait(s_full(s1), ph1);
-          wait_slot_free(g, 0, 2u);
+          TR(21);
+          wait_slot_free(slot, (MODE != MODE_FWD && C::SEP_T) ? 1u : 2u);
+          TR(22);
           fence_after();
           if (leader) {
             const uint64_t bS = dS + (uint64_t)(s1 * (C::STAGE_BYTES >> 4));
@@ -295,21 +316,24 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
             for (int x = 0; x < NX; ++x) {
               const uint64_t a0 = dR + (uint64_t)(x * (C::R_BYTES >> 4));
               const uint64_t b0 = bS + (uint64_t)(x * (C::S_BYTES >> 4));
-              const uint32_t dcol = tmem + xcol(g, x);
+              const uint32_t dcol = tmem + xcol(ig, MODE == MODE_FWD ? slot : x);
 #pragma unroll
               for (int kk = 0; kk < DP / 16; ++kk)
                 if (kk < ks1)
                   umma_f16(dcol, a0 + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2),
                            b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2), idesc1, kk > 0 ? 1u : 0u);
             }
-            umma_commit(x_full(g, 0));
-            if (j == n_tiles - 1) umma_commit(r_empty);
+            umma_commit(x_full(ig, slot));
           }
           __syncwarp();
-          if (++s1 == NSTAGE) s1 = 0, ph1 ^= 1;
+          TR(23);
         }
-        kb0 += per_g0;
-        kb1 += per_g1;
+        // this issuer's stage-1 MMAs of the work item have read the resident tiles (one arrival per issuer; an issuer without tiles
+        // in this item arrives at once)
+        if (leader) umma_commit(r_empty);
+        __syncwarp();
+        tbase += n_tiles;
+        kb += ig == 0 ? per_g0 : per_g1;
       }
     }
   } else if (warp == 10) {
@@ -322,13 +346,17 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     int tu0 = 0, tu1 = 0;   // t_full phases consumed so far, per group
     int wi = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
+      TR(28);
       mbar_wait(acc_empty, (wi & 1) ^ 1);                    // the epilogue of the previous work item has drained the accumulators
+      TR(29);
       fence_after();
       for (int j = 0; j < n_tiles; ++j) {
         const int g = gsel(j);
         const int use = (g ? tu1 : tu0) + (XBUF == 2 ? (j >> 1) : j);      // fills of this group's X so far (== kf for FWD)
         const int slot = (MODE == MODE_FWD && XSLOTS == 2) ? (use & 1) : 0;
+        TR(30);
         mbar_wait(t_full(g, slot), ((MODE == MODE_FWD && XSLOTS == 2) ? (use >> 1) : use) & 1);
+        TR(31);
         fence_after();
         if (leader) {
           const uint64_t bS = dSmn + (uint64_t)(s2 * (C::STAGE_BYTES >> 4));
@@ -337,7 +365,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
             // B operand: FWD -> V (S2); DQ -> K (S1); DKV: dV <- dO (S2), dK <- Q (S1)
             const int cs = MODE == MODE_FWD ? 1 : (MODE == MODE_DQ ? 0 : (a == 0 ? 1 : 0));
             // A operand in TMEM: FWD P in its X slot; DQ dS over X1; DKV P^T over X1 (-> dV), dS^T over X2 (-> dK)
-            const uint32_t acol = tmem + xcol(g, MODE == MODE_FWD ? slot : a);
+            const uint32_t acol = tmem + (MODE == MODE_FWD ? xcol(g, slot) : tcol(g, a));
             const uint64_t b0 = bS + (uint64_t)(cs * (C::S_BYTES >> 4));
             const uint32_t dcol = tmem + acccol(MODE == MODE_FWD ? g : a);     // FWD: each group accumulates into its own O
             const bool first = MODE == MODE_FWD ? j < 2 : j == 0;
@@ -350,6 +378,7 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
           if (j == n_tiles - 1) umma_commit(acc_full);
         }
         __syncwarp();
+        TR(33);
         if (++s2 == NSTAGE) s2 = 0;
       }
       tu0 += per_g0;
@@ -364,6 +393,18 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
     const bool active = XBUF == 2 || g == 0;      // with one X buffer only group 0 transforms (group 1 helps in the epilogue)
     const int jstep = XBUF == 2 ? 2 : 1;
     const float c2 = p.scale * 1.4426950408889634f;
+    // FWD, exponent turn-taking.  Warp q of group 0 and warp q of group 1 share a scheduler and its MUFU unit (16 ex2/clk/SM).  Left
+    // alone the two drift into the SAME phase: both exponentiate at half rate (~1100 clocks), then both sit in the latency-bound
+    // part (row maximum, TMEM round trips, barriers) with the MUFU idle (per-warp event trace: MUFU 49 % busy).  A token per warp
+    // pair forces the exponent phases to alternate, so one warp's latencies hide under the other's exponentials.  Two named
+    // barriers per pair: the owner waits with bar.sync (64 = its 32 threads + the partner's 32 arrivals), the partner hands the turn
+    // over with bar.arrive after its own phase.  Turns follow the tile order (tile j belongs to group j & 1); with an odd number of
+    // tiles group 1 passes once without work so that the next work item starts with group 0 again.
+    constexpr bool TURNS = MODE == MODE_FWD && XBUF == 2;
+    const int bar_mine = 3 + 2 * q + g, bar_other = 3 + 2 * q + (g ^ 1);
+    auto turn_wait = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory"); };
+    auto turn_pass = [&]() { asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory"); };
+    if (TURNS && g == 1) turn_pass();      // group 0 moves first
     int kx = 0;           // running X use count of this group (across work items)
     uint32_t v1[32], v2[32];
     int wi = 0;
@@ -380,16 +421,21 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
         int kw = 0;                                      // tiles of this group in this work item so far
         for (int j = g; j < n_tiles; j += 2, ++kx, ++kw) {
           const int slot = XSLOTS == 2 ? (kx & 1) : 0;
+          TR(0);
           mbar_wait(x_full(g, slot), (XSLOTS == 2 ? (kx >> 1) : kx) & 1);
+          TR(1);
           fence_after();
           tmem_ld32(tl + xcol(g, slot), v1);
           tmem_ld32(tl + xcol(g, slot) + 32, v2);
           tmem_wait_ld();
+          TR(2);
           const int ncol = min(BN, p.Ls - j * BN);
           float mt = -INFINITY;
           if (ncol == BN) {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four independent chains (a single one is 32 dependent FMNMX3)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mt = fmaxf(mt, fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(v1[i]), __uint_as_float(v2[i])));
+            mt = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -421,8 +467,10 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
               tmem_wait_st();
             }
           }
+          TR(3);
           const float mc = m * c2;
           const uint32_t tdst = tl + xcol(g, slot);      // P overwrites the logits of this slot (32 of its 64 columns)
+          if (TURNS) turn_wait();
           if (ncol == BN) {
             fwd_chunk<false>(v1, 0, ncol, c2, mc, l, tdst);
             fwd_chunk<false>(v2, 1, ncol, c2, mc, l, tdst);
@@ -430,10 +478,19 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
             fwd_chunk<true>(v1, 0, ncol, c2, mc, l, tdst);
             fwd_chunk<true>(v2, 1, ncol, c2, mc, l, tdst);
           }
+          if (TURNS) turn_pass();
+          TR(4);
           tmem_wait_st();
+          TR(5);
           fence_before();
           mbar_arrive(t_full(g, slot));
+          TR(6);
         }
+        if (TURNS && g == 1 && (n_tiles & 1)) {      // odd tile count: the last turn was group 0's and so is the next one
+          turn_wait();
+          turn_pass();
+        }
+        TR(10);
         // ---- merge the two groups: M = max(m_0, m_1), w_g = exp2((m_g - M) c), L = sum w_g l_g, O = sum w_g O_g / L
         sred[(g * BM + row) * 2] = m;
         sred[(g * BM + row) * 2 + 1] = l;
@@ -442,14 +499,18 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
         const float mm = fmaxf(m0, m1);
         const float w0 = ex2f((m0 - mm) * c2), w1 = n_tiles > 1 ? ex2f((m1 - mm) * c2) : 0.f;    // a group without tiles has m = -inf, l = 0
         const float lsum = w0 * l0 + w1 * l1;
+        TR(11);
         mbar_wait(acc_full, wi & 1);
+        TR(12);
         fence_after();
         const float f0 = w0 / lsum, f1 = w1 / lsum;
         bf16* orow = p.out0 + (long long)b * p.o_bs + (long long)r * p.o_rs + (long long)h * p.D;
+        TR(15);
         for (int cc = g; cc * 16 < p.D; cc += 2) {
           tmem_ld16(tl + acccol(0) + cc * 16, v1);
           if (n_tiles > 1) tmem_ld16(tl + acccol(1) + cc * 16, v2);
           tmem_wait_ld();
+          TR(16);
           if (r < p.Lr) {
             float o[16];
 #pragma unroll
@@ -469,11 +530,15 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
                 *reinterpret_cast<uint4*>(orow + cc * 16 + u * 8) = wv;
               }
           }
+          TR(17);
         }
         fence_before();
         mbar_arrive(acc_empty);
+        TR(18);
         if (g == 0 && r < p.Lr) p.lse[((long long)b * p.H + h) * p.Lr + r] = mm * p.scale + __logf(lsum);
+        TR(13);
         asm volatile("bar.sync 2, 256;" ::: "memory");   // sred is rewritten by the next work item
+        TR(14);
       } else {
         // ---- backward modes
         float lse2 = INFINITY, dl = 0.f;   // DQ: this thread's row statistics
@@ -501,13 +566,19 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
           for (int j = g; j < n_tiles; j += jstep, ++kx) {
             const float4* cst = reinterpret_cast<const float4*>(sstat + j * BN);
             const float4* cdl = reinterpret_cast<const float4*>(sstat + C::STAT_COLS + j * BN);
+            TR(0);
             mbar_wait(x_full(g, 0), kx & 1);
+            TR(1);
             fence_after();
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
               tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
               tmem_ld32(tl + xcol(g, 1) + c * 32, v2);
               tmem_wait_ld();
+              if (C::SEP_T && c == BN / 32 - 1) {       // the logits of this tile are in registers: stage 1 may refill the buffer
+                fence_before();
+                mbar_arrive(x_empty(g, 0));
+              }
               uint32_t pp[16], dd[16];
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
@@ -529,20 +600,29 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
                 dd[i >> 1] = pack2(de[0], de[1]);
                 dd[(i >> 1) + 1] = pack2(de[2], de[3]);
               }
-              // in place over the logits already consumed: DQ: dS over X1; DKV: P^T over X1, dS^T over X2 (16 columns per 32 logits)
+              if (C::SEP_T && c == 0 && kx > 0) {       // stage 2 of this group's previous tile has consumed the T columns
+                mbar_wait(p_empty(g, 0), (kx - 1) & 1);
+                fence_after();
+              }
+              // DQ: dS; DKV: P^T and dS^T (16 columns per 32 logits) -- in their own columns, or in place over the logits already consumed
               if (MODE == MODE_DKV) {
-                tmem_st16(tl + xcol(g, 0) + c * 16, pp);
-                tmem_st16(tl + xcol(g, 1) + c * 16, dd);
+                tmem_st16(tl + tcol(g, 0) + c * 16, pp);
+                tmem_st16(tl + tcol(g, 1) + c * 16, dd);
               } else {
-                tmem_st16(tl + xcol(g, 0) + c * 16, dd);
+                tmem_st16(tl + tcol(g, 0) + c * 16, dd);
               }
             }
+            TR(4);
             tmem_wait_st();
+            TR(5);
             fence_before();
             mbar_arrive(t_full(g, 0));
+            TR(6);
           }
         // ---- epilogue: accumulators -> bf16 rows
+        TR(11);
         mbar_wait(acc_full, wi & 1);
+        TR(12);
         fence_after();
 #pragma unroll
         for (int a = 0; a < NACC; ++a) {
@@ -569,8 +649,10 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
         }
         fence_before();
         mbar_arrive(acc_empty);
+        TR(13);
       }
     }
+    if (TURNS && g == 0) turn_wait();      // consume group 1's last hand-over: the named barriers are left clean
   }
 
   fence_before();
@@ -642,7 +724,13 @@ int launch_attn(const AParams& ap, dim3 grid, cudaStream_t st) {
   PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(attn_kernel<MODE, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<MODE, DP>::SMEM_BYTES));
   const long long work = (long long)grid.x * grid.y * grid.z;   // (row blocks, heads, batch) -> one persistent CTA per SM
   const int sms = pt_num_sms();
-  attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 352, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
+#ifdef PT_ATTN_TRACE
+  AParams apt = ap;
+  if (g_attn_trace_mode >= 0 && g_attn_trace_mode != MODE) apt.trace = nullptr;
+  attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 384, ACfg<MODE, DP>::SMEM_BYTES, st>>>(apt);
+#else
+  attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 384, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
+#endif
   PT_LAUNCH_CHECK();
   return PT_OK;
 }
@@ -670,6 +758,7 @@ extern "C" int pt_attn_fwd(const pt_attn_t* a, void* stream) {
   PT_REQUIRE(a->o != nullptr && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0 && a->o_rs % 8 == 0 && a->o_bs % 8 == 0, "pt_attn_fwd: output alignment");
   AParams ap;
   memset(&ap, 0, sizeof(ap));
+    PT_ATTN_SET_TRACE(ap);
   if (int r = encode_heads(&ap.tmR[0], a->q, a->d, a->Lq, a->H, a->B, a->q_rs, a->q_bs, BM, "q")) return r;
   if (int r = encode_heads(&ap.tmS[0], a->k, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BN, "k")) return r;
   if (int r = encode_heads(&ap.tmS[1], a->v, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BN, "v")) return r;
@@ -707,6 +796,7 @@ extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
   {  // dQ: resident Q, dO ; streamed K, V
     AParams ap;
     memset(&ap, 0, sizeof(ap));
+    PT_ATTN_SET_TRACE(ap);
     if (int r = encode_heads(&ap.tmR[0], a->q, a->d, a->Lq, a->H, a->B, a->q_rs, a->q_bs, BM, "q")) return r;
     if (int r = encode_heads(&ap.tmR[1], a->d_o, a->d, a->Lq, a->H, a->B, a->do_rs, a->do_bs, BM, "do")) return r;
     if (int r = encode_heads(&ap.tmS[0], a->k, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BN, "k")) return r;
@@ -728,6 +818,7 @@ extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
   {  // dK, dV: resident K, V ; streamed Q, dO
     AParams ap;
     memset(&ap, 0, sizeof(ap));
+    PT_ATTN_SET_TRACE(ap);
     if (int r = encode_heads(&ap.tmR[0], a->k, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BM, "k")) return r;
     if (int r = encode_heads(&ap.tmR[1], a->v, a->d, a->Lk, a->H, a->B, a->kv_rs, a->kv_bs, BM, "v")) return r;
     if (int r = encode_heads(&ap.tmS[0], a->q, a->d, a->Lq, a->H, a->B, a->q_rs, a->q_bs, BN, "q")) return r;
@@ -749,3 +840,12 @@ extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
   }
   return PT_OK;
 }
+
+#ifdef PT_ATTN_TRACE
+// development builds only: per-warp event log of CTA 0 (see TR above); buf = [12][1024][2] uint64, zero-filled by the caller
+extern "C" int pt_attn_set_trace(void* buf, int mode) {
+  g_attn_trace_mode = mode;
+  g_attn_trace = reinterpret_cast<unsigned long long*>(buf);
+  return PT_OK;
+}
+#endif
