@@ -12,7 +12,7 @@ pids=""
 for f in $SRC/*.cu; do
   o=build/$(basename ${f%.cu}).o
   objs="$objs $o"
-  if [ ! -f $o ] || [ $f -nt $o ] || [ $SRC/common.cuh -nt $o ] || [ $SRC/tc_common.cuh -nt $o ] || [ include/prompt_tts_b200.h -nt $o ]; then
+  if [ ! -f $o ] || [ $f -nt $o ] || [ $SRC/common.cuh -nt $o ] || [ $SRC/tc_common.cuh -nt $o ] || [ $SRC/gemm_tile_table.inc -nt $o ] || [ include/prompt_tts_b200.h -nt $o ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f -o $o &
     pids="$pids $!"
   fi

@@ -17,7 +17,7 @@
 // reference maximum only moves when a row's maximum grows by more than 2^8 (then that group's accumulator is rescaled in TMEM,
 // which is rare), and the two groups are merged exactly in the epilogue.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warps 1 and 11 stage-1 MMA issuers (one per group), warp 10 stage-2 MMA issuer, warps 2-5 and 6-9 two
+// Warp roles (352 threads): warp 0 TMA producer, warp 1 stage-1 MMA issuer, warp 10 stage-2 MMA issuer, warps 2-5 and 6-9 two
 // transform groups that ping-pong over the streamed tiles (group g owns TMEM buffer X[g]),
 // so the tensor core computes the logits of tile j+1 while the CUDA cores exponentiate tile j.
 // Every streamed tile is used twice from the same shared-memory bytes: K-major as the B operand of stage 1 and
@@ -26,6 +26,24 @@
 
 #include <type_traits>
 
+#ifdef PT_ATTN_TRACE
+// development builds: a wait that has spun 2^20 times writes (barrier offset, parity) of its warp and the raw words of all barriers of
+// its CTA to g_watch (pinned host memory: survives the trap that follows).  Layout per CTA: [12 warps] + [40 barrier words].
+#include <stdint.h>
+__device__ unsigned long long* g_watch = nullptr;
+__device__ __forceinline__ void pt_mbar_watch(uint32_t bar, uint32_t parity) {
+  if (g_watch == nullptr) return;
+  volatile unsigned long long* w = g_watch + (size_t)blockIdx.x * 52;
+  const uint32_t base = bar & ~511u;
+  w[threadIdx.x >> 5] = (1ull << 63) | ((unsigned long long)(threadIdx.x & 31) << 40) | ((unsigned long long)parity << 32) | (bar - base);
+  for (int i = 0; i < 40; ++i) {
+    unsigned long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(base + 8u * i));
+    w[12 + i] = v;
+  }
+}
+#define PT_MBAR_WATCH(bar, parity) pt_mbar_watch(bar, parity)
+#endif
 #include "tc_common.cuh"
 
 namespace {
@@ -48,21 +66,30 @@ struct alignas(64) AParams {
   const float* delta;  // DQ/DKV.                      [B, H, Lq]
 #ifdef PT_ATTN_TRACE
   unsigned long long* trace;   // development builds only (tools/attn_trace.py): [12 warps][1024 events][id, clock] of CTA 0
+  int trace_last;
 #endif
 };
 
 #ifdef PT_ATTN_TRACE
 unsigned long long* g_attn_trace = nullptr;
 int g_attn_trace_mode = -1;   // trace only kernels of this MODE (-1: all)
+int g_attn_trace_last = 0;
+// trace_last = 0: event log of CTA 0.  trace_last = 1: only the LAST event of every warp of every CTA, [CTA][12 warps][id | count << 32]:
+// pointed at pinned host memory it survives a trapped kernel and shows where each warp of a dead pipeline is waiting.
 #define TR(id)                                                                   \
   do {                                                                           \
-    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_n < 1024) {     \
-      p.trace[(warp * 1024 + tr_n) * 2] = (unsigned long long)(id);              \
-      p.trace[(warp * 1024 + tr_n) * 2 + 1] = (unsigned long long)clock64();     \
-      ++tr_n;                                                                    \
+    if (p.trace != nullptr && lane == 0) {                                       \
+      if (p.trace_last) {                                                        \
+        *(volatile unsigned long long*)(p.trace + blockIdx.x * 12 + warp) = (unsigned long long)(id) | ((unsigned long long)tr_n << 32); \
+        ++tr_n;                                                                  \
+      } else if (blockIdx.x == 0 && tr_n < 1024) {                               \
+        p.trace[(warp * 1024 + tr_n) * 2] = (unsigned long long)(id);            \
+        p.trace[(warp * 1024 + tr_n) * 2 + 1] = (unsigned long long)clock64();   \
+        ++tr_n;                                                                  \
+      }                                                                          \
     }                                                                            \
   } while (0)
-#define PT_ATTN_SET_TRACE(ap) (ap).trace = g_attn_trace
+#define PT_ATTN_SET_TRACE(ap) ((ap).trace = g_attn_trace, (ap).trace_last = g_attn_trace_last)
 #else
 #define TR(id)
 #define PT_ATTN_SET_TRACE(ap)
@@ -147,7 +174,7 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t* v, int c, int ncol, fl
 }
 
 template <int MODE, int DP>
-__global__ void __launch_bounds__(384, 1) attn_kernel(const __grid_constant__ AParams p) {
+__global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AParams p) {
   using C = ACfg<MODE, DP>;
   constexpr int NX = C::NX, NACC = C::NACC, XBUF = C::XBUF, KB = C::KB, NSTAGE = C::NSTAGE, XSLOTS = C::XSLOTS;
   extern __shared__ uint8_t smem_raw[];
@@ -196,7 +223,7 @@ __global__ void __launch_bounds__(384, 1) attn_kernel(const __grid_constant__ AP
     for (int i = 0; i < NX; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmR[i])) : "memory");
     for (int i = 0; i < 2; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmS[i])) : "memory");
     mbar_init(r_full, 1);
-    mbar_init(r_empty, XBUF == 2 ? 2 : 1);      // one arrival per stage-1 issuer
+    mbar_init(r_empty, 1);
     for (int s = 0; s < 8; ++s) {
       mbar_init(s_full(s), 1);
       mbar_init(s_empty(s), 1);
@@ -263,51 +290,54 @@ __global__ void __launch_bounds__(384, 1) attn_kernel(const __grid_constant__ AP
       };
       for (int j = 0; j < n_tiles; ++j) load_tile(&p.tmS[0], &p.tmS[1], j * BN, j * BN);
     }
-  } else if (warp == 1 || warp == 11) {
-    // ------------------------------------------------------------------ stage-1 MMA issuers, one per transform group (warp-uniform
-    // control flow, one elected lane issues).  Each runs ahead of its group as far as the ring and the X buffers allow and never
-    // waits on stage 2.  One issuer for both groups (the first version) was the serial bottleneck of all three kernels: per tile it
-    // waits for the ring stage, waits for the X buffer, converts ~25 operands to uniform registers and issues up to 8 MMAs + commits --
-    // 1000-1400 clocks of dependent scalar work per tile (per-warp event trace, tools/attn_trace.py), i.e. the whole tile time.
-    const int ig = warp == 1 ? 0 : 1;
-    if (XBUF == 2 || ig == 0) {
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ stage-1 MMA issuer (warp-uniform control flow, one elected lane issues).
+    // Runs ahead of the transform groups as far as the ring and the X buffers allow; never waits on stage 2.  Per tile it waits for the
+    // ring stage and the X buffer, converts ~25 operands to uniform registers and issues up to 8 MMAs + a commit: 1000-1400 clocks of
+    // dependent scalar work per tile (per-warp event trace, tools/attn_trace.py).  A second issuer warp (one per group) was tried:
+    // 3 % faster forward, but the d = 160 forward died with a launch failure within seconds (not a barrier time-out: no wait had
+    // spun long) in every build that had two warps issuing stage-1 MMAs, and never with one -- not shipped.
+    constexpr uint32_t gmask = 3u;      // groups served by this issuer (bit g)
+    if (gmask != 0) {
       const bool leader = elect_one();
       const uint32_t idesc1 = idesc_f16(0, 0, BN, BM);
       // UMMA descriptors are linear in the shared-memory address: precompute the bases, add (bytes >> 4) per use
       const uint64_t dR = umma_desc(sR, 0, 1024);            // resident tiles, K-major
       const uint64_t dS = umma_desc(sS, 0, 1024);            // streamed tiles, K-major view
-      const int jstep1 = XBUF == 2 ? 2 : 1;
       int tbase = 0;         // streamed tiles of earlier work items (ring position of tile j = (tbase + j) % NSTAGE)
-      int kb = 0;            // X fills of this group by earlier work items
+      int kb0 = 0, kb1 = 0;  // X fills by earlier work items, per group
       // FWD: an X slot is released by the stage-2 commit (P was written over the logits and has been consumed).  Backward with separate
-      // T columns: by the transform threads once they have read the logits (x_empty).  Per slot: what the last fill was (2 bits: 0 none,
-      // 1 released by x_empty, 2 by p_empty) and the parity of the next phase of each of its two barriers.
+      // T columns: by the transform threads once they have read the logits (x_empty).  Per slot i = g * 2 + slot: what the last fill was
+      // (2 bits: 0 none, 1 released by x_empty, 2 by p_empty) and the parity of the next phase of each of its two barriers.
       uint32_t last_kind = 0, par_x = 0, par_p = 0;
-      auto wait_slot_free = [&](int slot, uint32_t kind) {
-        const uint32_t prev = (last_kind >> (2 * slot)) & 3u;
+      auto wait_slot_free = [&](int g, int slot, uint32_t kind) {
+        const int i = g * 2 + slot;
+        const uint32_t prev = (last_kind >> (2 * i)) & 3u;
         if (prev == 1u) {
-          mbar_wait(x_empty(ig, slot), (par_x >> slot) & 1u);
-          par_x ^= 1u << slot;
+          mbar_wait(x_empty(g, slot), (par_x >> i) & 1u);
+          par_x ^= 1u << i;
         } else if (prev == 2u) {
-          mbar_wait(p_empty(ig, slot), (par_p >> slot) & 1u);
-          par_p ^= 1u << slot;
+          mbar_wait(p_empty(g, slot), (par_p >> i) & 1u);
+          par_p ^= 1u << i;
         }
-        last_kind = (last_kind & ~(3u << (2 * slot))) | (kind << (2 * slot));
+        last_kind = (last_kind & ~(3u << (2 * i))) | (kind << (2 * i));
       };
       int wi = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
         mbar_wait(r_full, wi & 1);
-        for (int j = XBUF == 2 ? ig : 0; j < n_tiles; j += jstep1) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const int g = gsel(j);
+          if (!((gmask >> g) & 1u)) continue;
           const int t = tbase + j;
           const int s1 = t % NSTAGE;
           const uint32_t ph1 = (uint32_t)(t / NSTAGE) & 1u;
           // FWD: the group's k-th tile overall uses X slot k % XSLOTS; backward: one buffer (X1 | X2)
-          const int k = kb + (XBUF == 2 ? (j >> 1) : j);
+          const int k = (g ? kb1 : kb0) + (XBUF == 2 ? (j >> 1) : j);
           const int slot = (MODE == MODE_FWD && XSLOTS == 2) ? (k & 1) : 0;
           TR(20);
           mbar_wait(s_full(s1), ph1);
           TR(21);
-          wait_slot_free(slot, (MODE != MODE_FWD && C::SEP_T) ? 1u : 2u);
+          wait_slot_free(g, slot, (MODE != MODE_FWD && C::SEP_T) ? 1u : 2u);
           TR(22);
           fence_after();
           if (leader) {
@@ -316,24 +346,23 @@ __global__ void __launch_bounds__(384, 1) attn_kernel(const __grid_constant__ AP
             for (int x = 0; x < NX; ++x) {
               const uint64_t a0 = dR + (uint64_t)(x * (C::R_BYTES >> 4));
               const uint64_t b0 = bS + (uint64_t)(x * (C::S_BYTES >> 4));
-              const uint32_t dcol = tmem + xcol(ig, MODE == MODE_FWD ? slot : x);
+              const uint32_t dcol = tmem + xcol(g, MODE == MODE_FWD ? slot : x);
 #pragma unroll
               for (int kk = 0; kk < DP / 16; ++kk)
                 if (kk < ks1)
                   umma_f16(dcol, a0 + (uint64_t)((kk >> 2) * (BM * 128 >> 4) + (kk & 3) * 2),
                            b0 + (uint64_t)((kk >> 2) * (BN * 128 >> 4) + (kk & 3) * 2), idesc1, kk > 0 ? 1u : 0u);
             }
-            umma_commit(x_full(ig, slot));
+            umma_commit(x_full(g, slot));
           }
           __syncwarp();
           TR(23);
         }
-        // this issuer's stage-1 MMAs of the work item have read the resident tiles (one arrival per issuer; an issuer without tiles
-        // in this item arrives at once)
-        if (leader) umma_commit(r_empty);
+        if (leader) umma_commit(r_empty);      // the stage-1 MMAs of the work item have read the resident tiles
         __syncwarp();
         tbase += n_tiles;
-        kb += ig == 0 ? per_g0 : per_g1;
+        kb0 += per_g0;
+        kb1 += per_g1;
       }
     }
   } else if (warp == 10) {
@@ -400,13 +429,47 @@ __global__ void __launch_bounds__(384, 1) attn_kernel(const __grid_constant__ AP
     // barriers per pair: the owner waits with bar.sync (64 = its 32 threads + the partner's 32 arrivals), the partner hands the turn
     // over with bar.arrive after its own phase.  Turns follow the tile order (tile j belongs to group j & 1); with an odd number of
     // tiles group 1 passes once without work so that the next work item starts with group 0 again.
+#ifdef PT_ATTN_NO_TURNS
+    constexpr bool TURNS = false;
+#else
     constexpr bool TURNS = MODE == MODE_FWD && XBUF == 2;
+#endif
     const int bar_mine = 3 + 2 * q + g, bar_other = 3 + 2 * q + (g ^ 1);
     auto turn_wait = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory"); };
     auto turn_pass = [&]() { asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory"); };
     if (TURNS && g == 1) turn_pass();      // group 0 moves first
     int kx = 0;           // running X use count of this group (across work items)
     uint32_t v1[32], v2[32];
+    // Backward: the softmax statistics of a work item (lse, delta: global loads, a DRAM round trip) are requested one work item ahead --
+    // before the epilogue of the previous one -- and only consumed here; loaded on demand they stalled every work item for the full
+    // latency (per-warp event trace: 1300 clocks in dQ, 2300 in dK/dV per work item).
+    constexpr int NPRE = 4;                 // DKV: statistics columns per thread held in registers (4 x 256 = 1024 query rows; beyond: on demand)
+    float pre_a[MODE == MODE_DKV ? NPRE : 1], pre_d[MODE == MODE_DKV ? NPRE : 1];
+    auto prefetch_stats = [&](int w2) {
+      if (MODE == MODE_FWD) return;
+      int r0n, hn, bn_;
+      decode(w2, r0n, hn, bn_);
+      if (MODE == MODE_DQ) {
+        pre_a[0] = INFINITY, pre_d[0] = 0.f;
+        if (w2 < total_work && r0n + row < p.Lr) {
+          const long long si = ((long long)bn_ * p.H + hn) * p.Lr + r0n + row;
+          pre_a[0] = __ldg(p.lse + si);
+          pre_d[0] = __ldg(p.delta + si);
+        }
+      } else {
+        const long long sb = ((long long)bn_ * p.H + hn) * p.Ls;
+#pragma unroll
+        for (int u = 0; u < NPRE; ++u) {
+          const int qi = (int)threadIdx.x - 64 + u * 256;
+          pre_a[u] = INFINITY, pre_d[u] = 0.f;
+          if (w2 < total_work && qi < p.Ls) {
+            pre_a[u] = __ldg(p.lse + sb + qi);
+            pre_d[u] = __ldg(p.delta + sb + qi);
+          }
+        }
+      }
+    };
+    prefetch_stats(blockIdx.x);
     int wi = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++wi) {
       int r0, h, b;
@@ -541,17 +604,21 @@ __global__ void __launch_bounds__(384, 1) attn_kernel(const __grid_constant__ AP
         TR(14);
       } else {
         // ---- backward modes
-        float lse2 = INFINITY, dl = 0.f;   // DQ: this thread's row statistics
-        if (MODE == MODE_DQ && r < p.Lr) {
-          const long long si = ((long long)b * p.H + h) * p.Lr + r;
-          lse2 = p.lse[si] * 1.4426950408889634f;
-          dl = p.delta[si] * p.scale;
-        }
+        // DQ: this thread's row statistics (+inf masks a row beyond Lr)
+        const float lse2 = MODE == MODE_DQ ? pre_a[0] * 1.4426950408889634f : INFINITY, dl = MODE == MODE_DQ ? pre_d[0] * p.scale : 0.f;
         if (MODE == MODE_DKV) {
           // column statistics of the whole work item (columns = query rows), once: lse * log2(e) (+inf masks a column), delta * scale
           asm volatile("bar.sync 2, 256;" ::: "memory");     // everyone has finished reading the previous work item's statistics
           const long long sb = ((long long)b * p.H + h) * p.Ls;
-          for (int qi = threadIdx.x - 64; qi < n_tiles * BN; qi += 256) {
+#pragma unroll
+          for (int u = 0; u < NPRE; ++u) {
+            const int qi = (int)threadIdx.x - 64 + u * 256;
+            if (qi < n_tiles * BN) {
+              sstat[qi] = pre_a[u] * 1.4426950408889634f;
+              sstat[C::STAT_COLS + qi] = pre_d[u] * p.scale;
+            }
+          }
+          for (int qi = threadIdx.x - 64 + NPRE * 256; qi < n_tiles * BN; qi += 256) {
             float a = INFINITY, d = 0.f;
             if (qi < p.Ls) {
               a = __ldg(p.lse + sb + qi) * 1.4426950408889634f;
@@ -619,6 +686,7 @@ __global__ void __launch_bounds__(384, 1) attn_kernel(const __grid_constant__ AP
             mbar_arrive(t_full(g, 0));
             TR(6);
           }
+        prefetch_stats(w + (int)gridDim.x);      // the next work item's statistics: in flight during the epilogue
         // ---- epilogue: accumulators -> bf16 rows
         TR(11);
         mbar_wait(acc_full, wi & 1);
@@ -727,9 +795,9 @@ int launch_attn(const AParams& ap, dim3 grid, cudaStream_t st) {
 #ifdef PT_ATTN_TRACE
   AParams apt = ap;
   if (g_attn_trace_mode >= 0 && g_attn_trace_mode != MODE) apt.trace = nullptr;
-  attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 384, ACfg<MODE, DP>::SMEM_BYTES, st>>>(apt);
+  attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 352, ACfg<MODE, DP>::SMEM_BYTES, st>>>(apt);
 #else
-  attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 384, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
+  attn_kernel<MODE, DP><<<(unsigned)(work < sms ? work : sms), 352, ACfg<MODE, DP>::SMEM_BYTES, st>>>(ap);
 #endif
   PT_LAUNCH_CHECK();
   return PT_OK;
@@ -844,8 +912,11 @@ extern "C" int pt_attn_bwd(const pt_attn_t* a, void* stream) {
 #ifdef PT_ATTN_TRACE
 // development builds only: per-warp event log of CTA 0 (see TR above); buf = [12][1024][2] uint64, zero-filled by the caller
 extern "C" int pt_attn_set_trace(void* buf, int mode) {
-  g_attn_trace_mode = mode;
+  g_attn_trace_mode = (mode < 0 || mode == 7) ? -1 : (mode & 3);   // 7: every kernel, last-event form
+  g_attn_trace_last = mode >= 0 && (mode & 4) ? 1 : 0;      // mode | 4: last-event-per-warp form (all CTAs)
   g_attn_trace = reinterpret_cast<unsigned long long*>(buf);
+  unsigned long long* wp = (buf != nullptr && g_attn_trace_last) ? g_attn_trace + 160 * 12 : nullptr;   // after the last-event table
+  cudaMemcpyToSymbol(g_watch, &wp, sizeof(wp));
   return PT_OK;
 }
 #endif

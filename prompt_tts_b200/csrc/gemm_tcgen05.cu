@@ -775,18 +775,40 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   }
 
   // tile width: cost model fitted to tools/gemm_sweep.py on B200 (profiles/r01_gemm_sweep_v3.txt).  One k-iteration (BK = 64) of a
-  // 128 x bn tile costs ~800 / 730 / 660 / 640 / 430 / 260 cycles for bn = 256 / 224 / 192 / 160 / 128 / 64 (each SM ingests
-  // operands at ~64 B/clk, which favours wide tiles).  Data-parallel launches are paced by the busiest SM (ceil(tiles / SMs)
+  // 128 x bn tile costs ~800 / 730 / 660 / 640 / 430 / 260 cycles for bn = 256 / 224 / 192 / 160 / 128 / 64 in this model (an
+  // effective figure that folds the per-tile epilogue and fill in; the marginal mainloop cost is the tensor pipe's, see DESIGN.md 3.1;
+  // what favours wide tiles is the fixed cost per tile).  Data-parallel launches are paced by the busiest SM (ceil(tiles / SMs)
   // tiles); stream-K launches are balanced but pay one atomic flush of a tile per segment (~0.65 cycles per flushed column-row),
   // and their 64-wide tiles (MN-major operands, two CTAs per SM sharing the flush path) run ~1.6x slower than that table.
   const bool streamk = g->out_dtype == PT_OUT_F32_ATOMIC_ADD;
   PT_REQUIRE(!streamk || (g->bias == nullptr && g->bias_z2 == nullptr && g->residual == nullptr),
              "pt_gemm: PT_OUT_F32_ATOMIC_ADD outputs are scheduled stream-K and take no bias/residual");
   int bn = g->block_n & ~1;                 // bit 0 of block_n: 1 = do not form clusters (calibration runs)
-  const bool allow_cluster = (g->block_n & 1) == 0;
+  bool table_no_cluster = false;
+  const bool allow_cluster_arg = (g->block_n & 1) == 0;
   const long long mt = (g->M + BM - 1) / BM;
   const long long zz = (long long)g->nz2 * g->nz3;
   const int sms = pt_num_sms();
+  if (g->block_n == 0) {
+    // measured per-shape overrides of the cost model below (the shapes of the bench model's train step; PT_GEMM_NO_TABLE=1 ignores them)
+    struct TileRow { int M, N, K, zz, nseg, ak, bk, od, res, bn; };
+    static const TileRow table[] = {
+#include "gemm_tile_table.inc"
+        {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
+    static const bool no_table = getenv("PT_GEMM_NO_TABLE") != nullptr;
+    if (!no_table) {
+      long long ktot = 0;
+      for (int s = 0; s < g->nseg; ++s) ktot += (long long)g->seg[s].nk * g->seg[s].nrep;
+      for (const TileRow& r : table)
+        if (r.M == g->M && r.N == g->N && r.K == ktot && r.zz == zz && r.nseg == g->nseg && r.ak == kp.a_kmajor && r.bk == kp.b_kmajor &&
+            r.od == g->out_dtype && r.res == (g->residual != nullptr)) {
+          bn = r.bn & ~1;
+          table_no_cluster = (r.bn & 1) != 0;
+          break;
+        }
+    }
+  }
+  const bool allow_cluster = allow_cluster_arg && !table_no_cluster;
   if (bn == 0) {
     // 224 / 192 exist for wave quantisation: when a narrower tile keeps the number of waves, every wave gets shorter
     const int cand[6] = {256, 224, 192, 128, 64, 160};

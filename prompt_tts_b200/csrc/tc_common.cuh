@@ -40,6 +40,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
+#ifdef PT_MBAR_WATCH
+    if (spins == (1u << 20)) PT_MBAR_WATCH(bar, parity);   // development builds: record what a stuck wait is waiting for
+#endif
     if (++spins > (1u << 22)) __trap();  // a dead pipeline becomes a launch error, not a hang
   }
 }
