@@ -53,6 +53,9 @@ int pt_check_device(int dev);
 int pt_set_sm_reserve(int n);
 /* cumulative number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long pt_launch_count(void);
+/* tile configuration the last pt_gemm call of this thread chose: block_n | (cluster of two ? 0 : 1) -- the value that, passed as
+   pt_gemm_t.block_n, reproduces it (tools/gemm_sweep.py: is a forced width a different configuration from the library's choice?) */
+int pt_gemm_last_tile(void);
 
 /* ------------------------------------------------------------------ tcgen05 GEMM family ------- */
 /* One operand = a bf16 tensor of rank <= 4.  dim[0] is the contiguous axis (stride[0] == 1).
@@ -121,6 +124,11 @@ int pt_groupnorm_stats(const void* x, float* stats, int B, int L, int C, int G, 
 /* y = act(gn(x) * gamma + beta); act: 0 none, 1 SiLU */
 int pt_groupnorm_apply(const void* x, const float* stats, const float* gamma, const float* beta, void* y,
                        int B, int L, int C, int G, int act, void* stream);
+/* stats + apply in one call (tts/ldm/resnet.py:238-240, 267-273: GroupNorm -> SiLU).  When one sample [L, C] fits in the shared
+ * memory of a cluster of 8 CTAs (<= 100 KB each) it is read from HBM once (bulk copy -> reduce -> exchange of the group sums over distributed shared
+ * memory -> normalise from the resident copy); otherwise the two calls above.  stats[B, G, 2] is written for the backward pass. */
+int pt_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
+                     int B, int L, int C, int G, float eps, int act, void* stream);
 /* backward of apply+stats: dx bf16 (+ dx_add if not NULL: fused accumulation of the gradient that reached x through another
  * branch; dx may alias dx_add); dgamma/dbeta fp32 [C] are ACCUMULATED (atomic add).  scratch: fp32 [B, G, 2], zero-filled by the callee. */
 int pt_groupnorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta,

@@ -93,6 +93,7 @@ _SIGS = {
     "attn_bwd": "pp",
     "groupnorm_stats": "ppiiiifp",
     "groupnorm_apply": "pppppiiiiip",
+    "groupnorm_fwd": "pppppiiiifip",
     "groupnorm_bwd": "ppppppppppiiiiip",
     "layernorm_fwd": "ppppplifp",
     "layernorm_bwd": "pppppppplip",
@@ -142,7 +143,7 @@ _SIGS = {
     "adamw_step_dev": "ppippplpp",
 }
 _CT = {"p": C.c_void_p, "i": C.c_int, "l": C.c_int64, "f": C.c_float}
-EXPORTS = ["pt_version", "pt_last_error", "pt_launch_count", "pt_rvq_encode_tc_scratch_bytes"] + ["pt_" + k for k in _SIGS]
+EXPORTS = ["pt_version", "pt_last_error", "pt_launch_count", "pt_gemm_last_tile", "pt_rvq_encode_tc_scratch_bytes"] + ["pt_" + k for k in _SIGS]
 
 
 def _bind(l):

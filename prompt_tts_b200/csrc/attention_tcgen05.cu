@@ -637,16 +637,8 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
             mbar_wait(x_full(g, 0), kx & 1);
             TR(1);
             fence_after();
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-              tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
-              tmem_ld32(tl + xcol(g, 1) + c * 32, v2);
-              tmem_wait_ld();
-              if (C::SEP_T && c == BN / 32 - 1) {       // the logits of this tile are in registers: stage 1 may refill the buffer
-                fence_before();
-                mbar_arrive(x_empty(g, 0));
-              }
-              uint32_t pp[16], dd[16];
+            // 32 logit columns of both products -> P / dS as bf16 pairs
+            auto chunk = [&](int c, const uint32_t* x1, const uint32_t* x2, uint32_t* pp, uint32_t* dd) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 float l4[4] = {lse2, lse2, lse2, lse2}, d4[4] = {dl, dl, dl, dl};
@@ -658,25 +650,42 @@ __global__ void __launch_bounds__(352, 1) attn_kernel(const __grid_constant__ AP
                 float pe[4], de[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const float e = ex2f(fmaf(__uint_as_float(v1[i + u]), c2, -l4[u]));
+                  const float e = ex2f(fmaf(__uint_as_float(x1[i + u]), c2, -l4[u]));
                   pe[u] = e;
-                  de[u] = e * fmaf(__uint_as_float(v2[i + u]), p.scale, -d4[u]);
+                  de[u] = e * fmaf(__uint_as_float(x2[i + u]), p.scale, -d4[u]);
                 }
                 pp[i >> 1] = pack2(pe[0], pe[1]);
                 pp[(i >> 1) + 1] = pack2(pe[2], pe[3]);
                 dd[i >> 1] = pack2(de[0], de[1]);
                 dd[(i >> 1) + 1] = pack2(de[2], de[3]);
               }
-              if (C::SEP_T && c == 0 && kx > 0) {       // stage 2 of this group's previous tile has consumed the T columns
+            };
+            auto wait_t_free = [&]() {                  // stage 2 of this group's previous tile has consumed the T columns
+              if (C::SEP_T && kx > 0) {
                 mbar_wait(p_empty(g, 0), (kx - 1) & 1);
                 fence_after();
               }
-              // DQ: dS; DKV: P^T and dS^T (16 columns per 32 logits) -- in their own columns, or in place over the logits already consumed
-              if (MODE == MODE_DKV) {
-                tmem_st16(tl + tcol(g, 0) + c * 16, pp);
-                tmem_st16(tl + tcol(g, 1) + c * 16, dd);
-              } else {
-                tmem_st16(tl + tcol(g, 0) + c * 16, dd);
+            };
+            {
+#pragma unroll
+              for (int c = 0; c < BN / 32; ++c) {
+                tmem_ld32(tl + xcol(g, 0) + c * 32, v1);
+                tmem_ld32(tl + xcol(g, 1) + c * 32, v2);
+                tmem_wait_ld();
+                if (C::SEP_T && c == BN / 32 - 1) {       // the logits of this tile are in registers: stage 1 may refill the buffer
+                  fence_before();
+                  mbar_arrive(x_empty(g, 0));
+                }
+                uint32_t pp[16], dd[16];
+                chunk(c, v1, v2, pp, dd);
+                if (c == 0) wait_t_free();
+                // DQ: dS; DKV: P^T and dS^T (16 columns per 32 logits) -- in their own columns, or in place over the logits already consumed
+                if (MODE == MODE_DKV) {
+                  tmem_st16(tl + tcol(g, 0) + c * 16, pp);
+                  tmem_st16(tl + tcol(g, 1) + c * 16, dd);
+                } else {
+                  tmem_st16(tl + tcol(g, 0) + c * 16, dd);
+                }
               }
             }
             TR(4);

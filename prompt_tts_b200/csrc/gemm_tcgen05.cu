@@ -729,6 +729,9 @@ int launch(const KParams& kp, dim3 grid, cudaStream_t st) {
 
 }  // namespace
 
+static thread_local int g_last_tile = 0;
+extern "C" int pt_gemm_last_tile(void) { return g_last_tile; }
+
 extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   PT_REQUIRE(g != nullptr, "pt_gemm: null descriptor");
   PT_REQUIRE(g->nseg >= 1 && g->nseg <= 8, "pt_gemm: nseg=%d", g->nseg);
@@ -908,6 +911,7 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   if (G > slots) G = slots;
   dim3 grid((unsigned)(G * mc), 1, 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  g_last_tile = bn | (bn == 256 && mc == 1 ? 1 : 0);
   switch (bn) {
     case 64: return launch<64, 1>(kp, grid, st);
     case 128: return launch<128, 1>(kp, grid, st);

@@ -1,5 +1,7 @@
 // GroupNorm (+SiLU) and LayerNorm, forward and backward, channels-last bf16 activations, fp32 math.
 // HBM-bound: 16-byte vector accesses, one pass for statistics, one for the apply.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -378,6 +380,237 @@ int gn_fast(const float* stats, const float* gamma, const float* beta, int C, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// GroupNorm forward with the sample resident in shared memory: a cluster of GN_CL CTAs owns one batch element; CTA k streams its
+// slice of rows ([L / GN_CL rows] x C) from HBM ONCE, stashing the raw vectors in shared memory while it reduces them, exchanges
+// the per-group partial sums with its peers through distributed shared memory, and normalises from the resident copy: 1 read + 1
+// write of the tensor instead of 2 reads + 1 write (statistics kernel + apply kernel).  Same thread mapping and arithmetic as the
+// streaming kernels above.  Measured cold (tools/gn_probe.py, B = 32): 14.2 vs 16.5 us at 752 x 320, 14.7 vs 18.1 at 376 x 640,
+// 17.0 vs 19.6 at 188 x 1280 -- as long as a CTA's slice is small enough for two CTAs per SM.  Beyond that (one CTA per SM) only
+// ~8 clusters of 8 are resident at a time and the kernel runs in 3-4 waves (752 x 640: 41.8 vs 24.5 us), which is also why the
+// backward pass (x AND dy resident: twice the bytes) stays on the streaming pair: a resident-sample backward kernel measured 59 vs
+// 33 us at 752 x 320.  (Loading the slice with cp.async.bulk instead of vector loads made no difference either way.)
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_CL = 8;
+
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t gn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gn_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// a float at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ float gn_ld_peer(const float* p, uint32_t rank) {
+  uint32_t a;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(gn_smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+// per-channel coefficients of this thread's 8 channels, statistics (mean, rstd per group) in shared memory
+__device__ __forceinline__ void gn_coeffs_sm(const float* sstat, const float* __restrict__ gamma, const float* __restrict__ beta, int c0, int cpg,
+                                             bool vec, float* a1, float* b1, float* rs, float* ms) {
+  float gm[8], bt[8];
+  if (vec) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), e1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    gm[0] = g0.x, gm[1] = g0.y, gm[2] = g0.z, gm[3] = g0.w, gm[4] = g1.x, gm[5] = g1.y, gm[6] = g1.z, gm[7] = g1.w;
+    bt[0] = e0.x, bt[1] = e0.y, bt[2] = e0.z, bt[3] = e0.w, bt[4] = e1.x, bt[5] = e1.y, bt[6] = e1.z, bt[7] = e1.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gm[j] = gamma[c0 + j], bt[j] = beta[c0 + j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    const float mean = sstat[2 * g], rstd = sstat[2 * g + 1];
+    a1[j] = rstd * gm[j];
+    b1[j] = bt[j] - mean * rstd * gm[j];
+    if (rs) {
+      rs[j] = rstd;
+      ms[j] = -mean * rstd;
+    }
+  }
+}
+
+// sum over the cluster of every CTA's part[0 .. 2G) -> tot[0 .. 2G) (tot: this CTA's scratch, >= (GN_CL + 1) * 2G floats).  The remote
+// loads are spread over the threads (one dependent DSMEM round trip each instead of 2 * GN_CL in a row per thread).
+__device__ __forceinline__ void gn_cluster_sum(const float* part, float* tot, int G) {
+  const int n = 2 * G;
+  float* tmp = tot + n;      // [GN_CL][2G]
+  for (int i = threadIdx.x; i < n * GN_CL; i += blockDim.x) tmp[i] = gn_ld_peer(part + (i % n), (uint32_t)(i / n));
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < GN_CL; ++k) a += tmp[k * n + i];
+    tot[i] = a;
+  }
+  __syncthreads();
+}
+
+// shared memory: [chunk(s) of rows, bf16][threads * 16 floats reduction scratch][G * 2 partials][G * 2 statistics][mbarrier]
+struct GnClSmem {
+  uint8_t* x;
+  uint8_t* dy;
+  float* red;
+  float* part;
+  float* stat;
+  uint32_t bar;
+};
+__device__ __forceinline__ GnClSmem gn_cl_carve(uint8_t* raw, int chunk_bytes, int nchunks, int threads, int G) {
+  GnClSmem m;
+  m.x = raw;
+  m.dy = raw + chunk_bytes;
+  m.red = reinterpret_cast<float*>(raw + (size_t)chunk_bytes * nchunks);
+  m.part = m.red + threads * 16;
+  m.stat = m.part + 2 * G;
+  m.bar = gn_smem_u32(m.stat + 2 * G);
+  return m;
+}
+// fold per-thread per-channel pairs (s[j], q[j]) over the rpp row phases into per-channel pairs red[c * 2 + {0, 1}]
+__device__ __forceinline__ void gn_fold_channels(float* red, const GnMap& m, int C, const float* s, const float* q) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[((m.rsub * C) + m.v * 8 + j) * 2] = s[j];
+    red[((m.rsub * C) + m.v * 8 + j) * 2 + 1] = q[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += m.threads) {
+    float a = red[c * 2], d = red[c * 2 + 1];
+    for (int k = 1; k < m.rpp; ++k) {
+      a += red[(k * C + c) * 2];
+      d += red[(k * C + c) * 2 + 1];
+    }
+    red[c * 2] = a;
+    red[c * 2 + 1] = d;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(320) gn_fwd_cluster_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             bf16* __restrict__ y, float* __restrict__ stats, int L, int C, int G,
+                                                             int rows_per_cta, int chunk_bytes, float eps, int act, int vec) {
+  extern __shared__ __align__(128) uint8_t gn_raw[];
+  const GnMap m = gn_map(C);
+  const GnClSmem sm = gn_cl_carve(gn_raw, chunk_bytes, 1, m.threads, G);
+  const int rank = (int)gn_cluster_rank();
+  const int b = blockIdx.y;
+  const int r0 = rank * rows_per_cta;
+  const int nrows = max(0, min(L, r0 + rows_per_cta) - r0);
+  const long long gbase = ((long long)b * L + r0) * C;
+  // pass 1: stream this CTA's rows from HBM in batches of U per thread (all loads of a batch in flight at once), keep the raw
+  // vectors in shared memory, accumulate the per-channel sums on the way.  (A bulk copy of the whole slice followed by a pass over
+  // shared memory was measured first: one CTA per SM then has far too few bytes in flight -- 6 GB/s per SM.)
+  bf16* sx = reinterpret_cast<bf16*>(sm.x);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  {
+    constexpr int U = 8;
+    const bf16* xg = x + gbase + m.v * 8;
+    for (int r = m.rsub; r < nrows; r += U * m.rpp) {
+      bf16x8 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r + u * m.rpp < nrows) raw[u] = load8raw(xg + (size_t)(r + u * m.rpp) * C);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (r + u * m.rpp < nrows) {
+          st16(sx + (size_t)(r + u * m.rpp) * C + m.v * 8, raw[u]);
+          float f[8];
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s[j] += f[j];
+            q[j] = fmaf(f[j], f[j], q[j]);
+          }
+        }
+    }
+  }
+  gn_fold_channels(sm.red, m, C, s, q);
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += m.threads) {
+    float a = 0.f, d = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      a += sm.red[(g * cpg + k) * 2];
+      d += sm.red[(g * cpg + k) * 2 + 1];
+    }
+    sm.part[2 * g] = a;
+    sm.part[2 * g + 1] = d;
+  }
+  gn_cluster_sync();      // every CTA's partials are written
+  const float inv_count = 1.f / ((float)cpg * (float)L);
+  gn_cluster_sum(sm.part, sm.red, G);      // red is free again: [2G] totals + [GN_CL][2G] staging
+  for (int g = threadIdx.x; g < G; g += m.threads) {
+    const float a = sm.red[2 * g], d = sm.red[2 * g + 1];
+    const float mean = a * inv_count;
+    const float var = fmaxf(d * inv_count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    sm.stat[2 * g] = mean;
+    sm.stat[2 * g + 1] = rstd;
+    if (rank == 0) {
+      stats[((long long)b * G + g) * 2] = mean;
+      stats[((long long)b * G + g) * 2 + 1] = rstd;
+    }
+  }
+  gn_cluster_sync();      // peers have read this CTA's partials (it may exit); the statistics are visible to the whole CTA
+  float a1[8], b1[8];
+  gn_coeffs_sm(sm.stat, gamma, beta, m.v * 8, cpg, vec != 0, a1, b1, nullptr, nullptr);
+  bf16* yb = y + gbase + m.v * 8;
+#pragma unroll 2
+  for (int r = m.rsub; r < nrows; r += m.rpp) {
+    float f[8];
+    load8(sx + (size_t)r * C + m.v * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(f[j], a1[j], b1[j]);
+      f[j] = act ? z * sigmoid_fast(z) : z;
+    }
+    store8(yb + (size_t)r * C, f);
+  }
+}
+
+// rows per CTA, bytes of one resident chunk and the dynamic shared memory of the cluster kernels; false if the sample does not fit
+bool gn_cluster_fit(int L, int C, int G, int threads, int nchunks, int* rows_per_cta, int* chunk_bytes, size_t* smem) {
+  static const bool off = getenv("PT_GN_NO_CLUSTER") != nullptr;
+  if (off) return false;
+  const int rows = (L + GN_CL - 1) / GN_CL;
+  const int cb = (rows * C * 2 + 127) / 128 * 128;
+  const size_t need = (size_t)cb * nchunks + (size_t)threads * 16 * sizeof(float) + (size_t)4 * G * sizeof(float) + 16;
+  *rows_per_cta = rows;
+  *chunk_bytes = cb;
+  *smem = need;
+  return need <= 100 * 1024 && (C * 2) % 16 == 0;      // two CTAs per SM: all clusters of a batch of 32 resident at once (see above)
+}
+
+template <typename K, typename... Args>
+int gn_cluster_launch(K kernel, int B, int threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(GN_CL, B, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GN_CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (getenv("PT_GN_DEBUG")) {
+    int n = 0;
+    cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+    fprintf(stderr, "[groupnorm] cluster kernel: %d threads, %zu B smem, %d clusters of %d resident at once (B = %d)\n", threads, smem, n, GN_CL, B);
+  }
+  PT_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, args...));
+  PT_LAUNCH_CHECK();
+  return PT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers (C <= 2048).
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 8;
@@ -615,6 +848,24 @@ extern "C" int pt_groupnorm_apply(const void* x, const float* stats, const float
                                                                                                        (bf16*)y, L, C, G, g.rows_apply, act);
   PT_LAUNCH_CHECK();
   return PT_OK;
+}
+
+// statistics + normalisation (+ SiLU) in one call: the sample-resident cluster kernel when a sample fits, else the two streaming kernels
+extern "C" int pt_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int B, int L, int C, int G,
+                                float eps, int act, void* stream) {
+  PT_REQUIRE(B > 0 && L > 0 && G > 0 && C % G == 0, "groupnorm_fwd: B=%d L=%d C=%d G=%d", B, L, C, G);
+  GnGeom g;
+  if (int r = gn_geom(B, L, C, &g)) return r;
+  int rows, cb;
+  size_t smem;
+  if (gn_cluster_fit(L, C, G, g.threads, 1, &rows, &cb, &smem)) {
+    PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(gn_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    const int vec = ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    return gn_cluster_launch(gn_fwd_cluster_kernel, B, g.threads, smem, (cudaStream_t)stream, (const bf16*)x, gamma, beta, (bf16*)y, stats, L, C, G,
+                             rows, cb, eps, act, vec);
+  }
+  if (int r = pt_groupnorm_stats(x, stats, B, L, C, G, eps, stream)) return r;
+  return pt_groupnorm_apply(x, stats, gamma, beta, y, B, L, C, G, act, stream);
 }
 
 extern "C" int pt_groupnorm_bwd(const void* dy, const void* x, const float* stats, const float* gamma, const float* beta, const void* dx_add,

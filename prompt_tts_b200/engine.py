@@ -372,8 +372,8 @@ def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: 
 
 # ------------------------------------------------------------------------------------------------ norms
 def groupnorm(tape: Tape, x: Var, gamma: torch.Tensor, beta: torch.Tensor, eps: float, act: bool, groups: int = 32) -> Var:
-    stats = ops.groupnorm_stats(x.data, groups, eps)
-    y = Var(ops.groupnorm_apply(x.data, stats, gamma.detach(), beta.detach(), groups, act))
+    yd, stats = ops.groupnorm_fwd(x.data, gamma.detach(), beta.detach(), groups, eps, act)
+    y = Var(yd)
 
     def bwd():
         if y.grad is None:

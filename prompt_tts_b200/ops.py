@@ -117,6 +117,15 @@ def groupnorm_apply(x, stats, gamma, beta, G: int, act: bool) -> torch.Tensor:
     return y
 
 
+def groupnorm_fwd(x, gamma, beta, G: int, eps: float, act: bool):
+    """(y, stats): statistics and normalisation (+ SiLU) in one call -- one read of x when a sample fits in a cluster's shared memory."""
+    B, L, Cc = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty(B, G, 2, dtype=F32, device=x.device)
+    call("groupnorm_fwd", _p(x), _p(gamma), _p(beta), _p(y), _p(stats), B, L, Cc, G, eps, 1 if act else 0, _stream())
+    return y, stats
+
+
 def groupnorm_bwd(dy, x, stats, gamma, beta, dgamma, dbeta, G: int, act: bool, dx_add=None, out=None) -> torch.Tensor:
     """dx (+ dx_add: the gradient that already reached x through another branch, fused into the same pass; `out` may be dx_add)."""
     B, L, Cc = x.shape

@@ -20,16 +20,25 @@ def gen(seed=0):
     return torch.Generator(device="cuda").manual_seed(seed)
 
 
-@pytest.mark.parametrize("B,L,C,act", [(2, 50, 64, True), (3, 94, 320, True), (2, 188, 1920, False), (2, 33, 2560, True)])
-def test_groupnorm_fwd_bwd(cuda, B, L, C, act):
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("B,L,C,act", [(2, 50, 64, True), (3, 94, 320, True), (2, 188, 1920, False), (2, 33, 2560, True), (3, 752, 320, True),
+                                       (2, 752, 640, True), (2, 5, 64, True)])
+def test_groupnorm_fwd_bwd(cuda, B, L, C, act, fused):
+    """fused: pt_groupnorm_fwd (the sample-resident cluster kernel where a sample fits; 752 x 640 fits forward but not backward; L = 5
+    leaves three CTAs of a cluster without rows); else the streaming statistics + apply pair.  pt_groupnorm_bwd picks by itself."""
     from prompt_tts_b200 import ops
     g = gen(1)
     x = bf(torch.randn(B, L, C, device=cuda, generator=g) * 2 + 0.5)
     gamma = torch.randn(C, device=cuda, generator=g)
     beta = torch.randn(C, device=cuda, generator=g)
     dy = bf(torch.randn(B, L, C, device=cuda, generator=g))
-    stats = ops.groupnorm_stats(x, 32, 1e-5)
-    y = ops.groupnorm_apply(x, stats, gamma, beta, 32, act)
+    if fused:
+        y, stats = ops.groupnorm_fwd(x, gamma, beta, 32, 1e-5, act)
+        ref_stats = ops.groupnorm_stats(x, 32, 1e-5)
+        assert rel(stats, ref_stats) < 1e-4
+    else:
+        stats = ops.groupnorm_stats(x, 32, 1e-5)
+        y = ops.groupnorm_apply(x, stats, gamma, beta, 32, act)
     xr = x.float().transpose(1, 2).requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     yr = F.group_norm(xr, 32, gr, br, 1e-5)

@@ -30,6 +30,7 @@ for L, C in ((752, 320), (752, 640), (752, 960), (376, 640), (376, 1280), (376, 
     stats = ops.groupnorm_stats(x, 32, 1e-5)
     row(f"gn_stats   L={L} C={C}", t(lambda: ops.groupnorm_stats(x, 32, 1e-5)), n)
     row(f"gn_apply   L={L} C={C}", t(lambda: ops.groupnorm_apply(x, stats, gamma, beta, 32, True)), 2 * n)
+    row(f"gn_fwd     L={L} C={C} (one call)", t(lambda: ops.groupnorm_fwd(x, gamma, beta, 32, 1e-5, True)), 2 * n)
     row(f"gn_bwd     L={L} C={C} (reduce+apply)", t(lambda: ops.groupnorm_bwd(dy, x, stats, gamma, beta, dg, db, 32, True)), 5 * n)
     add = torch.randn_like(x)
     row(f"gn_bwd+add L={L} C={C} (reduce+apply)", t(lambda: ops.groupnorm_bwd(dy, x, stats, gamma, beta, dg, db, 32, True, dx_add=add, out=add)), 6 * n)

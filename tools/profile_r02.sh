@@ -4,10 +4,11 @@
 set -u
 O=gpurun_out/r02prof
 mkdir -p $O
-BENCH="python bench.py --no-graph --steps 2 --warmup 3 --no-cpu-baseline --no-sampling --no-rvq --no-full-step"
-# 1. launch list of one steady eager step of the bench workload (cold-cache, serialised: compare SHARES)
+BENCH="python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --no-sampling --no-rvq --no-full-step"
+# 1. launch list of the eager steps of the bench workload (cold-cache, serialised: compare SHARES); the summary keeps the last step
+#    (from the last add_noise kernel, which runs once per step, to the end)
 $BENCH > $O/bench_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 8300 -c 1750 --csv --log-file $O/launches_step.csv $BENCH > $O/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file $O/launches_all.csv $BENCH > $O/ncu_launches.log 2>&1
 echo "launch list rc=$?"
 # 2. full captures of the dominant kernels
 cap() {  # name, regex, skip, count, command...

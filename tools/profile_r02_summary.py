@@ -91,13 +91,18 @@ def main():
     _, t2 = summarise("rvq_rest", "RVQ: exhaustive exact-fp32 quantiser and the two embedding-sum kernels (32 clips x 900 / 512 clips x 900)")
     open(os.path.join(OUT, "r02_rvq_full_summary.txt"), "w").write(t1 + "\n" + t2)
     # launch list
+    la = os.path.join(SRC, "launches_all.csv")
     ll = os.path.join(SRC, "launches_step.csv")
+    if os.path.exists(la):      # keep the last step: from the last add_noise kernel (once per step) to the end
+        lines = [l for l in open(la) if not l.startswith("==")]
+        last = max(i for i, l in enumerate(lines) if "add_noise" in l)
+        open(ll, "w").writelines([lines[0]] + lines[last:])
     if os.path.exists(ll):
         lines = [l for l in open(ll) if not l.startswith("==")]
         open(os.path.join(OUT, "r02_launches_step.csv"), "w").writelines(lines)
         s = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), ll, "12"], capture_output=True, text=True).stdout
-        head = ("# ncu --metrics gpu__time_duration.sum --clock-control none -s 8300 -c 1750, `python bench.py --no-graph --steps 2 --warmup 3 "
-                "--no-cpu-baseline --no-sampling --no-rvq --no-full-step`: one steady eager train step of the bench workload, round-2 final build.\n"
+        head = ("# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --no-graph --steps 1 --warmup 3 "
+                "--no-cpu-baseline --no-sampling --no-rvq --no-full-step`: the last (steady) eager train step of the bench workload, round-2 final build.\n"
                 "# Per-launch times are cold-cache and serialised: compare SHARES with the in-graph figures of tools/step_profile.py.\n")
         open(os.path.join(OUT, "r02_launches_step_summary.txt"), "w").write(head + s)
     sm = os.path.join(SRC, "sass_mnemonics.txt")
