@@ -1,5 +1,5 @@
 """Per-warp event timeline of the fused attention kernels (development aid).  Needs a library built with -DPT_ATTN_TRACE
-(build the attention object with that define and link it with the other objects), loaded through PT_B200_LIB:
+(tools/build_trace.sh builds ab/libpt_trace.so), loaded through PT_B200_LIB:
     PT_B200_LIB=ab/libpt_trace.so python tools/attn_trace.py full_d40_self fwd|dq|dkv
 Prints, for CTA 0, the mean clocks between consecutive trace points per warp role (steady state) and one work item's raw timeline."""
 import collections

@@ -17,7 +17,8 @@ cap() {  # name, regex, skip, count, command...
   ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -o $O/$name "$@" > $O/${name}_ncu.log 2>&1
   echo "$name rc=$?"
 }
-cap gemm_pair_6016x1280x10240 gemm_kernel 2 1 python tools/gemm_one.py 6016 1280 10240 1 1 0 0 3
+cap gemm_pair_6016x1280x10240 gemm_kernel 2 1 python tools/gemm_one.py 6016 1280 10240 1 1 0 256 3
+cap gemm_auto_6016x1280x10240 gemm_kernel 2 1 python tools/gemm_one.py 6016 1280 10240 1 1 0 0 3
 cap gemm_shortk_24064x2560x320 gemm_kernel 2 1 python tools/gemm_one.py 24064 2560 320 1 1 0 0 3
 cap gemm_wgrad_1280x1280x6016 gemm_kernel 2 1 python tools/gemm_one.py 1280 1280 6016 0 0 2 0 3
 cap attn_d40_self attn_kernel 3 3 python tools/attn_one.py full_d40_self 2
