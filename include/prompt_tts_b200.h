@@ -100,7 +100,7 @@ typedef struct {
   int32_t M, N;            /* output tile space per (z2,z3) */
   int32_t nz2, nz3;        /* batch extents of the output tile space */
   int32_t splitk;          /* ignored (kept for ABI stability): PT_OUT_F32_ATOMIC_ADD outputs are scheduled stream-K by the library */
-  int32_t block_n;         /* 0 = auto; else 64 / 128 / 160 / 192 / 224 / 256; bit 0 set (e.g. 257) = never pair CTAs into multicast clusters */
+  int32_t block_n;         /* 0 = auto; else 64 / 96 (K-major B only) / 128 / 160 / 192 / 224 / 256; bit 0 set (e.g. 257) = never pair CTAs into multicast clusters */
   /* epilogue:  out = alpha * acc + bias[n] + bias_z2[z2, n] + residual[z2,z3,m,n] */
   void* out;
   int32_t out_dtype;
@@ -114,6 +114,11 @@ typedef struct {
   int64_t res_stride_m, res_stride_z2, res_stride_z3;
   int64_t bias_z2_stride;  /* elements; 0 means N */
   int64_t out_stride_n;    /* PT_OUT_F32_ATOMIC_ADD only: element stride between output columns; 0 means 1 */
+  int32_t out_transposed;  /* PT_OUT_BF16 only.  1: `out` and `residual` are indexed [z2, z3, n, m] -- the M index is the contiguous one and
+                            * out_stride_m / res_stride_m are the element strides of the N index -- and bias / bias_z2 are indexed by m.
+                            * This is how a convolution over few rows per sample runs with the WEIGHTS on the 128-row side of the tile:
+                            * M = C_out (a multiple of 128), N = L (tile width = L rounded up to 16: block_n 96 / 192 for 94 / 188 rows)
+                            * instead of 128-row tiles that are 27 % padding.  M and the strides must be multiples of 8. */
 } pt_gemm_t;
 
 int pt_gemm(const pt_gemm_t* g, void* stream);

@@ -30,7 +30,7 @@ class Gemm(C.Structure):
                 ("out_stride_m", C.c_int64), ("out_stride_z2", C.c_int64), ("out_stride_z3", C.c_int64),
                 ("alpha", C.c_float), ("bias", C.c_void_p), ("bias_z2", C.c_void_p), ("residual", C.c_void_p),
                 ("res_stride_m", C.c_int64), ("res_stride_z2", C.c_int64), ("res_stride_z3", C.c_int64),
-                ("bias_z2_stride", C.c_int64), ("out_stride_n", C.c_int64)]
+                ("bias_z2_stride", C.c_int64), ("out_stride_n", C.c_int64), ("out_transposed", C.c_int32)]
 
 
 class Attn(C.Structure):

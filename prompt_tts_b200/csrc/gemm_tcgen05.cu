@@ -59,6 +59,7 @@ struct alignas(64) KParams {
   long long rsm, rsz2, rsz3;
   long long bz2_stride;
   long long osn;
+  int out_t;            // bf16 output / residual indexed [z][n][m] (M contiguous), bias per row: see pt_gemm_t.out_transposed
   int vec_red;          // fp32 atomic output: rows are contiguous and 16-byte aligned -> red.global.add.v4.f32
 };
 
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(Cfg<BN, PAIR>::THREADS, Cfg<BN, PAIR>::CTAS_PE
       const int acc = segi & 1;
       // stage the per-column additive term (bias + per-batch time shift) in shared memory -- only when the column block (or the
       // batch element of a time shift) differs from what is already there: tiles are walked m-fastest, so this is rare
-      if (n0 != staged_n0 || (p.bias_z2 != nullptr && z2 != staged_z2)) {
+      if (!p.out_t && (n0 != staged_n0 || (p.bias_z2 != nullptr && z2 != staged_z2))) {
         asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");   // everyone is done with the previous contents
         const float* bz = p.bias_z2 ? p.bias_z2 + (long long)z2 * p.bz2_stride : nullptr;
         for (int j = et; j < BN; j += ET) {
@@ -437,6 +438,15 @@ __global__ void __launch_bounds__(Cfg<BN, PAIR>::THREADS, Cfg<BN, PAIR>::CTAS_PE
         uint32_t v[2][CH];
         bf16x8 rr[2][NIT];
         auto load_res = [&](int pass, bf16x8* dst) {
+          if (p.out_t) {      // staging tile = [32 columns n][32 rows m]: the residual is read along its contiguous m
+            const int mb = mw + cvec * 8;
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+              const int n = n0 + pass * CH + crow + i * RPI;
+              if (n < p.N && mb < p.M) dst[i] = ld16(p.res + zoff_r + (long long)n * p.rsm + mb);
+            }
+            return;
+          }
           const int nb = n0 + pass * CH + cvec * 8;
 #pragma unroll
           for (int i = 0; i < NIT; ++i) {
@@ -444,6 +454,11 @@ __global__ void __launch_bounds__(Cfg<BN, PAIR>::THREADS, Cfg<BN, PAIR>::CTAS_PE
             if (m < p.M && nb < p.N) dst[i] = ld16(p.res + zoff_r + (long long)m * p.rsm + nb);
           }
         };
+        float brow = 0.f;     // transposed output: the additive term belongs to this thread's row
+        if (p.out_t && mw + lane < p.M) {
+          if (p.bias) brow += __ldg(p.bias + mw + lane);
+          if (p.bias_z2) brow += __ldg(p.bias_z2 + (long long)z2 * p.bz2_stride + mw + lane);
+        }
         if (has_res && last_k >= 0) load_res(half, rr[0]);
         mbar_wait(tmem_full_bar(acc), full_parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -476,6 +491,25 @@ __global__ void __launch_bounds__(Cfg<BN, PAIR>::THREADS, Cfg<BN, PAIR>::CTAS_PE
 #pragma unroll
               for (int i = 0; i < NIT; ++i) st16(cell(crow + i * RPI, cvec), rr[k & 1][i]);
               __syncwarp();
+            }
+            if (p.out_t) {
+              // the tile leaves as [32 columns n][32 rows m] (m contiguous in memory): this thread owns column `lane` of every staging
+              // row -- 32 two-byte accesses instead of 4 sixteen-byte ones (consecutive lanes hit consecutive bf16: no bank conflicts)
+#pragma unroll
+              for (int j = 0; j < CH; ++j) {
+                bf16* cellp = reinterpret_cast<bf16*>(cell(j, lane >> 3)) + (lane & 7);
+                float f = fmaf(__uint_as_float(v[k & 1][j]), p.alpha, brow);
+                if (has_res) f += __bfloat162float(*cellp);
+                *cellp = __float2bfloat16_rn(f);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&p.tmO, smem_u32(stg), mw, nb, z2, z3);
+                tma_store_commit();
+              }
+              ++pc;
+              continue;
             }
             const float* sb = sbias + c * CH;
 #pragma unroll
@@ -666,7 +700,8 @@ int encode_output(CUtensorMap* tm, const pt_gemm_t* g) {
     return PT_ECUDA;
   }
   PT_REQUIRE((reinterpret_cast<uintptr_t>(g->out) & 15) == 0, "pt_gemm: bf16 output base not 16-byte aligned");
-  const long long ext[4] = {g->N, g->M, g->nz2, g->nz3};
+  // transposed output: the contiguous axis is M and out_stride_m is the stride of the N index
+  const long long ext[4] = {g->out_transposed ? g->M : g->N, g->out_transposed ? g->N : g->M, g->nz2, g->nz3};
   const long long str[4] = {1, g->out_stride_m, g->out_stride_z2, g->out_stride_z3};
   cuuint64_t dims[4], strides[3];
   for (int i = 0; i < 4; ++i) dims[i] = (cuuint64_t)ext[i];
@@ -739,9 +774,9 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   PT_REQUIRE(g->nz2 >= 1 && g->nz3 >= 1, "pt_gemm: bad batch extents");
   PT_REQUIRE(g->out != nullptr, "pt_gemm: null output");
   if (g->out_dtype == PT_OUT_BF16) {
-    PT_REQUIRE(g->N % 8 == 0 && g->out_stride_m % 8 == 0 && g->out_stride_z2 % 8 == 0 && g->out_stride_z3 % 8 == 0 &&
+    PT_REQUIRE((g->out_transposed ? g->M : g->N) % 8 == 0 && g->out_stride_m % 8 == 0 && g->out_stride_z2 % 8 == 0 && g->out_stride_z3 % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(g->out) & 15) == 0,
-               "pt_gemm: bf16 output needs N, strides multiples of 8 and a 16-byte aligned base (N=%d)", g->N);
+               "pt_gemm: bf16 output needs N (M if transposed), strides multiples of 8 and a 16-byte aligned base (M=%d N=%d)", g->M, g->N);
   } else if (g->out_dtype == PT_OUT_F32) {
     PT_REQUIRE(g->out_stride_m % 4 == 0 && g->out_stride_z2 % 4 == 0 && g->out_stride_z3 % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(g->out) & 15) == 0,
@@ -750,7 +785,7 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
     PT_REQUIRE(g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: out_dtype=%d", g->out_dtype);
   }
   if (g->residual) {
-    PT_REQUIRE(g->N % 8 == 0 && g->res_stride_m % 8 == 0 && g->res_stride_z2 % 8 == 0 && g->res_stride_z3 % 8 == 0 &&
+    PT_REQUIRE((g->out_transposed ? g->M : g->N) % 8 == 0 && g->res_stride_m % 8 == 0 && g->res_stride_z2 % 8 == 0 && g->res_stride_z3 % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(g->residual) & 15) == 0,
                "pt_gemm: residual alignment");
   }
@@ -833,12 +868,16 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
       }
     }
   }
-  PT_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 192 || bn == 224 || bn == 256, "pt_gemm: block_n=%d", bn);
+  PT_REQUIRE(bn == 64 || bn == 96 || bn == 128 || bn == 160 || bn == 192 || bn == 224 || bn == 256, "pt_gemm: block_n=%d", bn);
+  PT_REQUIRE(bn != 96 || kp.b_kmajor, "pt_gemm: block_n = 96 needs a K-major B operand");
+  PT_REQUIRE(!g->out_transposed || (g->out_dtype == PT_OUT_BF16 && g->M % 8 == 0), "pt_gemm: out_transposed needs a bf16 output and M %% 8 == 0 (M=%d)", g->M);
 
   // clusters of two CTAs (TMA multicast of the B tile) for the 256-wide tiles whenever there are two row tiles to pair
   // (measured: +1-3 % on the large data-parallel shapes, -4 % on stream-K ones, so only the former use it)
   // (a cluster of four sharing B in quarters was measured too: 24064 x 2560 x 320 67 -> 74 us, 6016 x 3840 x 1280 57 -> 64 us --
   // what limits the mainloop is each SM's own ingest rate, ~64 B/clk, which multicast does not change)
+  // (pairing along the BATCH axis for launches with one row tile per sample -- k=3 convolutions over <= 128 rows -- so that two samples
+  // share the weight tile was measured too: 56.3 vs 52.8 us at 32 x 94 x 1280 -> 1280, slower; profiles/r02_small_conv_probe.txt)
   const int mc = (bn == 256 && mt >= 2 && allow_cluster && !streamk) ? 2 : 1;
   // ... and those clusters run as tcgen05 CTA pairs (cta_group::2: one 256 x 256 tile per pair, each SM ingests 32 KB instead of
   // 48 KB per k-iteration) unless an odd, small number of row tiles would leave a quarter of a pair's work empty
@@ -900,6 +939,7 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   kp.rsz3 = g->res_stride_z3;
   kp.bz2_stride = g->bias_z2_stride ? g->bias_z2_stride : g->N;
   kp.osn = g->out_stride_n ? g->out_stride_n : 1;
+  kp.out_t = g->out_transposed ? 1 : 0;
   PT_REQUIRE(kp.osn == 1 || g->out_dtype == PT_OUT_F32_ATOMIC_ADD, "pt_gemm: out_stride_n needs PT_OUT_F32_ATOMIC_ADD");
   kp.vec_red = (g->out_dtype == PT_OUT_F32_ATOMIC_ADD && kp.osn == 1 && g->out_stride_m % 4 == 0 && g->out_stride_z2 % 4 == 0 &&
                 g->out_stride_z3 % 4 == 0 && (reinterpret_cast<uintptr_t>(g->out) & 15) == 0 && !getenv("PT_GEMM_SCALAR_RED"))
@@ -914,6 +954,7 @@ extern "C" int pt_gemm(const pt_gemm_t* g, void* stream) {
   g_last_tile = bn | (bn == 256 && mc == 1 ? 1 : 0);
   switch (bn) {
     case 64: return launch<64, 1>(kp, grid, st);
+    case 96: return launch<96, 1>(kp, grid, st);
     case 128: return launch<128, 1>(kp, grid, st);
     case 160: return launch<160, 1>(kp, grid, st);
     case 192: return launch<192, 1>(kp, grid, st);

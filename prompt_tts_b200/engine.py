@@ -300,6 +300,21 @@ class TimeShift:
         self.proj, self.dproj, self.offset = proj, dproj, offset
 
 
+CONV_SWAP = os.environ.get("PT_CONV_NO_SWAP") is None
+
+
+def _swap_tile(L: int, rows: int) -> int:
+    """Tile width for running a k=3 convolution with the WEIGHTS on the 128-row side of the tile (M = channels, N = L, transposed
+    output), or 0 to keep the rows of x there.  With at most 96 rows per sample (94 at level 3 of the bench model) a 128-row tile per
+    sample is 27 % zero padding; the channel count is a multiple of 128 and the tile width can be L rounded up to 64 / 96.
+    Measured (tools/conv_streamk_probe.py, B = 32): 49.3 vs 52.6 us at 94 x 1280 -> 1280, 90.6 vs 92.3 at 2560 -> 1280; at 188 rows
+    (tile width 192 vs two row tiles) the two forms tie, so those keep the rows of x on the rows; the step gains 0.25 ms."""
+    if not CONV_SWAP or rows % 128 != 0 or L > 96:
+        return 0
+    bn = 64 if L <= 64 else 96
+    return bn if L / bn > L / 128 + 0.08 else 0
+
+
 def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: int = 1,
           tshift: Optional[TimeShift] = None, residual: Optional[Var] = None) -> Var:
     """Conv1d(k=3, padding=1, stride 1|2) on channels-last x[B, L, Ci] as an implicit GEMM: three K segments whose
@@ -318,9 +333,17 @@ def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: 
         taps = [(1, -1), (0, 0), (1, 0)]                      # in row 2l-1 = odd[l-1], 2l = even[l], 2l+1 = odd[l]
     segs = [ops.segment(Ci, a_idx=ai, a_shift=sh, b_k0=t * Ci) for t, (ai, sh) in enumerate(taps)]
     bz2 = tshift.proj[:, tshift.offset:] if tshift is not None else None
-    ops.gemm(a_ops, [ops.operand(wp, True)], segs, Lo, Co, out, out_strides=(Co, Lo * Co, 0), nz2=B,
-             bias=bias.detach(), bias_z2=bz2, bias_z2_stride=tshift.proj.stride(0) if tshift is not None else 0,
-             residual=residual.data if residual is not None else None, res_strides=(Co, Lo * Co, 0))
+    sw = _swap_tile(L, Co) if stride == 1 else 0
+    if sw:
+        # weights on the rows: out^T[co, l] = sum_t W[co, t*Ci : (t+1)*Ci] . x[l + t - 1, :]
+        segs_w = [ops.segment(Ci, a_k0=t * Ci, b_shift=t - 1) for t in range(3)]
+        ops.gemm([ops.operand(wp, True)], a_ops, segs_w, Co, Lo, out, out_strides=(Co, Lo * Co, 0), nz2=B,
+                 bias=bias.detach(), bias_z2=bz2, bias_z2_stride=tshift.proj.stride(0) if tshift is not None else 0,
+                 residual=residual.data if residual is not None else None, res_strides=(Co, Lo * Co, 0), block_n=sw, out_transposed=True)
+    else:
+        ops.gemm(a_ops, [ops.operand(wp, True)], segs, Lo, Co, out, out_strides=(Co, Lo * Co, 0), nz2=B,
+                 bias=bias.detach(), bias_z2=bz2, bias_z2_stride=tshift.proj.stride(0) if tshift is not None else 0,
+                 residual=residual.data if residual is not None else None, res_strides=(Co, Lo * Co, 0))
     y = Var(out)
 
     def bwd():
@@ -350,9 +373,16 @@ def conv3(tape: Tape, x: Var, wparam: torch.Tensor, bias: torch.Tensor, stride: 
             if stride == 1:
                 own = x.grad is not None and x.owned
                 dx = x.grad if own else torch.empty_like(xd)
-                segs_dx = [ops.segment(Co, a_shift=1 - t, b_shift=t * Ci) for t in range(3)]
-                ops.gemm([dy_k], [wp_mn], segs_dx, L, Ci, dx, out_strides=(Ci, L * Ci, 0), nz2=B,
-                         residual=x.grad, res_strides=(Ci, L * Ci, 0))
+                swx = _swap_tile(L, Ci)
+                if swx:
+                    # dx^T[ci, l] = sum_t W[:, t*Ci + ci]^T . dy[l + 1 - t, :]: the weights (read transposed in place) on the rows
+                    segs_dx = [ops.segment(Co, a_shift=t * Ci, b_shift=1 - t) for t in range(3)]
+                    ops.gemm([wp_mn], [dy_k], segs_dx, Ci, L, dx, out_strides=(Ci, L * Ci, 0), nz2=B,
+                             residual=x.grad, res_strides=(Ci, L * Ci, 0), block_n=swx, out_transposed=True)
+                else:
+                    segs_dx = [ops.segment(Co, a_shift=1 - t, b_shift=t * Ci) for t in range(3)]
+                    ops.gemm([dy_k], [wp_mn], segs_dx, L, Ci, dx, out_strides=(Ci, L * Ci, 0), nz2=B,
+                             residual=x.grad, res_strides=(Ci, L * Ci, 0))
                 x.grad, x.owned = dx, True
             else:
                 dx = torch.empty_like(xd)

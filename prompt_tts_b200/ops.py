@@ -62,8 +62,9 @@ def gemm(a: Sequence[Operand], b: Sequence[Operand], segs: Sequence[Segment], M:
          out_strides=(None, 0, 0), out_mode: int = OUT_BF16, nz2: int = 1, nz3: int = 1, splitk: int = 1,
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, bias_z2: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, res_strides=(None, 0, 0), block_n: int = 0,
-         bias_z2_stride: int = 0, out_stride_n: int = 0) -> None:
-    """out[z2, z3, m, n] (element strides out_strides = (m, z2, z3)) = epilogue(sum over segments)."""
+         bias_z2_stride: int = 0, out_stride_n: int = 0, out_transposed: bool = False) -> None:
+    """out[z2, z3, m, n] (element strides out_strides = (m, z2, z3)) = epilogue(sum over segments).
+    out_transposed (bf16 only): out / residual are [z2, z3, n, m] (m contiguous, out_strides[0] = stride of n), bias / bias_z2 per m."""
     g = Gemm()
     for i, o in enumerate(a):
         g.a[i] = o
@@ -83,6 +84,7 @@ def gemm(a: Sequence[Operand], b: Sequence[Operand], segs: Sequence[Segment], M:
     g.out_stride_z2, g.out_stride_z3 = out_strides[1], out_strides[2]
     g.alpha = alpha
     g.out_stride_n = out_stride_n
+    g.out_transposed = 1 if out_transposed else 0
     if bias is not None:
         _need(bias, F32, "gemm bias")
         g.bias = bias.data_ptr()

@@ -151,3 +151,45 @@ def test_thin_conv_on_the_gemm_path(cuda, Ci, Co):
     assert rel(y.data.float().transpose(1, 2), yr) < 5e-3
     assert rel(tape.pgrads[id(w)], wr.grad) < 1e-4 and rel(tape.pgrads[id(b)], br.grad) < 1e-4
     assert rel(xv.grad.float().transpose(1, 2), xr.grad) < 5e-3
+
+
+@pytest.mark.parametrize("L,Ci,Co", [(94, 256, 384), (47, 128, 128), (64, 384, 256), (81, 128, 256)])
+def test_conv_with_the_weights_on_the_tile_rows(cuda, L, Ci, Co):
+    """Few rows per sample: engine.conv3 runs the convolution with M = channels, N = L and a transposed-output epilogue (tile width 96 or
+    64 here) instead of 128-row tiles that are mostly padding.  Forward with bias, per-sample shift and residual, data
+    gradient accumulated onto an existing gradient, weight and bias gradients -- against F.conv1d in fp32; and the two forms agree."""
+    from prompt_tts_b200 import engine as E
+    assert E._swap_tile(L, Co) and E._swap_tile(L, Ci)
+    g = torch.Generator(device="cuda").manual_seed(L)
+    Bn = 3
+    x = bf(torch.randn(Bn, L, Ci, device=cuda, generator=g))
+    w = (torch.randn(Co, Ci, 3, device=cuda, generator=g) * 0.1).requires_grad_(True)
+    b = torch.randn(Co, device=cuda, generator=g).requires_grad_(True)
+    res = bf(torch.randn(Bn, L, Co, device=cuda, generator=g))
+    dy = bf(torch.randn(Bn, L, Co, device=cuda, generator=g))
+    prev = bf(torch.randn(Bn, L, Ci, device=cuda, generator=g))
+    outs = []
+    for swap in (True, False):
+        E.CONV_SWAP = swap
+        try:
+            tape = E.Tape(E.PackCache())
+            xv, rv = E.Var(x), E.Var(res)
+            xv.grad, xv.owned = prev.clone(), True
+            y = E.conv3(tape, xv, w, b, residual=rv)
+            y.grad, y.owned = dy, True
+            tape.backward()
+            torch.cuda.synchronize()
+            outs.append((y.data.clone(), xv.grad.clone(), tape.pgrads[id(w)].clone(), tape.pgrads[id(b)].clone()))
+        finally:
+            E.CONV_SWAP = True
+    xr = x.float().transpose(1, 2).requires_grad_(True)
+    wr = bf(w.detach()).float().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yr = F.conv1d(xr, wr, br, padding=1) + res.float().transpose(1, 2)
+    yr.backward(dy.float().transpose(1, 2))
+    y_sw, dx_sw, dw_sw, db_sw = outs[0]
+    assert rel(y_sw.float().transpose(1, 2), yr) < 5e-3
+    assert rel(dx_sw.float().transpose(1, 2), xr.grad + prev.float().transpose(1, 2)) < 6e-3
+    assert rel(dw_sw, wr.grad) < 1e-4 and rel(db_sw, br.grad) < 1e-4
+    # same contraction order per output element in both forms: equal up to the bf16 rounding of identical fp32 sums
+    assert rel(y_sw, outs[1][0]) < 1e-5 and rel(dx_sw, outs[1][1]) < 1e-5
