@@ -4,11 +4,13 @@
 set -u
 O=gpurun_out/r02prof
 mkdir -p $O
-BENCH="python bench.py --no-graph --steps 1 --warmup 3 --no-cpu-baseline --no-sampling --no-rvq --no-full-step"
-# 1. launch list of the eager steps of the bench workload (cold-cache, serialised: compare SHARES); the summary keeps the last step
-#    (from the last add_noise kernel, which runs once per step, to the end)
+BENCH="python bench.py --no-graph --steps 2 --warmup 3 --no-cpu-baseline --no-sampling --no-rvq --no-full-step"
+# 1. launch list of the end of the eager run of the bench workload (cold-cache, serialised: compare SHARES).  Five steps launch ~7200
+#    kernels (1670 in the first, ~1382 in each of the others); the first 5500 are skipped and the summary keeps the last step: from the
+#    last add_noise kernel, which runs once per step, to the end.  (Either way ncu intercepts every launch: this pass takes ~17
+#    GPU-minutes on its own -- tools/profile_r02_launchlist.sh runs just it, tools/profile_r02_partial.sh just a few full captures.)
 $BENCH > $O/bench_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 30000 --csv --log-file $O/launches_all.csv $BENCH > $O/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 5500 -c 30000 --csv --log-file $O/launches_all.csv $BENCH > $O/ncu_launches.log 2>&1
 echo "launch list rc=$?"
 # 2. full captures of the dominant kernels
 cap() {  # name, regex, skip, count, command...

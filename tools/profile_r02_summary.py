@@ -101,7 +101,7 @@ def main():
         lines = [l for l in open(ll) if not l.startswith("==")]
         open(os.path.join(OUT, "r02_launches_step.csv"), "w").writelines(lines)
         s = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), ll, "12"], capture_output=True, text=True).stdout
-        head = ("# ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --no-graph --steps 1 --warmup 3 "
+        head = ("# ncu --metrics gpu__time_duration.sum --clock-control none -s 5500, `python bench.py --no-graph --steps 2 --warmup 3 "
                 "--no-cpu-baseline --no-sampling --no-rvq --no-full-step`: the last (steady) eager train step of the bench workload, round-2 final build.\n"
                 "# Per-launch times are cold-cache and serialised: compare SHARES with the in-graph figures of tools/step_profile.py.\n")
         open(os.path.join(OUT, "r02_launches_step_summary.txt"), "w").write(head + s)
