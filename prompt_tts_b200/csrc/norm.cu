@@ -451,23 +451,19 @@ __device__ __forceinline__ void gn_cluster_sum(const float* part, float* tot, in
   __syncthreads();
 }
 
-// shared memory: [chunk(s) of rows, bf16][threads * 16 floats reduction scratch][G * 2 partials][G * 2 statistics][mbarrier]
+// shared memory: [this CTA's rows, bf16][threads * 16 floats reduction scratch][G * 2 partials][G * 2 statistics]
 struct GnClSmem {
   uint8_t* x;
-  uint8_t* dy;
   float* red;
   float* part;
   float* stat;
-  uint32_t bar;
 };
-__device__ __forceinline__ GnClSmem gn_cl_carve(uint8_t* raw, int chunk_bytes, int nchunks, int threads, int G) {
+__device__ __forceinline__ GnClSmem gn_cl_carve(uint8_t* raw, int chunk_bytes, int threads, int G) {
   GnClSmem m;
   m.x = raw;
-  m.dy = raw + chunk_bytes;
-  m.red = reinterpret_cast<float*>(raw + (size_t)chunk_bytes * nchunks);
+  m.red = reinterpret_cast<float*>(raw + chunk_bytes);
   m.part = m.red + threads * 16;
   m.stat = m.part + 2 * G;
-  m.bar = gn_smem_u32(m.stat + 2 * G);
   return m;
 }
 // fold per-thread per-channel pairs (s[j], q[j]) over the rpp row phases into per-channel pairs red[c * 2 + {0, 1}]
@@ -495,7 +491,7 @@ __global__ void __launch_bounds__(320) gn_fwd_cluster_kernel(const bf16* __restr
                                                              int rows_per_cta, int chunk_bytes, float eps, int act, int vec) {
   extern __shared__ __align__(128) uint8_t gn_raw[];
   const GnMap m = gn_map(C);
-  const GnClSmem sm = gn_cl_carve(gn_raw, chunk_bytes, 1, m.threads, G);
+  const GnClSmem sm = gn_cl_carve(gn_raw, chunk_bytes, m.threads, G);
   const int rank = (int)gn_cluster_rank();
   const int b = blockIdx.y;
   const int r0 = rank * rows_per_cta;
@@ -573,13 +569,13 @@ __global__ void __launch_bounds__(320) gn_fwd_cluster_kernel(const bf16* __restr
   }
 }
 
-// rows per CTA, bytes of one resident chunk and the dynamic shared memory of the cluster kernels; false if the sample does not fit
-bool gn_cluster_fit(int L, int C, int G, int threads, int nchunks, int* rows_per_cta, int* chunk_bytes, size_t* smem) {
+// rows per CTA, bytes of its resident slice and the dynamic shared memory of the cluster kernel; false if the sample does not fit
+bool gn_cluster_fit(int L, int C, int G, int threads, int* rows_per_cta, int* chunk_bytes, size_t* smem) {
   static const bool off = getenv("PT_GN_NO_CLUSTER") != nullptr;
   if (off) return false;
   const int rows = (L + GN_CL - 1) / GN_CL;
   const int cb = (rows * C * 2 + 127) / 128 * 128;
-  const size_t need = (size_t)cb * nchunks + (size_t)threads * 16 * sizeof(float) + (size_t)4 * G * sizeof(float) + 16;
+  const size_t need = (size_t)cb + (size_t)threads * 16 * sizeof(float) + (size_t)4 * G * sizeof(float) + 16;
   *rows_per_cta = rows;
   *chunk_bytes = cb;
   *smem = need;
@@ -858,7 +854,7 @@ extern "C" int pt_groupnorm_fwd(const void* x, const float* gamma, const float* 
   if (int r = gn_geom(B, L, C, &g)) return r;
   int rows, cb;
   size_t smem;
-  if (gn_cluster_fit(L, C, G, g.threads, 1, &rows, &cb, &smem)) {
+  if (gn_cluster_fit(L, C, G, g.threads, &rows, &cb, &smem)) {
     PT_ONCE_PER_DEVICE(cudaFuncSetAttribute(gn_fwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     const int vec = ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
     return gn_cluster_launch(gn_fwd_cluster_kernel, B, g.threads, smem, (cudaStream_t)stream, (const bf16*)x, gamma, beta, (bf16*)y, stats, L, C, G,
