@@ -172,3 +172,21 @@ def test_flop_count_matches_the_survey():
     assert abs(3 * (text + unet) * 32 / 1e12 - 25.29) < 0.01                       # one train step at batch 32
     text2, unet2 = count_flops.forward_flops(model, 1504, 550)
     assert abs(unet2 / 1e9 - 428.0) < 0.1 and abs((text2 + 100 * unet2) / 1e12 - 42.84) < 0.01   # sampling, per utterance
+
+
+def test_conv_tile_choice_and_gemm_tile_table():
+    """Host logic that needs no GPU: which k=3 convolutions run with the weights on the tile rows (engine._swap_tile), and the
+    generated per-shape tile table the library compiles in is well-formed (10 integers per row, a supported tile width)."""
+    import re
+    from prompt_tts_b200 import engine as E
+    assert E._swap_tile(94, 1280) == 96 and E._swap_tile(47, 256) == 64 and E._swap_tile(64, 128) == 64
+    assert E._swap_tile(188, 1280) == 0           # two row tiles vs one 192-wide tile: a tie when measured, the old form stays
+    assert E._swap_tile(94, 320) == 0             # channel count not a multiple of 128
+    assert E._swap_tile(128, 1280) == 0 and E._swap_tile(752, 1280) == 0
+    path = os.path.join(ROOT, "prompt_tts_b200", "csrc", "gemm_tile_table.inc")
+    rows = [l for l in open(path) if l.strip().startswith("{")]
+    assert rows, "empty tile table"
+    for l in rows:
+        vals = [int(v) for v in re.match(r"\s*\{([^}]*)\}", l).group(1).split(",")]
+        assert len(vals) == 10 and vals[0] > 0 and vals[1] > 0 and vals[2] > 0
+        assert vals[9] in (64, 128, 160, 192, 224, 256, 257) and vals[5] in (0, 1) and vals[6] in (0, 1) and vals[7] in (0, 2)
