@@ -1,5 +1,5 @@
 #!/bin/bash
-# Builds libpt_b200.so (sm_100a only) in-tree.  nvcc cross-compiles without a GPU.
+# Builds libpt_b200.so and libpt_seanet.so (sm_100a only) in-tree.  nvcc cross-compiles without a GPU.
 set -e
 cd "$(dirname "$0")"
 SRC=prompt_tts_b200/csrc
@@ -20,3 +20,11 @@ done
 for p in $pids; do wait $p; done
 $NVCC -shared -o $OUT $objs -lcudart
 echo "built $OUT"
+# EnCodec SEANet layers (include/prompt_tts_seanet.h): a separate library, one translation unit
+SN=prompt_tts_b200/libpt_seanet.so
+so=build/seanet.o
+if [ ! -f $so ] || [ $SRC/seanet/seanet.cu -nt $so ] || [ $SRC/seanet/seanet_core.h -nt $so ] || [ include/prompt_tts_seanet.h -nt $so ]; then
+  $NVCC $FLAGS -Xcompiler -Wno-unknown-pragmas ${PTXAS_V:+-Xptxas -v} -c $SRC/seanet/seanet.cu -o $so
+fi
+$NVCC -shared -o $SN $so -lcudart
+echo "built $SN"

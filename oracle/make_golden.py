@@ -2,7 +2,7 @@
 shim of oracle/diffusers_shim first on sys.path) and the transformers restatement of encodec's RVQ.  Run in the build
 container only (the GPU box has no /root/reference):
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py            (or `... make_golden.py seanet` for the EnCodec SEANet vectors only)
 
 TEST INFRASTRUCTURE ONLY.  The vectors pin oracle/ref_model.py and oracle/rvq_oracle.c (tests/test_oracle.py)."""
 import json
@@ -87,9 +87,31 @@ def rvq(name, seed, B, T, grid):
     print("wrote rvq", name, codes.shape)
 
 
+def seanet():
+    """EnCodec SEANet encoder / decoder: transformers' EncodecModel (the installed restatement of encodec 0.1.1; the reference's
+    generate_code.py:48 / decode_codec.py:16 run encodec's modules) on the seeded weights of seanet_oracle.make_weights.
+    The weights are not stored (60 MB at full width): the tests rebuild them from the seed."""
+    import seanet_oracle as so
+    out = {}
+    for name, cfg, seed, B, S in (("tiny", so.CFG_TINY, 21, 2, 3203), ("k24", so.CFG_24KHZ, 22, 1, 3040)):
+        P = so.make_weights(cfg, seed)
+        m = so.to_transformers_model(P, cfg)
+        wav = (np.random.default_rng(seed).standard_normal((B, 1, S)) * 0.3).astype(np.float32)
+        with torch.no_grad():
+            lat = m.encoder(torch.from_numpy(wav)).numpy()
+            rec = m.decoder(torch.from_numpy(lat)).numpy()
+        out.update({f"{name}_seed": np.int64(seed), f"{name}_wav": wav, f"{name}_lat": lat, f"{name}_out": rec})
+        print("seanet", name, lat.shape, rec.shape)
+    np.savez_compressed(os.path.join(OUT, "seanet_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["seanet"]:
+        seanet()
+        sys.exit(0)
     denoiser("tiny", 2, 16, 0)
     denoiser("tiny3", 2, 32, 1)
     rvq("grid", 0, 3, 77, True)
     rvq("gauss", 1, 2, 150, False)
+    seanet()
