@@ -419,7 +419,12 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    rvq = samp = None
+    rvq = samp = codec_line = None
+    if not args.no_codec:
+        try:      # a side figure must never take the bench line down
+            codec_line = codec_throughput(dev, torch, rank, world, max_over_ranks)
+        except Exception as e:
+            codec_line = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if not args.no_rvq:
         rvq = rvq_throughput(dev, torch, ops, peaks_all.get("hbm_gbs", 6500.0), rank, world, max_over_ranks)
     if not args.no_sampling:
@@ -429,6 +434,8 @@ def run_ours(args):
             line["rvq"] = rvq
         if samp is not None:
             line["sampling"] = samp
+        if codec_line is not None:
+            line["codec"] = codec_line
         if world == 1 and not args.no_cpu_baseline:
             del stepper, opt, grad_sync
             model = None
@@ -458,6 +465,62 @@ def run_ours(args):
         threading.Timer(30.0, lambda: os._exit(0)).start()
         dist.destroy_process_group()
         os._exit(0)
+
+
+def codec_throughput(dev, torch, rank=0, world=1, max_over_ranks=lambda x: x, B=32, secs=12):
+    """EnCodec 24 kHz on the reference's data-preparation batch -- 32 clips zero-padded to 12 s
+    (generate_code.py:94-96) -> SEANet encoder -> 8-codebook RVQ codes (model.encode, generate_code.py:48), and codes -> embedding sum
+    -> SEANet decoder (model.decode, decode_codec.py:16).  Seeded random weights (no checkpoint offline); every rank runs the same
+    batch shape on its own clips (no collective); seconds of audio of all ranks / the slowest rank's device time.  fp32 on the FMA
+    pipe: 2.98 GFLOP per second of audio and stack against the measured FMA peak (profiles/r02_fp32_fma_peak.json)."""
+    import numpy as np
+    from prompt_tts_b200 import codec
+    model = codec.EncodecModel.encodec_model_24khz(pretrained=False, device=dev)
+    rng = np.random.default_rng(0)
+    sd = {}
+    for name, shape in {**model.encoder.param_shapes(), **model.decoder.param_shapes()}.items():
+        fan = float(np.prod(shape[1:])) if len(shape) > 1 else 1.0
+        sd[name] = torch.ones(shape) if name.endswith("original0") else \
+            torch.from_numpy((rng.standard_normal(shape) / np.sqrt(fan)).astype(np.float32))
+    for q in range(model.cfg["num_codebooks"]):
+        sd[f"quantizer.layers.{q}.codebook.embed"] = torch.from_numpy(rng.standard_normal((1024, 128)).astype(np.float32))
+    model.load_state_dict(sd)
+    model.set_target_bandwidth(6.0)
+    wav = torch.randn(B, 1, 24000 * secs, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)) * 0.3
+    lib = codec.seanet_lib()
+
+    def timed(fn):
+        out = fn()
+        torch.cuda.synchronize()
+        n0 = lib.pt_sn_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return out, e0.elapsed_time(e1) / 1e3, int(lib.pt_sn_launch_count() - n0)
+
+    frames, t_enc, l_enc = timed(lambda: model.encode(wav))
+    codes = frames[0][0]
+    out, t_dec, l_dec = timed(lambda: model.decode([(codes, None)]))
+    ok = tuple(codes.shape) == (B, 8, 75 * secs) and tuple(out.shape) == (B, 1, 24000 * secs) and bool(torch.isfinite(out).all().item())
+    t_enc, t_dec = max_over_ranks(t_enc), max_over_ranks(t_dec)
+    audio = B * secs * world
+    fma_peak = 72.5
+    try:
+        fma_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r02_fp32_fma_peak.json")))["fp32_fma_tflops"])
+    except Exception:
+        pass
+    gflop_per_s_audio = 2.9795
+    return {"workload": f"{B} clips x {secs} s of 24 kHz audio per GPU (generate_code.py batch), 6 kbps = 8 codebooks, seeded random weights",
+            "n_gpus": world, "encode_audio_s_per_s": audio / t_enc, "decode_audio_s_per_s": audio / t_dec,
+            "encode_ms": t_enc * 1e3, "decode_ms": t_dec * 1e3, "encode_seanet_launches": l_enc, "decode_seanet_launches": l_dec,
+            "encode_tflops": audio / t_enc * gflop_per_s_audio / 1e3, "decode_tflops": audio / t_dec * gflop_per_s_audio / 1e3,
+            "roofline": {"bound": "fp32 FMA pipe", "peak_tflops": fma_peak * world,
+                         "encode_frac": audio / t_enc * gflop_per_s_audio / 1e3 / (fma_peak * world),
+                         "decode_frac": audio / t_dec * gflop_per_s_audio / 1e3 / (fma_peak * world)},
+            "shapes_ok_and_finite": ok, "dtype": "f32",
+            "note": "parity against the oracle in tests/test_seanet_gpu.py; the encode time includes the RVQ quantiser, the decode time the embedding sum"}
 
 
 def sampling_rtf(model, cfg, dev, torch, peak_tflops, rank=0, world=1, max_over_ranks=lambda x: x):
@@ -664,6 +727,7 @@ def main():
     ap.add_argument("--no-sampling", action="store_true")
     ap.add_argument("--no-full-step", action="store_true")
     ap.add_argument("--no-rvq", action="store_true")
+    ap.add_argument("--no-codec", action="store_true")
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":

@@ -36,6 +36,7 @@ typedef struct {
   int B, Ci, Co, Lin, Lout, K, stride, dil;
   int pad_left;       /* conv: samples of padding in front of x[.., 0]; transposed conv: samples trimmed from the front */
   int reflect;        /* conv: 1 = reflect padding (F.pad 'reflect'), 0 = zeros */
+  int Co_pad;         /* packed entry points only: row length of the packed weights (Co rounded up to a multiple of 8 or 16) */
 } pt_sn_conv_t;
 
 /* EncodecConv1d.forward (ME:150-170; encodec modules/conv.py SConv1d): y[b, co, t] = bias[co] +
@@ -48,6 +49,14 @@ int pt_sn_conv1d(const pt_sn_conv_t* p, void* stream);
  * of which [pad_left, pad_left + Lout) is produced.  dil must be 1; `reflect` is ignored. */
 int pt_sn_conv_transpose1d(const pt_sn_conv_t* p, void* stream);
 
+/* Packed weights for the fast kernels: wp[(ci * K + k) * Co_pad + co] = w[co, ci, k] (conv) or w[ci, co, k] (transposed = 1), zero
+ * for co >= Co.  Co_pad must be a multiple of 8.  A thread's 8 / 16 output channels are then two / four 16-byte loads. */
+int pt_sn_pack_conv_weight(const float* w, float* wp, int Co, int Ci, int K, int Co_pad, int transposed, void* stream);
+/* Same contracts as pt_sn_conv1d / pt_sn_conv_transpose1d with p->w = packed weights and p->Co_pad set: 16 output channels per
+ * thread when Co_pad % 16 == 0, else 8; threads whose windows lie inside the signal run a loop without index checks. */
+int pt_sn_conv1d_packed(const pt_sn_conv_t* p, void* stream);
+int pt_sn_conv_transpose1d_packed(const pt_sn_conv_t* p, void* stream);
+
 /* LSTM (EncodecLSTM.forward ME:219-223 = nn.LSTM, gate order i, f, g, o, zero initial state, + skip connection).
  * Packed weights: wt4[k][j][q] = W[q * H + j][k] for W = weight_ih / weight_hh [4H, H]; bias4[j][q] = b_ih[q*H+j] + b_hh[q*H+j]. */
 int pt_sn_lstm_pack(const float* w, float* wt4, int H, void* stream);
@@ -59,6 +68,11 @@ int pt_sn_linear_rows(const float* a, const float* wt, const float* bias, float*
 /* One time step for all B sequences: gates = xg[t] + h[t-1] * W_hh (packed), c and hseq[t] updated.  xg [T, B, H, 4],
  * hseq [T, B, H], c [B, H] (read only when t > 0).  Steps must be launched in order on one stream. */
 int pt_sn_lstm_step(const float* xg, const float* whh_t4, float* hseq, float* c, int t, int B, int H, void* stream);
+/* All T steps of one layer in ONE cooperative launch: H / 4 blocks, each keeps the recurrent weights of its 4 hidden units in shared
+ * memory for the whole sequence, stages h[t-1] through shared memory and meets the other blocks at a grid-wide barrier per step.
+ * Same arguments and results as T calls of pt_sn_lstm_step.  Returns -3 (nothing launched) if the device cannot keep H / 4 blocks
+ * co-resident or has no cooperative launch: the caller then uses pt_sn_lstm_step. */
+int pt_sn_lstm_seq(const float* xg, const float* whh_t4, float* hseq, float* c, int T, int B, int H, void* stream);
 /* y[b, c, t] = hseq[t, b, c] + x[b, c, t] (the skip), written raw and / or through ELU */
 int pt_sn_tbc_add_to_ncl(const float* hseq, const float* x, float* y, float* y_elu, int B, int Cn, int T, void* stream);
 

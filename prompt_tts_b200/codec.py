@@ -41,7 +41,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("y", C.c_void_p),
                 ("y_elu", C.c_void_p),
                 ("B", C.c_int), ("Ci", C.c_int), ("Co", C.c_int), ("Lin", C.c_int), ("Lout", C.c_int), ("K", C.c_int),
-                ("stride", C.c_int), ("dil", C.c_int), ("pad_left", C.c_int), ("reflect", C.c_int)]
+                ("stride", C.c_int), ("dil", C.c_int), ("pad_left", C.c_int), ("reflect", C.c_int), ("Co_pad", C.c_int)]
 
 
 # argtypes of every entry point of include/prompt_tts_seanet.h (p = pointer, i = int); the trailing p is the stream
@@ -49,11 +49,15 @@ SIGS = {
     "weight_norm_fold": "pppiip",
     "conv1d": "pp",
     "conv_transpose1d": "pp",
+    "pack_conv_weight": "ppiiiiip",
+    "conv1d_packed": "pp",
+    "conv_transpose1d_packed": "pp",
     "lstm_pack": "ppip",
     "lstm_pack_bias": "pppip",
     "ncl_to_tbc": "ppiiip",
     "linear_rows": "ppppiiip",
     "lstm_step": "ppppiiip",
+    "lstm_seq": "ppppiiip",
     "tbc_add_to_ncl": "ppppiiip",
 }
 EXPORTS = ["pt_sn_version", "pt_sn_last_error", "pt_sn_launch_count"] + ["pt_sn_" + k for k in SIGS]
@@ -104,7 +108,9 @@ class CudaDriver:
         stream = C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
         rc = getattr(self.lib, "pt_sn_" + name)(*args, stream)
         if rc != 0:
-            raise PtError(f"pt_sn_{name}: rc={rc}: {self.lib.pt_sn_last_error().decode()}")
+            err = PtError(f"pt_sn_{name}: rc={rc}: {self.lib.pt_sn_last_error().decode()}")
+            err.rc = rc
+            raise err
 
 
 # --------------------------------------------------------------------------------------------------------------- layer plan
@@ -165,52 +171,78 @@ class SeanetStack:
     `_needs` works out which of the two the consumers read (a residual block reads its input both ways: ELU'd by its first
     convolution, raw by its shortcut)."""
 
-    def __init__(self, cfg, side: str, drv):
+    def __init__(self, cfg, side: str, drv, fast: Optional[bool] = None):
         self.cfg, self.side, self.drv = cfg, side, drv
+        # fast: packed-weight convolutions + the whole-sequence LSTM launch; PT_SN_LEGACY=1 selects the first-draft kernels
+        # (reference-layout weights, one launch per LSTM step), kept as the A/B partner and as the fallback of pt_sn_lstm_seq
+        self.fast = (os.environ.get("PT_SN_LEGACY", "0") != "1") if fast is None else fast
+        self.lstm_whole = self.fast and os.environ.get("PT_SN_LSTM_STEPS", "0") != "1"     # measurement switch: one launch per step
         self.plan = layer_plan(cfg)[side]
         self.causal = bool(cfg["use_causal_conv"])
         self.reflect = 1 if cfg["pad_mode"] == "reflect" else 0
         self.w: Dict[str, object] = {}
 
     # ---- preparation
-    def param_names(self) -> List[str]:
-        names = []
+    def param_shapes(self) -> Dict[str, Tuple[int, ...]]:
+        """state_dict name -> shape of every tensor this stack reads (transformers naming; weight norm: original0 = g, original1 = v)."""
+        out: Dict[str, Tuple[int, ...]] = {}
+
+        def conv(prefix, ci, co, k, transposed=False):
+            out[prefix + _G] = ((ci if transposed else co), 1, 1)
+            out[prefix + _V] = (ci, co, k) if transposed else (co, ci, k)
+            out[prefix + ".conv.bias"] = (co,)
+
         for idx, kind, s in self.plan:
             p = f"{self.side}.layers.{idx}"
             if kind in ("conv", "convtr"):
-                names += [p + _G, p + _V, p + ".conv.bias"]
+                conv(p, s["ci"], s["co"], s["k"], kind == "convtr")
             elif kind == "res":
-                subs = [".block.1", ".block.3"] + ([".shortcut"] if self.cfg["use_conv_shortcut"] else [])
-                for sub in subs:
-                    names += [p + sub + _G, p + sub + _V, p + sub + ".conv.bias"]
+                dim, hid = s["dim"], s["dim"] // self.cfg["compress"]
+                conv(p + ".block.1", dim, hid, self.cfg["residual_kernel_size"])
+                conv(p + ".block.3", hid, dim, 1)
+                if self.cfg["use_conv_shortcut"]:
+                    conv(p + ".shortcut", dim, dim, 1)
             else:
+                H = s["dim"]
                 for l in range(self.cfg["num_lstm_layers"]):
-                    names += [f"{p}.lstm.{n}_l{l}" for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-        return names
+                    out[f"{p}.lstm.weight_ih_l{l}"] = (4 * H, H)
+                    out[f"{p}.lstm.weight_hh_l{l}"] = (4 * H, H)
+                    out[f"{p}.lstm.bias_ih_l{l}"] = (4 * H,)
+                    out[f"{p}.lstm.bias_hh_l{l}"] = (4 * H,)
+        return out
+
+    def param_names(self) -> List[str]:
+        return list(self.param_shapes())
 
     def prepare(self, params: Dict[str, object]) -> None:
         """params: name -> device buffer with the state_dict's shape.  Folds g * v / |v| (pt_sn_weight_norm_fold) and packs the LSTM
         matrices gate-interleaved and transposed (pt_sn_lstm_pack)."""
         d = self.drv
 
-        def fold(prefix, rows, cols):
+        def fold(prefix, ci, co, k, transposed=False):
+            rows, cols = (ci, co * k) if transposed else (co, ci * k)
             w = d.empty(rows * cols)
             d.call("weight_norm_fold", d.ptr(params[prefix + _V]), d.ptr(params[prefix + _G]), d.ptr(w), rows, cols)
             self.w[prefix + ".w"] = w
             self.w[prefix + ".b"] = params[prefix + ".conv.bias"]
+            if self.fast:                       # [Ci, K, Co_pad]: a thread's output channels become 16-byte loads
+                cop = self.co_pad(co)
+                wp = d.empty(ci * k * cop)
+                d.call("pack_conv_weight", d.ptr(w), d.ptr(wp), co, ci, k, cop, 1 if transposed else 0)
+                self.w[prefix + ".wp"] = wp
 
         for idx, kind, s in self.plan:
             p = f"{self.side}.layers.{idx}"
             if kind == "conv":
-                fold(p, s["co"], s["ci"] * s["k"])
+                fold(p, s["ci"], s["co"], s["k"])
             elif kind == "convtr":
-                fold(p, s["ci"], s["co"] * s["k"])
+                fold(p, s["ci"], s["co"], s["k"], transposed=True)
             elif kind == "res":
                 dim, hid = s["dim"], s["dim"] // self.cfg["compress"]
-                fold(p + ".block.1", hid, dim * self.cfg["residual_kernel_size"])
-                fold(p + ".block.3", dim, hid)
+                fold(p + ".block.1", dim, hid, self.cfg["residual_kernel_size"])
+                fold(p + ".block.3", hid, dim, 1)
                 if self.cfg["use_conv_shortcut"]:
-                    fold(p + ".shortcut", dim, dim)
+                    fold(p + ".shortcut", dim, dim, 1)
             else:
                 H = s["dim"]
                 if H % 4:
@@ -223,6 +255,11 @@ class SeanetStack:
                     b4 = d.empty(H * 4)
                     d.call("lstm_pack_bias", d.ptr(params[f"{p}.lstm.bias_ih_l{l}"]), d.ptr(params[f"{p}.lstm.bias_hh_l{l}"]), d.ptr(b4), H)
                     self.w[f"{p}.bias_l{l}"] = b4
+
+    @staticmethod
+    def co_pad(co: int) -> int:
+        """Row length of the packed weights: 16 output channels per thread from 9 channels up, else 8."""
+        return 8 if co <= 8 else -(-co // 16) * 16
 
     # ---- which forms of a layer's output are read
     def _needs(self, pos: int) -> Tuple[bool, bool]:
@@ -251,9 +288,15 @@ class SeanetStack:
             Lout = -(-L // stride)                                                                      # ME:125-133: extra right padding
         y = d.empty(B, co, Lout) if raw else None
         ye = d.empty(B, co, Lout) if elu else None
-        desc = ConvDesc(d.ptr(x), d.ptr(self.w[prefix + ".w"]), d.ptr(self.w[prefix + ".b"]), d.ptr(res), d.ptr(y), d.ptr(ye),
-                        B, ci, co, L, Lout, k, stride, dil, pad_left, self.reflect)
-        d.call("conv_transpose1d" if transposed else "conv1d", C.addressof(desc))
+        name = "conv_transpose1d" if transposed else "conv1d"
+        if self.fast:
+            desc = ConvDesc(d.ptr(x), d.ptr(self.w[prefix + ".wp"]), d.ptr(self.w[prefix + ".b"]), d.ptr(res), d.ptr(y), d.ptr(ye),
+                            B, ci, co, L, Lout, k, stride, dil, pad_left, self.reflect, self.co_pad(co))
+            name += "_packed"
+        else:
+            desc = ConvDesc(d.ptr(x), d.ptr(self.w[prefix + ".w"]), d.ptr(self.w[prefix + ".b"]), d.ptr(res), d.ptr(y), d.ptr(ye),
+                            B, ci, co, L, Lout, k, stride, dil, pad_left, self.reflect, 0)
+        d.call(name, C.addressof(desc))
         return y, ye, Lout
 
     def _res(self, prefix, x, xe, B, dim, L, dil, raw, elu):
@@ -277,8 +320,17 @@ class SeanetStack:
                    T * B, H, 4 * H)
             hseq, c = d.empty(T, B, H), d.empty(B, H)
             whh = d.ptr(self.w[f"{prefix}.weight_hh_l{l}"])
-            for t in range(T):
-                d.call("lstm_step", d.ptr(xg), whh, d.ptr(hseq), d.ptr(c), t, B, H)
+            whole = self.lstm_whole
+            if whole:
+                try:                                  # all T steps in one cooperative launch
+                    d.call("lstm_seq", d.ptr(xg), whh, d.ptr(hseq), d.ptr(c), T, B, H)
+                except PtError as e:
+                    if getattr(e, "rc", 0) != -3:     # -3: the blocks cannot be co-resident on this device -> one launch per step
+                        raise
+                    whole = False
+            if not whole:
+                for t in range(T):
+                    d.call("lstm_step", d.ptr(xg), whh, d.ptr(hseq), d.ptr(c), t, B, H)
             inp = hseq
         y = d.empty(B, H, T) if raw else None
         ye = d.empty(B, H, T) if elu else None
@@ -354,10 +406,13 @@ class EncodecModel:
     def load_state_dict(self, state_dict) -> None:
         """Accepts the key dialects of encodec 0.1.1 and of transformers' EncodecModel (see `normalise_key`)."""
         sd = {normalise_key(k): v for k, v in state_dict.items()}
-        need = self.encoder.param_names() + self.decoder.param_names()
+        need = {**self.encoder.param_shapes(), **self.decoder.param_shapes()}
         missing = [k for k in need if k not in sd]
         if missing:
             raise KeyError(f"state_dict is missing {len(missing)} SEANet tensors, e.g. {missing[:3]}")
+        wrong = [(k, tuple(sd[k].shape), shp) for k, shp in need.items() if tuple(sd[k].shape) != shp]
+        if wrong:
+            raise ValueError(f"state_dict shapes do not match the 24 kHz SEANet, e.g. {wrong[:2]}")
         self._params = {k: self.drv.upload(sd[k]) for k in need}
         self.encoder.prepare(self._params)
         self.decoder.prepare(self._params)

@@ -3,6 +3,7 @@
 // fp32 on the FMA pipe, the reference's [B, C, T] layout: these stacks feed the RVQ quantiser, whose codes flip on rounding noise, so
 // the first correct path keeps the reference's precision.  The kernel bodies are in seanet_core.h (shared with the host-side
 // index checker of the CPU test tier); this file is the __global__ wrappers, argument validation and launches.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -64,6 +65,39 @@ __global__ void __launch_bounds__(SN_THREADS)
   sn_lstm_step_thread(xg, whh_t4, hseq, c, t, B, H, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
 }
 
+template <int CT>
+__global__ void __launch_bounds__(SN_THREADS) sn_conv1d_packed_kernel(const pt_sn_conv_t p) {
+  sn_conv1d_packed_thread<CT>(p, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, blockDim.x);
+}
+__global__ void __launch_bounds__(SN_THREADS) sn_convtr_packed_kernel(const pt_sn_conv_t p) {
+  sn_convtr_packed_thread(p, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, blockDim.x);
+}
+__global__ void __launch_bounds__(SN_THREADS)
+    sn_pack_conv_weight_kernel(const float* w, float* wp, int Co, int Ci, int K, int Cop, int transposed) {
+  sn_pack_conv_weight_thread(w, wp, Co, Ci, K, Cop, transposed, blockIdx.x, threadIdx.x, blockDim.x);
+}
+
+// One layer of the LSTM over all T steps: H / SN_PU co-resident blocks (cooperative launch), one grid-wide barrier per step.
+__global__ void __launch_bounds__(32 * SN_PU)
+    sn_lstm_seq_kernel(const float* xg, const float* whh_t4, float* hseq, float* c, int T, int B, int H) {
+  extern __shared__ __align__(16) float sn_smem[];
+  float* wsm = sn_smem;                           // [SN_PU][H][4]
+  float* hs = sn_smem + (size_t)SN_PU * H * 4;    // [32][H + 4]
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  sn_lstm_seq_load_w(whh_t4, wsm, H, blockIdx.x, threadIdx.x, blockDim.x);
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    for (int b0 = 0; b0 < B; b0 += 32) {
+      const int nb = B - b0 < 32 ? B - b0 : 32;
+      if (t > 0) sn_lstm_seq_stage(hseq, hs, t, b0, nb, B, H, threadIdx.x, blockDim.x);
+      __syncthreads();
+      sn_lstm_seq_compute(xg, wsm, hs, hseq, c, t, b0, nb, B, H, blockIdx.x, threadIdx.x);
+      __syncthreads();  // hs is overwritten by the next chunk / step
+    }
+    if (t + 1 < T) grid.sync();  // h[t] of every block is visible before anyone stages it
+  }
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int check_conv_common(const pt_sn_conv_t* p, const char* what) {
@@ -117,6 +151,76 @@ int pt_sn_conv_transpose1d(const pt_sn_conv_t* p, void* stream) {
   if (g.y > 65535) return fail(-1, "conv_transpose1d: Co * stride too large");
   sn_convtr_kernel<<<to_dim3(g), SN_THREADS, 0, (cudaStream_t)stream>>>(*p);
   return launched("conv_transpose1d");
+}
+
+int pt_sn_pack_conv_weight(const float* w, float* wp, int Co, int Ci, int K, int Co_pad, int transposed, void* stream) {
+  if (!w || !wp || Co <= 0 || Ci <= 0 || K <= 0 || Co_pad < Co || Co_pad % 8) return fail(-1, "pack_conv_weight: bad arguments");
+  sn_pack_conv_weight_kernel<<<to_dim3(sn_linear_grid_1d((long long)Ci * K * Co_pad)), SN_THREADS, 0, (cudaStream_t)stream>>>(
+      w, wp, Co, Ci, K, Co_pad, transposed);
+  return launched("pack_conv_weight");
+}
+
+static int check_packed(const pt_sn_conv_t* p, const char* what) {
+  if (p->Co_pad < p->Co || p->Co_pad % 8) return fail(-1, "%s: Co_pad=%d must be a multiple of 8 that is >= Co=%d", what, p->Co_pad, p->Co);
+  if (!aligned16(p->w)) return fail(-1, "%s: packed weights must be 16-byte aligned", what);
+  return 0;
+}
+
+int pt_sn_conv1d_packed(const pt_sn_conv_t* p, void* stream) {
+  if (int r = check_conv_common(p, "conv1d_packed")) return r;
+  if (int r = check_packed(p, "conv1d_packed")) return r;
+  const long long last = (long long)(p->Lout - 1) * p->stride + (long long)(p->K - 1) * p->dil - p->pad_left;
+  if (p->reflect && (p->pad_left > p->Lin - 1 || last > 2LL * (p->Lin - 1)))
+    return fail(-1, "conv1d_packed: input of length %d is shorter than its reflect padding (%d in front, %lld behind)", p->Lin,
+                p->pad_left, last - (p->Lin - 1));
+  if (sn_conv1d_packed_ct(*p) == 16) {
+    const sn_grid g = sn_conv1d_packed_grid<16>(*p);
+    if (g.y > 65535) return fail(-1, "conv1d_packed: Co=%d too large", p->Co);
+    sn_conv1d_packed_kernel<16><<<to_dim3(g), SN_THREADS, 0, (cudaStream_t)stream>>>(*p);
+  } else {
+    const sn_grid g = sn_conv1d_packed_grid<8>(*p);
+    if (g.y > 65535) return fail(-1, "conv1d_packed: Co=%d too large", p->Co);
+    sn_conv1d_packed_kernel<8><<<to_dim3(g), SN_THREADS, 0, (cudaStream_t)stream>>>(*p);
+  }
+  return launched("conv1d_packed");
+}
+
+int pt_sn_conv_transpose1d_packed(const pt_sn_conv_t* p, void* stream) {
+  if (int r = check_conv_common(p, "conv_transpose1d_packed")) return r;
+  if (int r = check_packed(p, "conv_transpose1d_packed")) return r;
+  if (p->dil != 1) return fail(-1, "conv_transpose1d_packed: dilation %d is not supported", p->dil);
+  const long long full = (long long)(p->Lin - 1) * p->stride + p->K;
+  if ((long long)p->pad_left + p->Lout > full)
+    return fail(-1, "conv_transpose1d_packed: window [%d, %lld) exceeds the full output length %lld", p->pad_left,
+                (long long)p->pad_left + p->Lout, full);
+  const sn_grid g = sn_convtr_packed_grid(*p);
+  if (g.y > 65535) return fail(-1, "conv_transpose1d_packed: Co * stride too large");
+  sn_convtr_packed_kernel<<<to_dim3(g), SN_THREADS, 0, (cudaStream_t)stream>>>(*p);
+  return launched("conv_transpose1d_packed");
+}
+
+int pt_sn_lstm_seq(const float* xg, const float* whh_t4, float* hseq, float* c, int T, int B, int H, void* stream) {
+  if (!xg || !whh_t4 || !hseq || !c || T <= 0 || B <= 0 || H <= 0) return fail(-1, "lstm_seq: bad arguments");
+  if (H % SN_PU || H % 4) return fail(-1, "lstm_seq: H=%d must be a multiple of %d", H, SN_PU);
+  if (!aligned16(xg) || !aligned16(whh_t4) || !aligned16(hseq)) return fail(-1, "lstm_seq: pointers must be 16-byte aligned");
+  int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(-2, "lstm_seq: cudaGetDevice failed");
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!coop) return fail(-3, "lstm_seq: the device has no cooperative launch");
+  const size_t smem = sn_lstm_seq_smem_floats(H) * sizeof(float);
+  if (smem > 227 * 1024) return fail(-3, "lstm_seq: H=%d needs %zu bytes of shared memory", H, smem);
+  cudaError_t e = cudaFuncSetAttribute(sn_lstm_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(-3, "lstm_seq: shared memory opt-in failed: %s", cudaGetErrorString(e));
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sn_lstm_seq_kernel, 32 * SN_PU, smem);
+  const int blocks = H / SN_PU;
+  if (e != cudaSuccess || per_sm * sms < blocks)
+    return fail(-3, "lstm_seq: %d blocks cannot be co-resident (%d per SM x %d SMs)", blocks, per_sm, sms);
+  void* args[] = {(void*)&xg, (void*)&whh_t4, (void*)&hseq, (void*)&c, (void*)&T, (void*)&B, (void*)&H};
+  e = cudaLaunchCooperativeKernel((const void*)sn_lstm_seq_kernel, dim3(blocks), dim3(32 * SN_PU), args, smem, (cudaStream_t)stream);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail(-2, "lstm_seq: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int pt_sn_lstm_pack(const float* w, float* wt4, int H, void* stream) {

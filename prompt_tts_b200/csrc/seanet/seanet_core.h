@@ -43,6 +43,25 @@ SN_HD sn_f4 sn_ld4(const float* p) {
 }
 #endif
 
+// 16-byte loads / stores of ordinary (here: shared) memory
+SN_HD sn_f4 sn_ldv4(const float* p) {
+  sn_f4 r;
+#if defined(__CUDA_ARCH__)
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+#else
+  r.v[0] = p[0]; r.v[1] = p[1]; r.v[2] = p[2]; r.v[3] = p[3];
+#endif
+  return r;
+}
+SN_HD void sn_stv4(float* p, const sn_f4& v) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<float4*>(p) = make_float4(v.v[0], v.v[1], v.v[2], v.v[3]);
+#else
+  p[0] = v.v[0]; p[1] = v.v[1]; p[2] = v.v[2]; p[3] = v.v[3];
+#endif
+}
+
 SN_HD float sn_elu(float v) { return v > 0.f ? v : expm1f(v); }
 SN_HD float sn_sigmoid(float v) { return 1.f / (1.f + expf(-v)); }
 SN_HD unsigned sn_cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
@@ -354,4 +373,261 @@ SN_HD void sn_lstm_step_thread(const float* xg, const float* whh_t4, float* hseq
     c[o] = cn;
     hseq[(size_t)t * B * H + o] = sn_sigmoid(acc[r][3]) * tanhf(cn);
   }
+}
+
+// ================================================================================================ packed-weight kernels
+// wp[(ci * K + k) * Cop + co]: a thread's output channels are consecutive floats, read as 16-byte loads that are the same for the
+// whole warp; rows are zero-filled up to Cop, so the inner loops carry no channel predicate.
+SN_HD void sn_pack_conv_weight_thread(const float* w, float* wp, int Co, int Ci, int K, int Cop, int transposed, int bx, int tx,
+                                      int ntx) {
+  const long long o = (long long)bx * ntx + tx;
+  if (o >= (long long)Ci * K * Cop) return;
+  const int co = (int)(o % Cop);
+  const int k = (int)((o / Cop) % K);
+  const int ci = (int)(o / ((long long)Cop * K));
+  float v = 0.f;
+  if (co < Co) v = transposed ? SN_LD(w + ((size_t)ci * Co + co) * K + k) : SN_LD(w + ((size_t)co * Ci + ci) * K + k);
+  wp[o] = v;
+}
+
+SN_HD int sn_conv1d_packed_ct(const pt_sn_conv_t& p) { return p.Co_pad % 16 == 0 ? 16 : 8; }  // output channels per thread
+
+template <int CT>
+SN_HD sn_grid sn_conv1d_packed_grid(const pt_sn_conv_t& p) {
+  sn_grid g;
+  g.x = sn_cdiv(p.Lout, SN_THREADS * SN_TT);
+  g.y = (unsigned)(p.Co_pad / CT);
+  g.z = (unsigned)p.B;
+  return g;
+}
+
+template <int CT>
+SN_HD void sn_conv1d_packed_thread(const pt_sn_conv_t& p, int bx, int by, int bz, int tx, int ntx) {
+  const int co0 = by * CT;
+  const int t0 = bx * ntx * SN_TT + tx;
+  const int Cop = p.Co_pad;
+  float acc[CT][SN_TT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+#pragma unroll
+    for (int j = 0; j < SN_TT; ++j) acc[c][j] = 0.f;
+  int q0[SN_TT];
+  bool interior = true;  // every tap of every sample of this thread lies inside the signal
+#pragma unroll
+  for (int j = 0; j < SN_TT; ++j) {
+    const int t = t0 + j * ntx;
+    q0[j] = t * p.stride - p.pad_left;
+    interior = interior && t < p.Lout && q0[j] >= 0 && q0[j] + (p.K - 1) * p.dil < p.Lin;
+  }
+  const float* xb = p.x + (size_t)bz * p.Ci * p.Lin;
+  const float* wb = p.w + co0;
+  if (interior) {
+    for (int ci = 0; ci < p.Ci; ++ci) {
+      const float* xc = xb + (size_t)ci * p.Lin;
+      const float* wc = wb + (size_t)ci * p.K * Cop;
+      for (int k = 0; k < p.K; ++k) {
+        float wv[CT];
+#pragma unroll
+        for (int c4 = 0; c4 < CT / 4; ++c4) {
+          const sn_f4 w4 = sn_ld4(wc + (size_t)k * Cop + c4 * 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) wv[c4 * 4 + q] = w4.v[q];
+        }
+        const int off = k * p.dil;
+#pragma unroll
+        for (int j = 0; j < SN_TT; ++j) {
+          const float xv = SN_LD(xc + q0[j] + off);
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[c][j] = fmaf(wv[c], xv, acc[c][j]);
+        }
+      }
+    }
+  } else {
+    const int last = p.Lin - 1;
+    for (int ci = 0; ci < p.Ci; ++ci) {
+      const float* xc = xb + (size_t)ci * p.Lin;
+      const float* wc = wb + (size_t)ci * p.K * Cop;
+      for (int k = 0; k < p.K; ++k) {
+        float wv[CT];
+#pragma unroll
+        for (int c4 = 0; c4 < CT / 4; ++c4) {
+          const sn_f4 w4 = sn_ld4(wc + (size_t)k * Cop + c4 * 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) wv[c4 * 4 + q] = w4.v[q];
+        }
+#pragma unroll
+        for (int j = 0; j < SN_TT; ++j) {
+          // branch-free form of sn_src_index: mirror, clamp so the load is always legal, then select
+          const int q = q0[j] + k * p.dil;
+          const bool inside = q >= 0 && q <= last;
+          int s = q < 0 ? -q : q;
+          s = s > last ? 2 * last - s : s;
+          s = s < 0 ? 0 : (s > last ? last : s);
+          const bool use = (t0 + j * ntx < p.Lout) && (inside || p.reflect != 0);
+          const float xl = SN_LD(xc + s);
+          const float xv = use ? xl : 0.f;
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[c][j] = fmaf(wv[c], xv, acc[c][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    const int co = co0 + c;
+    if (co >= p.Co) continue;
+    const float bv = p.bias ? SN_LD(p.bias + co) : 0.f;
+#pragma unroll
+    for (int j = 0; j < SN_TT; ++j) {
+      const int t = t0 + j * ntx;
+      if (t >= p.Lout) continue;
+      const size_t o = ((size_t)bz * p.Co + co) * p.Lout + t;
+      float v = acc[c][j] + bv;
+      if (p.res) v += SN_LD(p.res + o);
+      if (p.y) p.y[o] = v;
+      if (p.y_elu) p.y_elu[o] = sn_elu(v);
+    }
+  }
+}
+
+// transposed convolution, packed weights: SN_UT frames x SN_UR phases x SN_PC channels per thread
+constexpr int SN_PC = 8;
+
+SN_HD sn_grid sn_convtr_packed_grid(const pt_sn_conv_t& p) {
+  sn_grid g;
+  g.x = sn_cdiv(sn_convtr_frames(p), SN_THREADS * SN_UT);
+  g.y = (unsigned)sn_convtr_phase_groups(p) * (unsigned)(p.Co_pad / SN_PC);
+  g.z = (unsigned)p.B;
+  return g;
+}
+
+SN_HD void sn_convtr_packed_thread(const pt_sn_conv_t& p, int bx, int by, int bz, int tx, int ntx) {
+  const int npg = sn_convtr_phase_groups(p);
+  const int r0 = (by % npg) * SN_UR;
+  const int co0 = (by / npg) * SN_PC;
+  const int i0 = bx * ntx * SN_UT + tx;
+  const int taps = (p.K + p.stride - 1) / p.stride;
+  const int Cop = p.Co_pad;
+  const int last = p.Lin - 1;
+  float acc[SN_UT][SN_UR][SN_PC];
+#pragma unroll
+  for (int j = 0; j < SN_UT; ++j)
+#pragma unroll
+    for (int r = 0; r < SN_UR; ++r)
+#pragma unroll
+      for (int c = 0; c < SN_PC; ++c) acc[j][r][c] = 0.f;
+  const float* xb = p.x + (size_t)bz * p.Ci * p.Lin;
+  for (int ci = 0; ci < p.Ci; ++ci) {
+    const float* xc = xb + (size_t)ci * p.Lin;
+    const float* wc = p.w + (size_t)ci * p.K * Cop + co0;
+    for (int m = 0; m < taps; ++m) {
+      float xv[SN_UT];
+#pragma unroll
+      for (int j = 0; j < SN_UT; ++j) {
+        const int s = i0 + j * ntx - m;
+        const int sc = s < 0 ? 0 : (s > last ? last : s);
+        const float xl = SN_LD(xc + sc);
+        xv[j] = (s >= 0 && s <= last) ? xl : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < SN_UR; ++r) {
+        const int k = r0 + r + m * p.stride;
+        if (r0 + r >= p.stride || k >= p.K) continue;  // warp-uniform
+#pragma unroll
+        for (int c4 = 0; c4 < SN_PC / 4; ++c4) {
+          const sn_f4 w4 = sn_ld4(wc + (size_t)k * Cop + c4 * 4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < SN_UT; ++j) acc[j][r][c4 * 4 + q] = fmaf(xv[j], w4.v[q], acc[j][r][c4 * 4 + q]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < SN_PC; ++c) {
+    const int co = co0 + c;
+    if (co >= p.Co) continue;
+    const float bv = p.bias ? SN_LD(p.bias + co) : 0.f;
+#pragma unroll
+    for (int j = 0; j < SN_UT; ++j)
+#pragma unroll
+      for (int r = 0; r < SN_UR; ++r) {
+        if (r0 + r >= p.stride) continue;
+        const long long t = (long long)(i0 + j * ntx) * p.stride + r0 + r - p.pad_left;
+        if (t < 0 || t >= p.Lout) continue;
+        const size_t o = ((size_t)bz * p.Co + co) * p.Lout + (size_t)t;
+        float v = acc[j][r][c] + bv;
+        if (p.res) v += SN_LD(p.res + o);
+        if (p.y) p.y[o] = v;
+        if (p.y_elu) p.y_elu[o] = sn_elu(v);
+      }
+  }
+}
+
+// ================================================================================================ LSTM, whole sequence in one launch
+// Block bx owns SN_PU hidden units for all sequences and all steps: warp u = unit bx * SN_PU + u, lane = sequence within a chunk
+// of 32.  Per block in shared memory: the units' recurrent weights wsm[u][k][gate] (loaded once) and the previous hidden state of
+// the current chunk hs[32][H + 4] (rows padded by 4 floats: the 16-byte reads of a quarter-warp fall into distinct banks).
+// The three pieces below are separated by barriers in the kernel (block barrier after load / stage / compute, grid barrier per
+// step); the host-side checker calls them in the same order.
+constexpr int SN_PU = 4;
+#if defined(__CUDA_ARCH__)
+#define SN_LD4_CG(p, r)                                            \
+  {                                                                \
+    const float4 t_ = __ldcg(reinterpret_cast<const float4*>(p)); \
+    (r).v[0] = t_.x; (r).v[1] = t_.y; (r).v[2] = t_.z; (r).v[3] = t_.w; \
+  }
+#else
+#define SN_LD4_CG(p, r) \
+  { (r).v[0] = (p)[0]; (r).v[1] = (p)[1]; (r).v[2] = (p)[2]; (r).v[3] = (p)[3]; }
+#endif
+
+SN_HD size_t sn_lstm_seq_smem_floats(int H) { return (size_t)SN_PU * H * 4 + (size_t)32 * (H + 4); }
+
+SN_HD void sn_lstm_seq_load_w(const float* whh_t4, float* wsm, int H, int bx, int tx, int ntx) {
+  for (int i = tx; i < SN_PU * H; i += ntx) {
+    const int u = i / H, k = i % H;
+    sn_stv4(wsm + (size_t)i * 4, sn_ld4(whh_t4 + ((size_t)k * H + (size_t)bx * SN_PU + u) * 4));
+  }
+}
+
+// hs[r][:] = hseq[t - 1][b0 + r][:] for r < nb, read through L2 (written by other blocks in the previous step)
+SN_HD void sn_lstm_seq_stage(const float* hseq, float* hs, int t, int b0, int nb, int B, int H, int tx, int ntx) {
+  const int h4 = H / 4;
+  const float* src = hseq + ((size_t)(t - 1) * B + b0) * H;
+  for (int i = tx; i < nb * h4; i += ntx) {
+    const int r = i / h4, k4 = i % h4;
+    sn_f4 v;
+    SN_LD4_CG(src + (size_t)r * H + k4 * 4, v);
+    sn_stv4(hs + (size_t)r * (H + 4) + k4 * 4, v);
+  }
+}
+
+SN_HD void sn_lstm_seq_compute(const float* xg, const float* wsm, const float* hs, float* hseq, float* c, int t, int b0, int nb, int B,
+                               int H, int bx, int tx) {
+  const int u = tx >> 5, lane = tx & 31;
+  const int j = bx * SN_PU + u;
+  if (lane >= nb || j >= H) return;
+  const int b = b0 + lane;
+  const sn_f4 g = sn_ld4(xg + (((size_t)t * B + b) * H + j) * 4);
+  float acc[4] = {g.v[0], g.v[1], g.v[2], g.v[3]};
+  if (t > 0) {
+    const float* hr = hs + (size_t)lane * (H + 4);
+    const float* wu = wsm + (size_t)u * H * 4;
+    for (int k = 0; k < H; k += 4) {
+      const sn_f4 hv = sn_ldv4(hr + k);            // conflict-free: rows are H + 4 floats apart
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const sn_f4 w4 = sn_ldv4(wu + (size_t)(k + kk) * 4);   // same address for the whole warp: a broadcast
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = fmaf(hv.v[kk], w4.v[q], acc[q]);
+      }
+    }
+  }
+  const size_t o = (size_t)b * H + j;
+  const float cp = t > 0 ? c[o] : 0.f;
+  const float cn = sn_sigmoid(acc[1]) * cp + sn_sigmoid(acc[0]) * tanhf(acc[2]);
+  c[o] = cn;
+  hseq[((size_t)t * B) * H + o] = sn_sigmoid(acc[3]) * tanhf(cn);
 }

@@ -8,6 +8,8 @@
 // prompt_tts_b200/ builds, loads or calls it, and the product raises when libpt_seanet.so or a GPU is missing.
 //
 // Build: g++ -O2 -fPIC -shared -o oracle/_build/libseanet_emul.so tests/seanet_emul.cpp   (oracle/Makefile)
+#include <vector>
+
 #include "../prompt_tts_b200/csrc/seanet/seanet_core.h"
 
 template <typename F>
@@ -47,6 +49,40 @@ void emu_sn_linear_rows(const float* a, const float* wt, const float* bias, floa
 }
 void emu_sn_lstm_step(const float* xg, const float* whh_t4, float* hseq, float* c, int t, int B, int H) {
   walk(sn_lstm_step_grid(B, H), [&](int bx, int by, int, int tx) { sn_lstm_step_thread(xg, whh_t4, hseq, c, t, B, H, bx, by, tx, SN_THREADS); });
+}
+
+void emu_sn_pack_conv_weight(const float* w, float* wp, int Co, int Ci, int K, int Cop, int transposed) {
+  walk(sn_linear_grid_1d((long long)Ci * K * Cop),
+       [&](int bx, int, int, int tx) { sn_pack_conv_weight_thread(w, wp, Co, Ci, K, Cop, transposed, bx, tx, SN_THREADS); });
+}
+void emu_sn_conv1d_packed(const pt_sn_conv_t* p) {
+  if (sn_conv1d_packed_ct(*p) == 16)
+    walk(sn_conv1d_packed_grid<16>(*p), [&](int bx, int by, int bz, int tx) { sn_conv1d_packed_thread<16>(*p, bx, by, bz, tx, SN_THREADS); });
+  else
+    walk(sn_conv1d_packed_grid<8>(*p), [&](int bx, int by, int bz, int tx) { sn_conv1d_packed_thread<8>(*p, bx, by, bz, tx, SN_THREADS); });
+}
+void emu_sn_conv_transpose1d_packed(const pt_sn_conv_t* p) {
+  walk(sn_convtr_packed_grid(*p), [&](int bx, int by, int bz, int tx) { sn_convtr_packed_thread(*p, bx, by, bz, tx, SN_THREADS); });
+}
+// the cooperative kernel sn_lstm_seq_kernel of seanet.cu with its barriers turned into loop boundaries: per step every block
+// stages + computes (blocks of one step are independent), "shared memory" is a per-block host array that lives across steps
+void emu_sn_lstm_seq(const float* xg, const float* whh_t4, float* hseq, float* c, int T, int B, int H) {
+  const int blocks = H / SN_PU, ntx = 32 * SN_PU;
+  const size_t per_block = sn_lstm_seq_smem_floats(H);
+  std::vector<float> smem(per_block * blocks, NAN);
+  for (int bx = 0; bx < blocks; ++bx)
+    for (int tx = 0; tx < ntx; ++tx) sn_lstm_seq_load_w(whh_t4, smem.data() + per_block * bx, H, bx, tx, ntx);
+  for (int t = 0; t < T; ++t)
+    for (int bx = 0; bx < blocks; ++bx) {
+      float* wsm = smem.data() + per_block * bx;
+      float* hs = wsm + (size_t)SN_PU * H * 4;
+      for (int b0 = 0; b0 < B; b0 += 32) {
+        const int nb = B - b0 < 32 ? B - b0 : 32;
+        if (t > 0)
+          for (int tx = 0; tx < ntx; ++tx) sn_lstm_seq_stage(hseq, hs, t, b0, nb, B, H, tx, ntx);
+        for (int tx = 0; tx < ntx; ++tx) sn_lstm_seq_compute(xg, wsm, hs, hseq, c, t, b0, nb, B, H, bx, tx);
+      }
+    }
 }
 
 }  // extern "C"

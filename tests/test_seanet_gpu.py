@@ -7,6 +7,7 @@ import ctypes as C
 
 import numpy as np
 import pytest
+import torch
 
 pytestmark = pytest.mark.gpu
 
@@ -62,6 +63,16 @@ def test_conv1d_kernel(drv, case):
     drv.call("conv1d", C.addressof(d))
     assert rel(y.cpu().numpy(), ref + res) < 1e-5
     assert rel(ye.cpu().numpy(), so.elu(ref + res)) < 1e-5
+    # packed weights: 8 / 16 output channels per thread; same products in the same order -> identical bits
+    for cop in sorted({codec.SeanetStack.co_pad(Co), -(-Co // 8) * 8}):
+        wp = drv.empty(Ci, K, cop).fill_(float("nan"))
+        drv.call("pack_conv_weight", wd.data_ptr(), wp.data_ptr(), Co, Ci, K, cop, 0)
+        y3, ye3 = drv.empty(B, Co, Lout).fill_(float("nan")), drv.empty(B, Co, Lout).fill_(float("nan"))
+        d = codec.ConvDesc(xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), rd.data_ptr(), y3.data_ptr(), ye3.data_ptr(),
+                           B, Ci, Co, L, Lout, K, stride, dil, left, 1 if reflect else 0, cop)
+        drv.call("conv1d_packed", C.addressof(d))
+        assert rel(y3.cpu().numpy(), ref + res) < 1e-5
+        assert torch.equal(y3, y) and torch.equal(ye3, ye), cop
 
 
 CONVTR_CASES = [
@@ -93,6 +104,15 @@ def test_conv_transpose_kernel(drv, case):
     drv.call("conv_transpose1d", C.addressof(d))
     assert rel(y.cpu().numpy(), ref) < 1e-5
     assert rel(ye.cpu().numpy(), so.elu(ref)) < 1e-5
+    cop = codec.SeanetStack.co_pad(Co)
+    wp = drv.empty(Ci, K, cop).fill_(float("nan"))
+    drv.call("pack_conv_weight", wd.data_ptr(), wp.data_ptr(), Co, Ci, K, cop, 1)
+    y3, ye3 = drv.empty(*ref.shape).fill_(float("nan")), drv.empty(*ref.shape).fill_(float("nan"))
+    d = codec.ConvDesc(xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), 0, y3.data_ptr(), ye3.data_ptr(),
+                       B, Ci, Co, L, ref.shape[-1], K, stride, 1, left, 0, cop)
+    drv.call("conv_transpose1d_packed", C.addressof(d))
+    assert rel(y3.cpu().numpy(), ref) < 1e-5
+    assert torch.equal(y3, y) and torch.equal(ye3, ye)
 
 
 def test_bad_arguments_raise(drv):
@@ -108,21 +128,64 @@ def test_bad_arguments_raise(drv):
         drv.call("linear_rows", x.data_ptr(), w.data_ptr(), 0, y.data_ptr(), 1, 3, 4)
 
 
+@pytest.mark.parametrize("B,H,T", [(1, 16, 9), (3, 64, 21), (37, 32, 5), (32, 512, 12), (2, 1024, 3)])
+def test_lstm_whole_sequence_equals_steps_and_oracle(drv, B, H, T):
+    """pt_sn_lstm_seq (one cooperative launch, grid barrier per step) against T launches of pt_sn_lstm_step and the oracle's
+    explicit loop; H = 1024 needs 256 co-resident blocks, which a B200 does not have: the -3 fallback is exercised."""
+    import seanet_oracle as so
+    from prompt_tts_b200 import codec
+    cfg = dict(so.CFG_TINY)
+    rng = np.random.default_rng(B * 100 + H)
+    prefix = "encoder.layers.13"
+    P = {}
+    for l in range(2):
+        for n, shape in (("weight_ih", (4 * H, H)), ("weight_hh", (4 * H, H)), ("bias_ih", (4 * H,)), ("bias_hh", (4 * H,))):
+            P[f"{prefix}.lstm.{n}_l{l}"] = (rng.uniform(-1, 1, shape) / np.sqrt(H) * 2).astype(np.float32)
+    x = rng.standard_normal((B, H, T)).astype(np.float32)
+    ref = so.lstm(x, P, prefix, 2)
+    st = codec.SeanetStack(cfg, "encoder", drv)
+    for l in range(2):
+        for n in ("weight_ih", "weight_hh"):
+            t4 = drv.empty(H, H, 4)
+            drv.call("lstm_pack", _dev(drv, P[f"{prefix}.lstm.{n}_l{l}"]).data_ptr(), t4.data_ptr(), H)
+            st.w[f"{prefix}.{n}_l{l}"] = t4
+        b4 = drv.empty(H, 4)
+        drv.call("lstm_pack_bias", _dev(drv, P[f"{prefix}.lstm.bias_ih_l{l}"]).data_ptr(), _dev(drv, P[f"{prefix}.lstm.bias_hh_l{l}"]).data_ptr(),
+                 b4.data_ptr(), H)
+        st.w[f"{prefix}.bias_l{l}"] = b4
+    xd = _dev(drv, x)
+    lib = codec.seanet_lib()
+    outs = {}
+    for whole in (True, False):
+        st.lstm_whole = whole
+        n0 = lib.pt_sn_launch_count()
+        y, ye = st._lstm(prefix, xd, B, H, T, True, True)
+        torch.cuda.synchronize()
+        launches = lib.pt_sn_launch_count() - n0
+        # transposes (2) + input projections (2) + either one launch per layer or one per step and layer
+        assert launches == 4 + (2 if whole and H <= 512 else 2 * T), (whole, launches)
+        assert rel(y.cpu().numpy(), ref) < 1e-5
+        assert rel(ye.cpu().numpy(), so.elu(ref)) < 1e-5
+        outs[whole] = y
+    assert torch.equal(outs[True], outs[False])
+
+
+@pytest.mark.parametrize("fast", [True, False])
 @pytest.mark.parametrize("name,S,B", [("tiny", 3203, 3), ("tiny_noshortcut", 2900, 1), ("tiny_noncausal", 3333, 2), ("k24", 3040, 2)])
-def test_stacks_match_oracle(drv, name, S, B):
+def test_stacks_match_oracle(drv, name, S, B, fast):
     import seanet_oracle as so
     from prompt_tts_b200 import codec
     cfg = {"tiny": so.CFG_TINY, "k24": so.CFG_24KHZ, "tiny_noshortcut": dict(so.CFG_TINY, use_conv_shortcut=False),
            "tiny_noncausal": dict(so.CFG_TINY, use_causal_conv=False)}[name]
     P = so.make_weights(cfg, 11)
     x = (np.random.default_rng(2).standard_normal((B, 1, S)) * 0.3).astype(np.float32)
-    enc = codec.SeanetStack(cfg, "encoder", drv)
+    enc = codec.SeanetStack(cfg, "encoder", drv, fast=fast)
     enc.prepare({k: drv.upload(P[k]) for k in enc.param_names()})
     lat, T = enc.forward(_dev(drv, x), B, S)
     lat_ref = so.encoder(x, P, cfg)
     assert tuple(lat.shape) == lat_ref.shape and T == lat_ref.shape[-1]
     assert rel(lat.cpu().numpy(), lat_ref) < TOL
-    dec = codec.SeanetStack(cfg, "decoder", drv)
+    dec = codec.SeanetStack(cfg, "decoder", drv, fast=fast)
     dec.prepare({k: drv.upload(P[k]) for k in dec.param_names()})
     wav, L = dec.forward(_dev(drv, lat_ref), B, T)
     wav_ref = so.decoder(lat_ref, P, cfg)

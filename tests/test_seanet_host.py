@@ -129,8 +129,8 @@ def test_header_symbols_exported_and_bound():
     for s in declared:
         assert hasattr(lib, s), s
     assert lib.pt_sn_version() == 1
-    # ctypes mirror of pt_sn_conv_t: six pointers then ten ints
-    assert C.sizeof(codec.ConvDesc) == 6 * 8 + 10 * 4
+    # ctypes mirror of pt_sn_conv_t: six pointers then eleven ints (padded to the pointer alignment)
+    assert C.sizeof(codec.ConvDesc) == 6 * 8 + 12 * 4
     body = re.sub(r"/\*.*?\*/", "", re.search(r"typedef struct \{(.*?)\} pt_sn_conv_t;", hdr, re.S).group(1), flags=re.S)
     names = [n for n in re.findall(r"[A-Za-z_]\w*", body) if n not in ("const", "float", "int")]
     assert names == [f[0] for f in codec.ConvDesc._fields_]
@@ -184,6 +184,17 @@ def test_conv1d_body_matches_oracle(drv, case):
     d = codec.ConvDesc(x.ctypes.data, w.ctypes.data, 0, 0, 0, ye2.ctypes.data, B, Ci, Co, L, Lout, K, stride, dil, left, 1 if reflect else 0)
     drv.call("conv1d", C.addressof(d))
     assert rel(ye2, so.elu(ref - b[None, :, None])) < 2e-6
+    # packed weights (8 or 16 output channels per thread, interior / boundary loops)
+    for cop in sorted({codec.SeanetStack.co_pad(Co), -(-Co // 8) * 8}):
+        wp = drv.empty(Ci, K, cop)
+        drv.call("pack_conv_weight", w.ctypes.data, wp.ctypes.data, Co, Ci, K, cop, 0)
+        assert np.array_equal(wp[:, :, :Co], w.transpose(1, 2, 0)) and not wp[:, :, Co:].any()
+        y3, ye3 = drv.empty(B, Co, Lout), drv.empty(B, Co, Lout)
+        d = codec.ConvDesc(x.ctypes.data, wp.ctypes.data, b.ctypes.data, res.ctypes.data, y3.ctypes.data, ye3.ctypes.data,
+                           B, Ci, Co, L, Lout, K, stride, dil, left, 1 if reflect else 0, cop)
+        drv.call("conv1d_packed", C.addressof(d))
+        assert np.array_equal(y3, y), cop               # same products in the same order as the reference-layout kernel
+        assert np.array_equal(ye3, ye)
 
 
 CONVTR_CASES = [
@@ -215,6 +226,15 @@ def test_conv_transpose_body_matches_oracle(drv, case):
     drv.call("conv_transpose1d", C.addressof(d))
     assert rel(y, ref) < 2e-6
     assert rel(ye, so.elu(ref)) < 2e-6
+    cop = codec.SeanetStack.co_pad(Co)
+    wp = drv.empty(Ci, K, cop)
+    drv.call("pack_conv_weight", w.ctypes.data, wp.ctypes.data, Co, Ci, K, cop, 1)
+    assert np.array_equal(wp[:, :, :Co], w.transpose(0, 2, 1)) and not wp[:, :, Co:].any()
+    y3, ye3 = drv.empty(*ref.shape), drv.empty(*ref.shape)
+    d = codec.ConvDesc(x.ctypes.data, wp.ctypes.data, b.ctypes.data, 0, y3.ctypes.data, ye3.ctypes.data,
+                       B, Ci, Co, L, ref.shape[-1], K, stride, 1, left, 0, cop)
+    drv.call("conv_transpose1d_packed", C.addressof(d))
+    assert np.array_equal(y3, y) and np.array_equal(ye3, ye)
 
 
 def test_weight_norm_and_lstm_packing(drv):
@@ -257,7 +277,7 @@ def test_transposes_and_linear_rows(drv):
         assert rel(o, a.astype(np.float64) @ wt.astype(np.float64) + bias) < 2e-6
 
 
-@pytest.mark.parametrize("B,H,T", [(1, 16, 9), (3, 64, 21), (5, 132, 6)])
+@pytest.mark.parametrize("B,H,T", [(1, 16, 9), (3, 64, 21), (5, 132, 6), (37, 32, 5)])
 def test_lstm_sequencing_matches_oracle(drv, B, H, T):
     cfg = dict(so.CFG_TINY, num_filters=H // 16)
     rng = np.random.default_rng(B * 100 + H)
@@ -277,25 +297,37 @@ def test_lstm_sequencing_matches_oracle(drv, B, H, T):
         b4 = drv.empty(H, 4)
         drv.call("lstm_pack_bias", P[f"{prefix}.lstm.bias_ih_l{l}"].ctypes.data, P[f"{prefix}.lstm.bias_hh_l{l}"].ctypes.data, b4.ctypes.data, H)
         st.w[f"{prefix}.bias_l{l}"] = b4
-    y, ye = st._lstm(prefix, x, B, H, T, True, True)
-    assert rel(y, ref) < 5e-6
-    assert rel(ye, so.elu(ref)) < 5e-6
+    outs = {}
+    for fast in (False, True):
+        st.lstm_whole = fast
+        drv.calls.clear()
+        y, ye = st._lstm(prefix, x, B, H, T, True, True)
+        assert rel(y, ref) < 5e-6
+        assert rel(ye, so.elu(ref)) < 5e-6
+        assert drv.calls.count("lstm_seq") == (2 if fast else 0) and drv.calls.count("lstm_step") == (0 if fast else 2 * T)
+        outs[fast] = y
+    assert np.array_equal(outs[True], outs[False])      # the whole-sequence kernel does the step kernel's arithmetic
 
 
 # ------------------------------------------------------------------------------------------------ whole stacks through the product's sequencing
+@pytest.mark.parametrize("fast", [True, False])
 @pytest.mark.parametrize("name,S,B", [("tiny", 3203, 2), ("tiny_noshortcut", 2900, 1), ("tiny_noncausal", 3333, 1), ("k24", 2881, 1)])
-def test_stacks_match_oracle(drv, name, S, B):
+def test_stacks_match_oracle(drv, name, S, B, fast):
     cfg = {"tiny": so.CFG_TINY, "k24": so.CFG_24KHZ, "tiny_noshortcut": dict(so.CFG_TINY, use_conv_shortcut=False),
            "tiny_noncausal": dict(so.CFG_TINY, use_causal_conv=False)}[name]
     P = so.make_weights(cfg, 11)
     x = (np.random.default_rng(2).standard_normal((B, 1, S)) * 0.3).astype(np.float32)
-    enc = codec.SeanetStack(cfg, "encoder", drv)
+    if name == "k24" and not fast:
+        pytest.skip("the 24 kHz widths run once, on the default path (CPU time)")
+    enc = codec.SeanetStack(cfg, "encoder", drv, fast=fast)
     enc.prepare({k: drv.upload(P[k]) for k in enc.param_names()})
+    drv.calls.clear()
     lat, T = enc.forward(x, B, S)
+    assert ("conv1d_packed" in drv.calls) == fast and ("conv1d" in drv.calls) == (not fast)
     lat_ref = so.encoder(x, P, cfg)
     assert lat.shape == lat_ref.shape and T == lat_ref.shape[-1]
     assert rel(lat, lat_ref) < 2e-5
-    dec = codec.SeanetStack(cfg, "decoder", drv)
+    dec = codec.SeanetStack(cfg, "decoder", drv, fast=fast)
     dec.prepare({k: drv.upload(P[k]) for k in dec.param_names()})
     wav, L = dec.forward(lat_ref, B, T)
     wav_ref = so.decoder(lat_ref, P, cfg)

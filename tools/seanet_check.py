@@ -1,7 +1,7 @@
 """One-process GPU check of the SEANet row: the parity tests of tests/test_seanet_gpu.py, then CUDA-event timings of the
 encoder / decoder stacks at 24 kHz widths.  Writes gpurun_out/seanet/{pytest.log,timing.json} as it goes.
 
-    gpurun --timeout 170 -- 'timeout 160 python tools/seanet_check.py'
+    gpurun --timeout 95 -- 'timeout -s KILL 85 python tools/seanet_check.py'
 """
 import io
 import json
@@ -18,12 +18,30 @@ os.makedirs(OUT, exist_ok=True)
 T0 = time.time()
 
 
-def run_tests():
+def probe_lstm_seq():
+    """The whole-sequence LSTM launch is the one kernel with a grid-wide barrier: run its smallest test in a child process with a
+    short timeout first, so that a hang costs 30 s and the rest of this script still runs (on the per-step LSTM)."""
+    import subprocess
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_seanet_gpu.py"), "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           "-k", "lstm_whole and 3-64-21"]
+    try:
+        r = subprocess.run(cmd, timeout=30, capture_output=True, text=True)
+        ok, tail = r.returncode == 0, (r.stdout + r.stderr)[-1500:]
+    except subprocess.TimeoutExpired:
+        ok, tail = False, "TIMEOUT (30 s): pt_sn_lstm_seq hung"
+    open(os.path.join(OUT, "lstm_seq_probe.log"), "w").write(f"ok={ok}\n{tail}\n")
+    print("lstm_seq probe:", "ok" if ok else "FAILED", tail[-300:])
+    if not ok:
+        os.environ["PT_SN_LSTM_STEPS"] = "1"
+    return ok
+
+
+def run_tests(lstm_ok=True):
     import pytest
     buf = io.StringIO()
     with redirect_stdout(buf), redirect_stderr(buf):
         rc = pytest.main([os.path.join(ROOT, "tests", "test_seanet_gpu.py"), "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout=60",
-                          "-x" if "-x" in sys.argv else "--maxfail=50"])
+                          "-x" if "-x" in sys.argv else "--maxfail=50"] + ([] if lstm_ok else ["-k", "not lstm_whole"]))
     open(os.path.join(OUT, "pytest.log"), "w").write(buf.getvalue())
     print(buf.getvalue()[-3000:])
     return int(rc)
@@ -38,14 +56,15 @@ def timings():
     drv = codec.CudaDriver("cuda:0")
     cfg = so.CFG_24KHZ
     P = so.make_weights(cfg, 1)
-    enc, dec = codec.SeanetStack(cfg, "encoder", drv), codec.SeanetStack(cfg, "decoder", drv)
-    enc.prepare({k: drv.upload(P[k]) for k in enc.param_names()})
-    dec.prepare({k: drv.upload(P[k]) for k in dec.param_names()})
     lib = codec.seanet_lib()
-    for B, secs in ((8, 4), (32, 12)):
-        if time.time() - T0 > 95:
+    res["lstm_whole_sequence"] = os.environ.get("PT_SN_LSTM_STEPS", "0") != "1"
+    for B, secs, fast in ((32, 12, True), (32, 12, False), (8, 4, True)):
+        if time.time() - T0 > 60:
             res[f"B{B}x{secs}s"] = "skipped (time)"
             break
+        enc, dec = codec.SeanetStack(cfg, "encoder", drv, fast=fast), codec.SeanetStack(cfg, "decoder", drv, fast=fast)
+        enc.prepare({k: drv.upload(P[k]) for k in enc.param_names()})
+        dec.prepare({k: drv.upload(P[k]) for k in dec.param_names()})
         S = 24000 * secs
         wav = torch.randn(B, 1, S, device="cuda") * 0.3
         out = {}
@@ -63,7 +82,7 @@ def timings():
             ms = e0.elapsed_time(e1)
             out[name] = {"ms": ms, "launches": int(lib.pt_sn_launch_count() - n0), "audio_s_per_s": B * secs / (ms / 1e3),
                          "finite": bool(torch.isfinite(y).all().item())}
-            res[f"B{B}x{secs}s"] = out
+            res[f"B{B}x{secs}s_{'fast' if fast else 'legacy'}"] = out
             json.dump(res, open(os.path.join(OUT, "timing.json"), "w"), indent=1)
         del wav
         torch.cuda.empty_cache()
@@ -81,13 +100,31 @@ def timings():
     print(json.dumps(res))
 
 
+def extras():
+    """The per-kernel table of the default path, bench.py's codec leg and smoke()'s codec check."""
+    import torch
+    sys.argv = [sys.argv[0], "32", "12", os.path.join(OUT, "layers_fast.json")]
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import seanet_profile
+    seanet_profile.main()
+    import bench
+    line = bench.codec_throughput(torch.device("cuda:0"), torch)
+    json.dump(line, open(os.path.join(OUT, "bench_codec.json"), "w"), indent=1)
+    print(json.dumps(line))
+    import __graft_entry__ as g
+    print("smoke_codec", g.smoke_codec(torch.device("cuda:0")))
+    open(os.path.join(OUT, "smoke_codec.txt"), "w").write("ok\n")
+
+
 if __name__ == "__main__":
-    rc = run_tests()
-    try:
-        timings()
-    except Exception as e:  # noqa: BLE001
-        import traceback
-        traceback.print_exc()
-        open(os.path.join(OUT, "timing_error.txt"), "w").write(traceback.format_exc())
+    lstm_ok = probe_lstm_seq()
+    rc = run_tests(lstm_ok)
+    for stage in (timings, extras):
+        try:
+            stage()
+        except Exception:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            open(os.path.join(OUT, stage.__name__ + "_error.txt"), "w").write(traceback.format_exc())
     print("pytest rc", rc, "elapsed", round(time.time() - T0, 1))
     sys.exit(rc)
