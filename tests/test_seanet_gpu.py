@@ -164,10 +164,12 @@ def test_lstm_whole_sequence_equals_steps_and_oracle(drv, B, H, T):
         launches = lib.pt_sn_launch_count() - n0
         # transposes (2) + input projections (2) + either one launch per layer or one per step and layer
         assert launches == 4 + (2 if whole and H <= 512 else 2 * T), (whole, launches)
-        assert rel(y.cpu().numpy(), ref) < 1e-5
-        assert rel(ye.cpu().numpy(), so.elu(ref)) < 1e-5
-        outs[whole] = y
-    assert torch.equal(outs[True], outs[False])
+        outs[whole] = (y, ye)
+    # the whole-sequence kernel does the step kernel's arithmetic in the step kernel's order: identical bits
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    # against the oracle: the recurrence amplifies the last-bit differences between CUDA's and the host's expf / tanhf
+    assert rel(outs[True][0].cpu().numpy(), ref) < TOL
+    assert rel(outs[True][1].cpu().numpy(), so.elu(ref)) < TOL
 
 
 @pytest.mark.parametrize("fast", [True, False])

@@ -58,7 +58,7 @@ def timings():
     P = so.make_weights(cfg, 1)
     lib = codec.seanet_lib()
     res["lstm_whole_sequence"] = os.environ.get("PT_SN_LSTM_STEPS", "0") != "1"
-    for B, secs, fast in ((32, 12, True), (32, 12, False), (8, 4, True)):
+    for B, secs, fast in ((32, 12, True), (8, 4, True)) if "--quick" in sys.argv else ((32, 12, True), (32, 12, False), (8, 4, True)):
         if time.time() - T0 > 60:
             res[f"B{B}x{secs}s"] = "skipped (time)"
             break
@@ -88,6 +88,8 @@ def timings():
         torch.cuda.empty_cache()
     # CPU comparison: transformers' EncodecModel (the restatement the oracle is pinned to) on the host cores, 1 x 4 s
     try:
+        if "--quick" in sys.argv:
+            raise RuntimeError("skipped (--quick)")
         m = so.to_transformers_model(P, cfg)
         x = torch.randn(1, 1, 24000 * 4) * 0.3
         with torch.no_grad():
@@ -103,7 +105,7 @@ def timings():
 def extras():
     """The per-kernel table of the default path, bench.py's codec leg and smoke()'s codec check."""
     import torch
-    sys.argv = [sys.argv[0], "32", "12", os.path.join(OUT, "layers_fast.json")]
+    sys.argv = [sys.argv[0], "32", "12", os.path.join(OUT, "layers_fast_seq.json")]
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import seanet_profile
     seanet_profile.main()
@@ -117,7 +119,7 @@ def extras():
 
 
 if __name__ == "__main__":
-    lstm_ok = probe_lstm_seq()
+    lstm_ok = True if "--quick" in sys.argv else probe_lstm_seq()      # --quick: no child-process probe of pt_sn_lstm_seq
     rc = run_tests(lstm_ok)
     for stage in (timings, extras):
         try:
