@@ -144,14 +144,19 @@ def test_lstm_whole_sequence_equals_steps_and_oracle(drv, B, H, T):
     x = rng.standard_normal((B, H, T)).astype(np.float32)
     ref = so.lstm(x, P, prefix, 2)
     st = codec.SeanetStack(cfg, "encoder", drv)
+    keep = []           # uploaded operands must outlive the asynchronous pack kernels (a freed block is handed to the next upload)
+
+    def up(a):
+        keep.append(_dev(drv, a))
+        return keep[-1].data_ptr()
+
     for l in range(2):
         for n in ("weight_ih", "weight_hh"):
             t4 = drv.empty(H, H, 4)
-            drv.call("lstm_pack", _dev(drv, P[f"{prefix}.lstm.{n}_l{l}"]).data_ptr(), t4.data_ptr(), H)
+            drv.call("lstm_pack", up(P[f"{prefix}.lstm.{n}_l{l}"]), t4.data_ptr(), H)
             st.w[f"{prefix}.{n}_l{l}"] = t4
         b4 = drv.empty(H, 4)
-        drv.call("lstm_pack_bias", _dev(drv, P[f"{prefix}.lstm.bias_ih_l{l}"]).data_ptr(), _dev(drv, P[f"{prefix}.lstm.bias_hh_l{l}"]).data_ptr(),
-                 b4.data_ptr(), H)
+        drv.call("lstm_pack_bias", up(P[f"{prefix}.lstm.bias_ih_l{l}"]), up(P[f"{prefix}.lstm.bias_hh_l{l}"]), b4.data_ptr(), H)
         st.w[f"{prefix}.bias_l{l}"] = b4
     xd = _dev(drv, x)
     lib = codec.seanet_lib()
