@@ -420,11 +420,8 @@ def run_ours(args):
         return float(tt.item())
 
     rvq = samp = codec_line = None
-    if not args.no_codec:
-        try:      # a side figure must never take the bench line down
-            codec_line = codec_throughput(dev, torch, rank, world, max_over_ranks)
-        except Exception as e:
-            codec_line = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    if not args.no_codec:      # SURVEY 8f row 4; local failures are caught inside, the reductions always run
+        codec_line = codec_throughput(dev, torch, rank, world, max_over_ranks)
     if not args.no_rvq:
         rvq = rvq_throughput(dev, torch, ops, peaks_all.get("hbm_gbs", 6500.0), rank, world, max_over_ranks)
     if not args.no_sampling:
@@ -467,12 +464,8 @@ def run_ours(args):
         os._exit(0)
 
 
-def codec_throughput(dev, torch, rank=0, world=1, max_over_ranks=lambda x: x, B=32, secs=12):
-    """SURVEY 8f row 4: EnCodec 24 kHz on the reference's data-preparation batch -- 32 clips zero-padded to 12 s
-    (generate_code.py:94-96) -> SEANet encoder -> 8-codebook RVQ codes (model.encode, generate_code.py:48), and codes -> embedding sum
-    -> SEANet decoder (model.decode, decode_codec.py:16).  Seeded random weights (no checkpoint offline); every rank runs the same
-    batch shape on its own clips (no collective); seconds of audio of all ranks / the slowest rank's device time.  fp32 on the FMA
-    pipe: 2.98 GFLOP per second of audio and stack against the measured FMA peak (profiles/r02_fp32_fma_peak.json)."""
+def _codec_local(dev, torch, rank, B, secs):
+    """This rank's part of `codec_throughput` (no collectives): (encode seconds, decode seconds, launches, launches, sane)."""
     import numpy as np
     from prompt_tts_b200 import codec
     model = codec.EncodecModel.encodec_model_24khz(pretrained=False, device=dev)
@@ -504,7 +497,27 @@ def codec_throughput(dev, torch, rank=0, world=1, max_over_ranks=lambda x: x, B=
     codes = frames[0][0]
     out, t_dec, l_dec = timed(lambda: model.decode([(codes, None)]))
     ok = tuple(codes.shape) == (B, 8, 75 * secs) and tuple(out.shape) == (B, 1, 24000 * secs) and bool(torch.isfinite(out).all().item())
-    t_enc, t_dec = max_over_ranks(t_enc), max_over_ranks(t_dec)
+    return t_enc, t_dec, l_enc, l_dec, ok
+
+
+def codec_throughput(dev, torch, rank=0, world=1, max_over_ranks=lambda x: x, B=32, secs=12):
+    """SURVEY 8f row 4: EnCodec 24 kHz on the reference's data-preparation batch -- 32 clips zero-padded to 12 s
+    (generate_code.py:94-96) -> SEANet encoder -> 8-codebook RVQ codes (model.encode, generate_code.py:48), and codes -> embedding sum
+    -> SEANet decoder (model.decode, decode_codec.py:16).  Seeded random weights (no checkpoint offline); every rank runs the same
+    batch shape on its own clips (no collective on the data path); seconds of audio of all ranks / the slowest rank's device time.
+    fp32 on the FMA pipe: 2.98 GFLOP per second of audio and stack against the measured FMA peak (profiles/r02_fp32_fma_peak.json).
+    A side figure must never take the bench line down: a local failure is reported in the line, and the two max-over-ranks reductions
+    run on every rank whatever happened locally (a rank that skipped them would hang the others)."""
+    local, err = None, None
+    try:
+        local = _codec_local(dev, torch, rank, B, secs)
+    except Exception as e:
+        err = f"{type(e).__name__}: {e}"[:200]
+    t_enc = max_over_ranks(local[0] if local else float("inf"))
+    t_dec = max_over_ranks(local[1] if local else float("inf"))
+    if local is None or t_enc == float("inf") or t_dec == float("inf"):
+        return {"unavailable": err or "failed on another rank"}
+    _, _, l_enc, l_dec, ok = local
     audio = B * secs * world
     fma_peak = 72.5
     try:
