@@ -1,8 +1,9 @@
 // seanet.cu -- libpt_seanet.so: EnCodec SEANet encoder / decoder layers for sm_100a (include/prompt_tts_seanet.h).
 //
 // fp32 on the FMA pipe, the reference's [B, C, T] layout: these stacks feed the RVQ quantiser, whose codes flip on rounding noise, so
-// the first correct path keeps the reference's precision.  The kernel bodies are in seanet_core.h (shared with the host-side
-// index checker of the CPU test tier); this file is the __global__ wrappers, argument validation and launches.
+// this path keeps the reference's precision.  The kernel bodies are in seanet_core.h (shared with the host-side index checker of
+// the CPU test tier); this file is the __global__ wrappers, argument validation and launches.  Default path: packed-weight
+// convolutions + one cooperative launch per LSTM layer; the first-draft kernels stay as A/B partners and as the LSTM fallback.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>

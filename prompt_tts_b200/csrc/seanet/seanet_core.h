@@ -1,8 +1,9 @@
 // seanet_core.h -- the per-thread bodies and launch geometry of the SEANet kernels (libpt_seanet.so).
 //
-// Every kernel of this library is "one thread = one register tile of outputs", with no shared memory and no barriers, so
+// Every kernel of this library but one is "one thread = one register tile of outputs", with no shared memory and no barriers, so
 // a kernel is completely described by  body(params, blockIdx, threadIdx.x, blockDim.x)  plus the grid that covers the problem.
-// Both live here as plain inline functions.  nvcc compiles them as device code (seanet.cu wraps each in a __global__ that
+// Both live here as plain inline functions.  (The exception, the whole-sequence LSTM kernel at the end of this file, is three such
+// bodies separated by barriers.)  nvcc compiles them as device code (seanet.cu wraps each in a __global__ that
 // passes the built-in indices); tests/seanet_emul.cpp compiles THE SAME text with g++ and walks the grid in a host loop, which
 // lets the CPU-only test tier check the index arithmetic (padding, strides, phase decomposition, packing) against the oracle.
 // That host build is a checker of this file, not a code path of the product: nothing under prompt_tts_b200/ loads it.
