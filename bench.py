@@ -524,7 +524,8 @@ def codec_throughput(dev, torch, rank=0, world=1, max_over_ranks=lambda x: x, B=
         fma_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r02_fp32_fma_peak.json")))["fp32_fma_tflops"])
     except Exception:
         pass
-    gflop_per_s_audio = 2.9795
+    from prompt_tts_b200 import codec
+    gflop_per_s_audio = codec.stack_flops(codec.CFG_24KHZ, "encoder", 24000) / 1e9        # 2.98; the decoder's count is the same
     return {"workload": f"{B} clips x {secs} s of 24 kHz audio per GPU (generate_code.py batch), 6 kbps = 8 codebooks, seeded random weights",
             "n_gpus": world, "encode_audio_s_per_s": audio / t_enc, "decode_audio_s_per_s": audio / t_dec,
             "encode_ms": t_enc * 1e3, "decode_ms": t_dec * 1e3, "encode_seanet_launches": l_enc, "decode_seanet_launches": l_dec,

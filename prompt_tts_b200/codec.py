@@ -148,6 +148,26 @@ def layer_plan(cfg) -> Dict[str, list]:
     return {"encoder": enc, "decoder": dec}
 
 
+def stack_flops(cfg, side: str, L: int) -> float:
+    """Algorithmic FLOPs (2 per multiply-add) of one sequence of input length L through a stack: Conv1d 2·Ci·Co·K per output
+    sample, ConvTranspose1d 2·Ci·Co·ceil(K / stride), LSTM 2·(2·H·4H) per step and layer.  24 kHz model: 2.98 GFLOP per second of
+    audio for either stack (encoder: L = samples, decoder: L = frames)."""
+    total = 0.0
+    for _, kind, s in layer_plan(cfg)[side]:
+        if kind == "conv":
+            L = -(-L // s["stride"])
+            total += 2.0 * s["ci"] * s["co"] * s["k"] * L
+        elif kind == "convtr":
+            L = L * s["stride"]
+            total += 2.0 * s["ci"] * s["co"] * -(-s["k"] // s["stride"]) * L
+        elif kind == "res":
+            dim, hid = s["dim"], s["dim"] // cfg["compress"]
+            total += 2.0 * L * (dim * hid * cfg["residual_kernel_size"] + hid * dim + (dim * dim if cfg["use_conv_shortcut"] else 0))
+        else:
+            total += 2.0 * L * cfg["num_lstm_layers"] * 2 * s["dim"] * 4 * s["dim"]
+    return total
+
+
 _G, _V = ".conv.parametrizations.weight.original0", ".conv.parametrizations.weight.original1"
 
 

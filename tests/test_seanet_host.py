@@ -105,6 +105,15 @@ def test_golden_vectors():
         assert rel(wav, g[f"{name}_out"]) < 1e-5
 
 
+def test_algorithmic_flops_per_second_of_audio():
+    """DESIGN.md 3.5 / bench.py's codec roofline: 2.98 GFLOP per second of audio for either stack of the 24 kHz model."""
+    enc = codec.stack_flops(codec.CFG_24KHZ, "encoder", 24000)
+    dec = codec.stack_flops(codec.CFG_24KHZ, "decoder", 75)
+    assert abs(enc / 1e9 - 2.9795) < 1e-3 and abs(dec / 1e9 - 2.9795) < 1e-3
+    # cross-check one layer by hand: the k = 16, stride 8 down-sampling convolution 256 -> 512 at 75 frames/s
+    assert 2 * 256 * 512 * 16 * 75 == 314572800
+
+
 def test_num_quantizers_and_key_dialects():
     assert so.num_quantizers(6.0) == 8 and so.num_quantizers(1.5) == 2 and so.num_quantizers(24.0) == 32
     nk = codec.normalise_key
