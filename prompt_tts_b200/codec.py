@@ -443,6 +443,35 @@ class EncodecModel:
             self.codebooks = torch.stack([self.drv.upload(c) for c in cbs]).contiguous()
             self._prepared_rvq = None
 
+    # ---- nn.Module manners the reference's scripts rely on (generate_code.py:15 `model.to(device)`)
+    def to(self, device=None, *args, **kwargs) -> "EncodecModel":
+        torch = self.drv.torch
+        if device is not None and not isinstance(device, torch.dtype):
+            d = torch.device(device)
+            if d.type != "cuda" or (d.index is not None and self.drv.device.index is not None and d.index != self.drv.device.index):
+                raise PtError(f"EncodecModel lives on {self.drv.device} (its kernels are CUDA-only); host tensors may be passed to "
+                              "encode() / decode() directly")
+        return self
+
+    def cuda(self, device=None) -> "EncodecModel":
+        return self
+
+    def eval(self) -> "EncodecModel":
+        return self
+
+    def train(self, mode: bool = True) -> "EncodecModel":
+        if mode:
+            raise NotImplementedError("the codec is inference-only here (the reference never trains it)")
+        return self
+
+    def _home(self, t, dtype, what: str):
+        """(device copy of `t`, the device `t` came from).  encode() / decode() accept host tensors the way the reference's
+        decode_codec.py passes them: copied in, results copied back -- the arithmetic still only runs on the GPU."""
+        torch = self.drv.torch
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"EncodecModel.{what}: expected a torch.Tensor, got {type(t).__name__}")
+        return t.to(device=self.drv.device, dtype=dtype).contiguous(), t.device
+
     # ---- the two calls of the reference
     def _check_wave(self, x):
         torch = self.drv.torch
@@ -453,7 +482,7 @@ class EncodecModel:
         return x.to(torch.float32).contiguous()
 
     def encode_latents(self, x):
-        """wav [B, 1, S] -> SEANet latents [B, 128, ceil(S / 320)]."""
+        """wav [B, 1, S] -> SEANet latents [B, 128, ceil(S / 320)].  Device tensors only (the layer-level entry point)."""
         x = self._check_wave(x)
         lat, _ = self.encoder.forward(x, x.shape[0], x.shape[2])
         return lat
@@ -463,13 +492,14 @@ class EncodecModel:
         from . import ops
         if self.codebooks is None:
             raise PtError("EncodecModel.encode: no codebooks loaded")
+        x, home = self._home(x, self.drv.torch.float32, "encode")
         lat = self.encode_latents(x)
         nq = self.num_quantizers
         cb = self.codebooks[:nq]
         if self._prepared_rvq is None or self._prepared_rvq[0] != nq:
             self._prepared_rvq = (nq, ops.rvq_prepare(cb) if cb.shape[1] % 128 == 0 and cb.shape[1] <= 1024 and cb.shape[2] == 128 else None)
         codes = ops.rvq_encode(lat, cb, prepared=self._prepared_rvq[1])
-        return [(codes, None)]
+        return [(codes.to(home), None)]
 
     def decode_latents(self, lat):
         torch = self.drv.torch
@@ -489,8 +519,9 @@ class EncodecModel:
             raise NotImplementedError("scaled frames belong to the 48 kHz model (normalize=True)")
         if self.codebooks is None:
             raise PtError("EncodecModel.decode: no codebooks loaded")
-        if not codes.is_cuda:
-            raise PtError("EncodecModel: the codes must be a CUDA tensor (no CPU fallback exists)")
+        codes, home = self._home(codes, self.drv.torch.int64, "decode")
+        if codes.dim() != 3:
+            raise ValueError(f"expected codes [B, n_q, T], got {tuple(codes.shape)}")
         nq = codes.shape[1]
-        lat = ops.rvq_decode(codes.to(self.drv.torch.int64).contiguous(), self.codebooks[:nq].contiguous())
-        return self.decode_latents(lat)
+        lat = ops.rvq_decode(codes, self.codebooks[:nq].contiguous())
+        return self.decode_latents(lat).to(home)

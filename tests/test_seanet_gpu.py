@@ -267,6 +267,12 @@ def test_encodec_model_encode_decode(cuda):
     m2.load_state_dict(old)
     m2.set_target_bandwidth(6.0)
     assert torch.equal(m2.encode(torch.from_numpy(wav).to(cuda))[0][0], codes)
+    # decode_codec.py keeps the codes on the host: host tensors are copied in and the result comes back to the host
+    out_h = model.decode([(codes.cpu(), None)])
+    assert out_h.device.type == "cpu" and torch.equal(out_h, out.cpu())
+    codes_h = model.encode(torch.from_numpy(wav))[0][0]
+    assert codes_h.device.type == "cpu" and torch.equal(codes_h, codes.cpu())
     from prompt_tts_b200._lib import PtError
     with pytest.raises(PtError):
-        model.encode(torch.from_numpy(wav))              # CPU tensor: no fallback
+        model.encode_latents(torch.from_numpy(wav))      # the layer-level entry points take device tensors only
+    assert model.to("cuda") is model and model.eval() is model      # generate_code.py:15
