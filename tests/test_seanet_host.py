@@ -65,7 +65,12 @@ def rel(a, b):
 # ------------------------------------------------------------------------------------------------ oracle pinning
 def test_oracle_matches_transformers_tiny_and_24khz():
     import torch
-    for cfg, S in ((so.CFG_TINY, 3203), (so.CFG_24KHZ, 3520)):
+    variants = ((so.CFG_TINY, 3203), (so.CFG_24KHZ, 3520),
+                (dict(so.CFG_TINY, use_causal_conv=False), 3333),           # the asymmetric padding of ME:159-163 / ME:203-204
+                (dict(so.CFG_TINY, use_conv_shortcut=False), 2900),         # encodec's true_skip
+                (dict(so.CFG_TINY, pad_mode="constant"), 3001),
+                (dict(so.CFG_TINY, num_residual_layers=2, dilation_growth_rate=3), 3200))
+    for cfg, S in variants:
         P = so.make_weights(cfg, 3)
         m = so.to_transformers_model(P, cfg)
         x = (np.random.default_rng(5).standard_normal((2, 1, S)) * 0.3).astype(np.float32)
@@ -320,10 +325,12 @@ def test_lstm_sequencing_matches_oracle(drv, B, H, T):
 
 # ------------------------------------------------------------------------------------------------ whole stacks through the product's sequencing
 @pytest.mark.parametrize("fast", [True, False])
-@pytest.mark.parametrize("name,S,B", [("tiny", 3203, 2), ("tiny_noshortcut", 2900, 1), ("tiny_noncausal", 3333, 1), ("k24", 2881, 1)])
+@pytest.mark.parametrize("name,S,B", [("tiny", 3203, 2), ("tiny_noshortcut", 2900, 1), ("tiny_noncausal", 3333, 1), ("tiny_res2_zero", 3200, 1),
+                                      ("k24", 2881, 1)])
 def test_stacks_match_oracle(drv, name, S, B, fast):
     cfg = {"tiny": so.CFG_TINY, "k24": so.CFG_24KHZ, "tiny_noshortcut": dict(so.CFG_TINY, use_conv_shortcut=False),
-           "tiny_noncausal": dict(so.CFG_TINY, use_causal_conv=False)}[name]
+           "tiny_noncausal": dict(so.CFG_TINY, use_causal_conv=False),
+           "tiny_res2_zero": dict(so.CFG_TINY, num_residual_layers=2, dilation_growth_rate=3, pad_mode="constant")}[name]
     P = so.make_weights(cfg, 11)
     x = (np.random.default_rng(2).standard_normal((B, 1, S)) * 0.3).astype(np.float32)
     if name == "k24" and not fast:
