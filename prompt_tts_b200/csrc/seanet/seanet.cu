@@ -110,6 +110,10 @@ int check_conv_common(const pt_sn_conv_t* p, const char* what) {
     return fail(-1, "%s: bad sizes B=%d Ci=%d Co=%d Lin=%d Lout=%d K=%d stride=%d dil=%d pad_left=%d", what, p->B, p->Ci, p->Co, p->Lin,
                 p->Lout, p->K, p->stride, p->dil, p->pad_left);
   if (p->B > 65535) return fail(-1, "%s: B=%d exceeds the grid's z extent", what, p->B);
+  // sample positions are 32-bit in the kernels: (Lout + one block tile) * stride + K * dil must fit
+  const long long reach = ((long long)p->Lout + SN_THREADS * SN_TT) * p->stride + (long long)p->K * p->dil + p->pad_left;
+  if (reach > 0x7fffffffLL || (long long)p->Lin > 0x7fffffffLL - SN_THREADS * SN_TT)
+    return fail(-1, "%s: sequence too long for 32-bit sample positions (Lin=%d Lout=%d stride=%d)", what, p->Lin, p->Lout, p->stride);
   return 0;
 }
 

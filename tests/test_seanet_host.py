@@ -150,6 +150,38 @@ def test_header_symbols_exported_and_bound():
     assert names == [f[0] for f in codec.ConvDesc._fields_]
 
 
+def test_argument_validation_needs_no_gpu():
+    """Every entry point validates before it touches the CUDA runtime: bad descriptors return -1 with a message (no launch is
+    attempted, so this runs in the CPU tier)."""
+    if not os.path.exists(codec.SEANET_LIB_PATH):
+        pytest.skip("libpt_seanet.so not built")
+    lib = codec.seanet_lib()
+    buf = np.zeros(64, np.float32)
+    p = buf.ctypes.data
+
+    def conv(**kw):
+        f = dict(x=p, w=p, bias=0, res=0, y=p, y_elu=0, B=1, Ci=1, Co=1, Lin=16, Lout=16, K=3, stride=1, dil=1, pad_left=2, reflect=1, Co_pad=8)
+        f.update(kw)
+        return codec.ConvDesc(**f)
+
+    cases = [("conv1d", conv(y=0), "neither y nor y_elu"), ("conv1d", conv(x=0), "x and w must be set"), ("conv1d", conv(K=0), "bad sizes"),
+             ("conv1d", conv(Lin=2, pad_left=2), "shorter than its reflect padding"),
+             ("conv1d", conv(Lout=2**31 - 8, stride=8, reflect=0), "too long"),
+             ("conv1d_packed", conv(Co=9, Co_pad=8), "Co_pad"), ("conv1d_packed", conv(Co_pad=12), "Co_pad"),
+             ("conv_transpose1d", conv(dil=2), "dilation"), ("conv_transpose1d", conv(Lout=64, pad_left=0), "exceeds the full output length"),
+             ("conv_transpose1d_packed", conv(Co_pad=4), "Co_pad")]
+    for name, d, msg in cases:
+        rc = getattr(lib, "pt_sn_" + name)(C.addressof(d), None)
+        assert rc == -1 and msg in lib.pt_sn_last_error().decode(), (name, msg, rc, lib.pt_sn_last_error())
+    assert lib.pt_sn_linear_rows(p, p, 0, p, 1, 3, 4, None) == -1 and b"multiples of 4" in lib.pt_sn_last_error()
+    assert lib.pt_sn_linear_rows(p + 4, p, 0, p, 1, 4, 4, None) == -1 and b"aligned" in lib.pt_sn_last_error()
+    assert lib.pt_sn_lstm_step(p, p, p, p, 0, 1, 6, None) == -1 and b"multiple of 4" in lib.pt_sn_last_error()
+    assert lib.pt_sn_lstm_seq(p, p, p, p, 0, 1, 8, None) == -1
+    assert lib.pt_sn_pack_conv_weight(p, p, 9, 1, 1, 8, 0, None) == -1
+    assert lib.pt_sn_weight_norm_fold(p, p, p, 0, 4, None) == -1
+    assert lib.pt_sn_launch_count() == 0
+
+
 def test_product_raises_without_gpu():
     import torch
     if torch.cuda.is_available():
