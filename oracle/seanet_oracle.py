@@ -214,7 +214,7 @@ def lstm(x: np.ndarray, P, prefix: str, layers: int) -> np.ndarray:
         for t in range(T):
             g = xg[t] + h @ whh.T
             i_, f_, g_, o_ = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
-            sig = lambda a: (1.0 / (1.0 + np.exp(-a))).astype(np.float32)
+            sig = lambda a: (1.0 / (1.0 + np.exp(-np.maximum(a, -80.0)))).astype(np.float32)     # exp(80) is finite in fp32
             c = sig(f_) * c + sig(i_) * np.tanh(g_)
             h = (sig(o_) * np.tanh(c)).astype(np.float32)
             out[t] = h

@@ -30,9 +30,9 @@ class TimingDriver(codec.CudaDriver):
         if not self.on:
             return super().call(name, *args)
         key, flops = name, 0.0
-        if name in ("conv1d", "conv_transpose1d"):
+        if name in ("conv1d", "conv_transpose1d", "conv1d_packed", "conv_transpose1d_packed"):
             d = C.cast(args[0], C.POINTER(codec.ConvDesc)).contents
-            taps = d.K if name == "conv1d" else -(-d.K // d.stride)
+            taps = d.K if name.startswith("conv1d") else -(-d.K // d.stride)
             flops = 2.0 * d.B * d.Ci * d.Co * taps * d.Lout
             key = f"{name} {d.Ci}->{d.Co} k{d.K} s{d.stride} d{d.dil} L{d.Lout}"
         elif name == "linear_rows":
@@ -43,6 +43,10 @@ class TimingDriver(codec.CudaDriver):
             B, H = args[5], args[6]
             flops = 2.0 * B * H * 4 * H
             key = f"{name} B{B} H{H}"
+        elif name == "lstm_seq":
+            T, B, H = args[4], args[5], args[6]
+            flops = 2.0 * T * B * H * 4 * H
+            key = f"{name} T{T} B{B} H{H}"
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         super().call(name, *args)
