@@ -466,18 +466,9 @@ def run_ours(args):
 
 def _codec_local(dev, torch, rank, B, secs):
     """This rank's part of `codec_throughput` (no collectives): (encode seconds, decode seconds, launches, launches, sane)."""
-    import numpy as np
     from prompt_tts_b200 import codec
-    model = codec.EncodecModel.encodec_model_24khz(pretrained=False, device=dev)
-    rng = np.random.default_rng(0)
-    sd = {}
-    for name, shape in {**model.encoder.param_shapes(), **model.decoder.param_shapes()}.items():
-        fan = float(np.prod(shape[1:])) if len(shape) > 1 else 1.0
-        sd[name] = torch.ones(shape) if name.endswith("original0") else \
-            torch.from_numpy((rng.standard_normal(shape) / np.sqrt(fan)).astype(np.float32))
-    for q in range(model.cfg["num_codebooks"]):
-        sd[f"quantizer.layers.{q}.codebook.embed"] = torch.from_numpy(rng.standard_normal((1024, 128)).astype(np.float32))
-    model.load_state_dict(sd)
+    model = codec.EncodecModel(codec.CFG_24KHZ, dev)
+    model.load_state_dict(codec.random_state_dict(model.cfg, seed=0))     # what encodec_model_24khz(pretrained=False) holds; own generator
     model.set_target_bandwidth(6.0)
     wav = torch.randn(B, 1, 24000 * secs, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)) * 0.3
     lib = codec.seanet_lib()

@@ -378,6 +378,36 @@ class SeanetStack:
         return x, L
 
 
+def random_state_dict(cfg, seed: Optional[int] = None):
+    """The tensors a freshly constructed (not pretrained) EnCodec holds, as `encodec_model_24khz(pretrained=False)` returns it in
+    the reference's package: PyTorch's default initialisation -- Conv / ConvTranspose v ~ U(+-1/sqrt(fan_in)) with weight-norm
+    g = |v| (so the effective weight is v), biases and LSTM tensors U(+-1/sqrt(fan_in or H)), codebooks U(+-sqrt(3 / dim)).
+    Host tensors from torch's CPU generator (the global one, or a fresh one seeded with `seed`)."""
+    import torch
+    gen = None if seed is None else torch.Generator().manual_seed(int(seed))
+
+    def uniform(shape, bound):
+        return (torch.rand(shape, generator=gen) * 2 - 1) * bound
+
+    sd = {}
+    shapes = {}
+    for side in ("encoder", "decoder"):
+        shapes.update(SeanetStack(cfg, side, None, fast=True).param_shapes())
+    for name, shape in shapes.items():
+        if name.endswith(_V):
+            bound = 1.0 / math.sqrt(shape[1] * shape[2])
+            v = uniform(shape, bound)
+            sd[name] = v
+            sd[name[:-len(_V)] + _G] = v.flatten(1).norm(dim=1).reshape(-1, 1, 1)
+            sd[name[:-len(_V)] + ".conv.bias"] = uniform(shapes[name[:-len(_V)] + ".conv.bias"], bound)
+        elif ".lstm." in name:
+            sd[name] = uniform(shape, 1.0 / math.sqrt(shape[-1] if len(shape) == 2 else shape[0] // 4))
+    dim = cfg["codebook_dim"] if "codebook_dim" in cfg else cfg["hidden_size"]
+    for q in range(cfg.get("num_codebooks", 32)):
+        sd[f"quantizer.layers.{q}.codebook.embed"] = uniform((cfg["codebook_size"], dim), math.sqrt(3.0 / dim))
+    return sd
+
+
 # --------------------------------------------------------------------------------------------------------------- model
 class EncodecModel:
     """Drop-in for the `encodec.EncodecModel` calls of generate_code.py / decode_codec.py (24 kHz, mono, causal, no chunking)."""
@@ -407,6 +437,8 @@ class EncodecModel:
                               "encodec_24khz-d7cc33bc.th>` or `pretrained=False` and call load_state_dict()")
             import torch
             m.load_state_dict(torch.load(path, map_location="cpu"))
+        else:
+            m.load_state_dict(random_state_dict(m.cfg))      # a randomly initialised model, as the reference's constructor gives
         return m
 
     def set_target_bandwidth(self, bandwidth: float) -> None:

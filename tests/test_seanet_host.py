@@ -110,6 +110,21 @@ def test_golden_vectors():
         assert rel(wav, g[f"{name}_out"]) < 1e-5
 
 
+def test_random_state_dict_is_a_fresh_model():
+    """`encodec_model_24khz(pretrained=False)` holds PyTorch-default-initialised tensors of the right shapes; g = |v| makes the folded
+    weight equal v; a seed makes it reproducible."""
+    import torch
+    sd = codec.random_state_dict(codec.CFG_24KHZ, seed=3)
+    assert {k: tuple(v.shape) for k, v in sd.items() if not k.startswith("quantizer")} == so.param_shapes(so.CFG_24KHZ)
+    assert sum(k.startswith("quantizer.layers.") for k in sd) == 32 and tuple(sd["quantizer.layers.31.codebook.embed"].shape) == (1024, 128)
+    k = "decoder.layers.3.conv.parametrizations.weight."
+    v = sd[k + "original1"].numpy()
+    assert np.abs(so.fold_weight_norm(sd[k + "original0"].numpy(), v) - v).max() < 1e-6
+    assert float(sd[k + "original1"].abs().max()) <= 1 / np.sqrt(256 * 16) + 1e-7           # fan_in of ConvTranspose1d(512, 256, 16)
+    again = codec.random_state_dict(codec.CFG_24KHZ, seed=3)
+    assert all(torch.equal(sd[n], again[n]) for n in sd)
+
+
 def test_algorithmic_flops_per_second_of_audio():
     """DESIGN.md 3.5 / bench.py's codec roofline: 2.98 GFLOP per second of audio for either stack of the 24 kHz model."""
     enc = codec.stack_flops(codec.CFG_24KHZ, "encoder", 24000)

@@ -12,7 +12,6 @@ from contextlib import redirect_stderr, redirect_stdout
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 OUT = os.path.join(ROOT, "gpurun_out", "seanet")
 os.makedirs(OUT, exist_ok=True)
 T0 = time.time()
@@ -48,14 +47,12 @@ def run_tests(lstm_ok=True):
 
 
 def timings():
-    import numpy as np
     import torch
-    import seanet_oracle as so
     from prompt_tts_b200 import codec
     res = {"device": torch.cuda.get_device_name(0)}
     drv = codec.CudaDriver("cuda:0")
-    cfg = so.CFG_24KHZ
-    P = so.make_weights(cfg, 1)
+    cfg = codec.CFG_24KHZ
+    P = codec.random_state_dict(cfg, seed=1)
     lib = codec.seanet_lib()
     res["lstm_whole_sequence"] = os.environ.get("PT_SN_LSTM_STEPS", "0") != "1"
     for B, secs, fast in ((32, 12, True), (8, 4, True)) if "--quick" in sys.argv else ((32, 12, True), (32, 12, False), (8, 4, True)):
@@ -90,7 +87,8 @@ def timings():
     try:
         if "--quick" in sys.argv:
             raise RuntimeError("skipped (--quick)")
-        m = so.to_transformers_model(P, cfg)
+        from transformers import EncodecConfig, EncodecModel
+        m = EncodecModel(EncodecConfig()).eval()              # the 24 kHz architecture, random weights: timing only
         x = torch.randn(1, 1, 24000 * 4) * 0.3
         with torch.no_grad():
             t = time.time(); lat = m.encoder(x); te = time.time() - t

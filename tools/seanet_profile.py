@@ -13,7 +13,6 @@ from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 import torch  # noqa: E402
 
@@ -58,10 +57,9 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     secs = int(sys.argv[2]) if len(sys.argv) > 2 else 12
     out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "seanet", "layers.json")
-    import seanet_oracle as so
     cfg = codec.CFG_24KHZ
     drv = TimingDriver()
-    P = so.make_weights(so.CFG_24KHZ, 1)
+    P = codec.random_state_dict(cfg, seed=1)
     enc, dec = codec.SeanetStack(cfg, "encoder", drv), codec.SeanetStack(cfg, "decoder", drv)
     enc.prepare({k: drv.upload(P[k]) for k in enc.param_names()})
     dec.prepare({k: drv.upload(P[k]) for k in dec.param_names()})
