@@ -488,6 +488,8 @@ def _codec_local(dev, torch, rank, B, secs):
     codes = frames[0][0]
     out, t_dec, l_dec = timed(lambda: model.decode([(codes, None)]))
     ok = tuple(codes.shape) == (B, 8, 75 * secs) and tuple(out.shape) == (B, 1, 24000 * secs) and bool(torch.isfinite(out).all().item())
+    del model, wav, out, frames, codes
+    torch.cuda.empty_cache()          # ~8 GB of layer buffers go back before the RVQ / sampling legs
     return t_enc, t_dec, l_enc, l_dec, ok
 
 
