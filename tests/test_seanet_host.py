@@ -397,3 +397,86 @@ def test_stacks_match_oracle(drv, name, S, B, fast):
     assert wav.shape == wav_ref.shape and L == 320 * T
     assert rel(wav, wav_ref) < 2e-5
     assert not np.isnan(wav).any() and not np.isnan(lat).any()
+
+
+# ------------------------------------------------------------------------------------------------ randomised shapes
+def _rand_conv_case(rng):
+    K = int(rng.integers(1, 9))
+    stride = int(rng.integers(1, K + 1))
+    dil = int(rng.integers(1, 4)) if stride == 1 else 1
+    reach = (K - 1) * dil + 1
+    L = int(rng.integers(reach + stride + 1, 700))
+    return dict(B=int(rng.integers(1, 3)), Ci=int(rng.integers(1, 7)), Co=int(rng.integers(1, 20)), L=L, K=K, stride=stride, dil=dil,
+                causal=bool(rng.integers(0, 2)), reflect=bool(rng.integers(0, 2)))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_conv_bodies_random_shapes(drv, seed):
+    """Ragged sizes the fixed cases do not hit: channel counts around the 8 / 16 tile edges, lengths around the 512-sample block
+    tile, strides that do not divide the kernel, dilation with and without reflection."""
+    rng = np.random.default_rng(1000 + seed)
+    c = _rand_conv_case(rng)
+    B, Ci, Co, L, K, stride, dil = c["B"], c["Ci"], c["Co"], c["L"], c["K"], c["stride"], c["dil"]
+    x = rng.standard_normal((B, Ci, L)).astype(np.float32)
+    w = rng.standard_normal((Co, Ci, K)).astype(np.float32)
+    b = rng.standard_normal(Co).astype(np.float32)
+    try:
+        ref = so.conv1d(x, w, b, stride, dil, c["causal"], "reflect" if c["reflect"] else "constant")
+    except ValueError:
+        pytest.skip("input shorter than its reflect padding")
+    left, _ = so.pad_amounts(K, stride, dil, c["causal"])
+    Lout = ref.shape[-1]
+    for cop, name in ((0, "conv1d"), (codec.SeanetStack.co_pad(Co), "conv1d_packed"), (-(-Co // 8) * 8, "conv1d_packed")):
+        wk = w
+        if cop:
+            wk = drv.empty(Ci, K, cop)
+            drv.call("pack_conv_weight", w.ctypes.data, wk.ctypes.data, Co, Ci, K, cop, 0)
+        y = drv.empty(B, Co, Lout)
+        d = codec.ConvDesc(x.ctypes.data, wk.ctypes.data, b.ctypes.data, 0, y.ctypes.data, 0, B, Ci, Co, L, Lout, K, stride, dil, left,
+                           1 if c["reflect"] else 0, cop)
+        drv.call(name, C.addressof(d))
+        assert rel(y, ref) < 3e-6, (c, name, cop)
+    # transposed: the same (K, stride) family, all of K - stride trimmed at the end (causal) or split (non-causal)
+    wt = rng.standard_normal((Ci, Co, K)).astype(np.float32)
+    Lt = int(rng.integers(1, 200))
+    xt = rng.standard_normal((B, Ci, Lt)).astype(np.float32)
+    reft = so.conv_transpose1d(xt, wt, b, stride, c["causal"])
+    total = K - stride
+    tl = 0 if c["causal"] else total - total // 2
+    for cop, name in ((0, "conv_transpose1d"), (codec.SeanetStack.co_pad(Co), "conv_transpose1d_packed")):
+        wk = wt
+        if cop:
+            wk = drv.empty(Ci, K, cop)
+            drv.call("pack_conv_weight", wt.ctypes.data, wk.ctypes.data, Co, Ci, K, cop, 1)
+        y = drv.empty(*reft.shape)
+        d = codec.ConvDesc(xt.ctypes.data, wk.ctypes.data, b.ctypes.data, 0, y.ctypes.data, 0, B, Ci, Co, Lt, reft.shape[-1], K, stride, 1, tl, 0, cop)
+        drv.call(name, C.addressof(d))
+        assert rel(y, reft) < 3e-6, (c, name, cop)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lstm_bodies_random_shapes(drv, seed):
+    """Whole-sequence body == step body bit for bit, for batch sizes around the 32-sequence chunk and widths around the block tile."""
+    rng = np.random.default_rng(2000 + seed)
+    B, H, T = int(rng.integers(1, 70)), 4 * int(rng.integers(1, 40)), int(rng.integers(1, 6))
+    xg = rng.standard_normal((T, B, H, 4)).astype(np.float32)
+    whh = (rng.standard_normal((H, H, 4)) / np.sqrt(H)).astype(np.float32)
+    out = []
+    for whole in (True, False):
+        hseq, c = drv.empty(T, B, H), drv.empty(B, H)
+        if whole:
+            drv.call("lstm_seq", xg.ctypes.data, whh.ctypes.data, hseq.ctypes.data, c.ctypes.data, T, B, H)
+        else:
+            for t in range(T):
+                drv.call("lstm_step", xg.ctypes.data, whh.ctypes.data, hseq.ctypes.data, c.ctypes.data, t, B, H)
+        assert not np.isnan(hseq).any() and not np.isnan(c).any()
+        out.append((hseq, c))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    # and against a plain numpy recurrence on the packed operands: gates = xg[t] + h @ W, order i, f, g, o
+    h, cc = np.zeros((B, H), np.float32), np.zeros((B, H), np.float32)
+    sig = lambda a: 1.0 / (1.0 + np.exp(-a))
+    for t in range(T):
+        g = xg[t].astype(np.float64) + np.einsum("bk,kjq->bjq", h.astype(np.float64), whh.astype(np.float64))
+        cc = sig(g[..., 1]) * cc + sig(g[..., 0]) * np.tanh(g[..., 2])
+        h = sig(g[..., 3]) * np.tanh(cc)
+        assert rel(out[0][0][t], h) < 1e-5
