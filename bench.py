@@ -442,6 +442,11 @@ def run_ours(args):
                 cb["rvq"] = cpu_rvq_baseline()
             except Exception as e:   # a baseline figure must never take the bench line down
                 cb["rvq"] = {"unavailable": str(e)[:120]}
+            if not args.no_codec:
+                try:
+                    cb["codec"] = cpu_codec_baseline()
+                except Exception as e:
+                    cb["codec"] = {"unavailable": str(e)[:120]}
             line["cpu_baseline"] = cb
             try:
                 line["gpu_eager_baseline"] = gpu_eager_baseline(dev)
@@ -555,6 +560,24 @@ def sampling_rtf(model, cfg, dev, torch, peak_tflops, rank=0, world=1, max_over_
             "tflops": flop / sec / 1e12, "frac_of_tensor_roofline": flop / sec / 1e12 / (peak_tflops * world),
             "finite": bool(torch.isfinite(x).all().item()),
             "note": "one complete sample() call after an untimed 4-step call: includes its own eager first step and the capture of the loop"}
+
+
+def cpu_codec_baseline(secs=4):
+    """The codec's CPU path beside `codec_throughput`: transformers' EncodecModel (the installed restatement of encodec 0.1.1, which
+    the reference runs; random weights, 24 kHz architecture) on the host threads torch uses, one clip of `secs` seconds."""
+    import torch
+    from transformers import EncodecConfig, EncodecModel
+    m = EncodecModel(EncodecConfig()).eval()
+    x = torch.randn(1, 1, 24000 * secs) * 0.3
+    with torch.no_grad():
+        m.decoder(m.encoder(x))                                  # warm-up
+        t0 = time.perf_counter()
+        codes = m.quantizer.encode(m.encoder(x), 6.0)            # [8, 1, T]
+        t1 = time.perf_counter()
+        m.decoder(m.quantizer.decode(codes))
+        t2 = time.perf_counter()
+    return {"encode_audio_s_per_s": secs / (t1 - t0), "decode_audio_s_per_s": secs / (t2 - t1), "cores": torch.get_num_threads(),
+            "kind": "reference restatement (transformers.EncodecModel)", "sample": f"1 clip x {secs} s, 6 kbps"}
 
 
 def cpu_rvq_baseline(n_clips=2, T=900):
