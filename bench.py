@@ -10,6 +10,9 @@ one step = add_noise -> forward -> MSE -> backward over a synthetic batch of 32 
 GPU (weak scaling; at N > 1 the step also all-reduces the gradients over NCCL, overlapped with the backward sweep).
 `value` = frames/s with the batch resident in HBM; `e2e` = the same step through the public API with the batch in pinned
 host memory (H2D copies and the loss read-back inside the timed region).
+Side objects in the same line (none of them part of `value`): `train_step_full` (+ clip + AdamW), `sampling` (100 DDPM steps), `rvq`
+(quantise / embedding sum of the data-preparation set), `codec` (EnCodec SEANet encode / decode of the reference's 32 x 12 s batch,
+fp32, against the FMA roof), `cpu_baseline` / `gpu_eager_baseline` (the reference's path on the box's host cores / eager PyTorch).
 """
 from __future__ import annotations
 
