@@ -276,3 +276,41 @@ def test_encodec_model_encode_decode(cuda):
     with pytest.raises(PtError):
         model.encode_latents(torch.from_numpy(wav))      # the layer-level entry points take device tensors only
     assert model.to("cuda") is model and model.eval() is model      # generate_code.py:15
+
+
+def test_full_batch_properties(cuda):
+    """The reference's data-preparation batch (32 clips x 12 s, generate_code.py:94-96) is too large for the numpy oracle; at that
+    size the path is checked through properties that hold bit for bit: clips are independent (a sub-batch gives the same codes and
+    latents), the 24 kHz model is causal (samples from s0 on change no latent frame before s0 / 320 and, in the decoder, frames from
+    f0 on change no sample before 320 f0), and decode(encode(x)) has the input's length."""
+    import os
+    import torch
+    from prompt_tts_b200 import codec
+    B, secs = (int(v) for v in os.environ.get("PT_SN_TEST_FULL", "32,12").split(","))
+    model = codec.EncodecModel(codec.CFG_24KHZ, cuda)
+    model.load_state_dict(codec.random_state_dict(model.cfg, seed=4))
+    model.set_target_bandwidth(6.0)
+    S = 24000 * secs
+    g = torch.Generator().manual_seed(0)
+    wav = (torch.randn(B, 1, S, generator=g) * 0.3).to(cuda)
+    lat = model.encode_latents(wav)
+    codes = model.encode(wav)[0][0]
+    assert tuple(lat.shape) == (B, 128, 75 * secs) and tuple(codes.shape) == (B, 8, 75 * secs)
+    assert bool(torch.isfinite(lat).all()) and int(codes.min()) >= 0 and int(codes.max()) < 1024
+    # independence of the clips
+    lo, hi = B // 3, B // 3 + max(1, B // 4)
+    assert torch.equal(model.encode_latents(wav[lo:hi].contiguous()), lat[lo:hi])
+    assert torch.equal(model.encode(wav[lo:hi].contiguous())[0][0], codes[lo:hi])
+    # causality of the encoder
+    f0 = (75 * secs) // 2
+    wav2 = wav.clone()
+    wav2[:, :, 320 * f0:] += 0.1 * torch.randn(B, 1, S - 320 * f0, generator=g).to(cuda)
+    lat2 = model.encode_latents(wav2)
+    assert torch.equal(lat2[:, :, :f0], lat[:, :, :f0]) and not torch.equal(lat2[:, :, f0:], lat[:, :, f0:])
+    # decoder: length, finiteness, causality
+    out = model.decode([(codes, None)])
+    assert tuple(out.shape) == (B, 1, S) and bool(torch.isfinite(out).all())
+    codes2 = codes.clone()
+    codes2[:, :, f0:] = (codes2[:, :, f0:] + 1) % 1024
+    out2 = model.decode([(codes2, None)])
+    assert torch.equal(out2[:, :, :320 * f0], out[:, :, :320 * f0]) and not torch.equal(out2[:, :, 320 * f0:], out[:, :, 320 * f0:])
