@@ -480,3 +480,21 @@ def test_lstm_bodies_random_shapes(drv, seed):
         cc = sig(g[..., 1]) * cc + sig(g[..., 0]) * np.tanh(g[..., 2])
         h = sig(g[..., 3]) * np.tanh(cc)
         assert rel(out[0][0][t], h) < 1e-5
+
+
+def test_encodec_dialect_round_trip_for_every_tensor():
+    """Every tensor name of the 24 kHz model, written the way encodec 0.1.1 names it (`model.N`, `conv.conv` / `convtr.convtr`,
+    `weight_g` / `weight_v`, `vq.layers.N._codebook`), maps back onto the name this package stores."""
+    plan = codec.layer_plan(codec.CFG_24KHZ)
+    transposed = {f"{side}.layers.{i}" for side, p in plan.items() for i, kind, _ in p if kind == "convtr"}
+    names = list(so.param_shapes(so.CFG_24KHZ)) + [f"quantizer.layers.{q}.codebook.embed" for q in range(32)]
+    for n in names:
+        old = n
+        if n.startswith(("encoder.", "decoder.")):
+            old = n.replace(".layers.", ".model.", 1)
+            inner = "convtr.convtr" if n.split(".conv.")[0] in transposed else "conv.conv"
+            old = old.replace(".conv.parametrizations.weight.original0", f".{inner}.weight_g").replace(
+                ".conv.parametrizations.weight.original1", f".{inner}.weight_v").replace(".conv.bias", f".{inner}.bias")
+        else:
+            old = n.replace("quantizer.layers.", "quantizer.vq.layers.").replace(".codebook.embed", "._codebook.embed")
+        assert old != n and codec.normalise_key(old) == n, (n, old, codec.normalise_key(old))
