@@ -71,10 +71,10 @@ def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "prompt_tts_b200")
     for dp, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh")):
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 code = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith(("//", "#", "*", "/*")))
-                assert not re.search(r"(import|from|include|dlopen|CDLL)[^\n]*(ref_model|rvq_oracle|oracle[/.])", code), f
+                assert not re.search(r"(import|from|include|dlopen|CDLL)[^\n]*(ref_model|rvq_oracle|seanet_oracle|seanet_emul|oracle[/.])", code), f
 
 
 def test_gradsync_gloo_world2():
@@ -138,6 +138,40 @@ dist.destroy_process_group()
 print("OK", rank)
 ''' % ROOT
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o[-2000:]
+
+
+def test_codec_leg_collectives_gloo_world2():
+    """bench.py's codec leg with two CPU ranks over gloo and a stubbed local measurement: the two max-over-ranks reductions run on
+    every rank whatever happened locally -- a rank whose kernels failed must not leave the other one waiting in an all-reduce --
+    and the line carries the slowest rank's time."""
+    code = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import bench
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", rank=rank, world_size=2)
+def mx(x):
+    t = torch.tensor([x], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+bench._codec_local = lambda dev, torch_, rank_, B, secs: (0.10 + 0.05 * rank_, 0.20 - 0.05 * rank_, 24, 24, True)
+line = bench.codec_throughput("cpu", torch, rank, 2, mx)
+assert abs(line["encode_ms"] - 150.0) < 1e-6 and abs(line["decode_ms"] - 200.0) < 1e-6 and line["n_gpus"] == 2, line
+assert abs(line["encode_audio_s_per_s"] - 2 * 32 * 12 / 0.15) < 1e-6
+assert abs(line["roofline"]["peak_tflops"] / 2 - 72.49) < 0.5
+def boom(*a):
+    if a[2] == 1: raise RuntimeError("kernel failed on this rank")
+    return (0.1, 0.2, 24, 24, True)
+bench._codec_local = boom
+line = bench.codec_throughput("cpu", torch, rank, 2, mx)
+assert "unavailable" in line and (("kernel failed" in line["unavailable"]) == (rank == 1)), line
+dist.destroy_process_group()
+print("OK", rank)
+''' % ROOT
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     procs = [subprocess.Popen([sys.executable, "-c", code], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
